@@ -283,9 +283,16 @@ struct orc {
 	int64_t cur_pos;
 	int tap_mask;
 	long inverted;
-	vec frames, records, blocks, tap[3];
+	vec frames, records, blocks, tap[3], tap_ch[3];
 	int16_t dbuf[2 * DEC_PER_BLOCK];
 };
+
+static void tap_put(orc_t *o, const chan *c, int kind, const void *v)
+{
+	uint8_t k = (uint8_t)c->kind;
+	vec_push(&o->tap[kind], v);
+	vec_push(&o->tap_ch[kind], &k);
+}
 
 static orc_frame *emit_frame(orc_t *o, chan *c, int status, int rssi, int offset, int byte_cnt)
 {
@@ -400,7 +407,7 @@ static int tfa1_sample(orc_t *o, chan *c, int thresh, int pwr, int index, const 
 		triggered = 1;
 		int dev = orc_fm_dev_nrzs(iq[0], iq[1], c->last_i, c->last_q);
 		if (o->tap_mask & 2)
-			vec_push(&o->tap[1], &dev);
+			tap_put(o, c, 1, &dev);
 		if (dev > c->mark_lvl)
 			c->mark_lvl = dev;
 		else
@@ -595,10 +602,10 @@ static int tfa2_sample(orc_t *o, chan *c, int thresh, int pwr, int index, const 
 		triggered = 1;
 		int dev = orc_fm_dev(iq[0], iq[1], c->last_i, c->last_q);
 		if (o->tap_mask & 1)
-			vec_push(&o->tap[0], &dev);
+			tap_put(o, c, 0, &dev);
 		double y = biquad_step(&c->lp, dev);
 		if (o->tap_mask & 4)
-			vec_push(&o->tap[2], &y);
+			tap_put(o, c, 2, &y);
 		int ld = (int)y;
 		if (c->bitcnt < 10) {
 			if (ld > c->dmax)
@@ -880,15 +887,15 @@ static int whb_sample(orc_t *o, chan *c, int thresh, int pwr, const int16_t *iq)
 		triggered = 1;
 		int dev = orc_fm_dev_nrzs(iq[0], iq[1], c->last_i, c->last_q);
 		if (o->tap_mask & 2)
-			vec_push(&o->tap[1], &dev);
+			tap_put(o, c, 1, &dev);
 		double y = biquad_step(&c->lp, dev);
 		if (o->tap_mask & 4)
-			vec_push(&o->tap[2], &y);
+			tap_put(o, c, 2, &y);
 		dev = (int)y;
 		if (!c->synced) {
 			double a = biquad_step(&c->lp_avg, 0.5 * dev);
 			if (o->tap_mask & 4)
-				vec_push(&o->tap[2], &a);
+				tap_put(o, c, 2, &a);
 			c->avg_of = (int)a;
 		}
 		c->timeout_cnt--;
@@ -965,6 +972,7 @@ orc_t *orc_create(int types, int filter, int thresh)
 	o->blocks.esz = sizeof(orc_block_trace);
 	o->tap[0].esz = o->tap[1].esz = sizeof(int32_t);
 	o->tap[2].esz = sizeof(double);
+	o->tap_ch[0].esz = o->tap_ch[1].esz = o->tap_ch[2].esz = 1;
 	return o;
 }
 void orc_destroy(orc_t *o)
@@ -976,8 +984,10 @@ void orc_destroy(orc_t *o)
 	free(o->frames.p);
 	free(o->records.p);
 	free(o->blocks.p);
-	for (int k = 0; k < 3; k++)
+	for (int k = 0; k < 3; k++) {
 		free(o->tap[k].p);
+		free(o->tap_ch[k].p);
+	}
 	free(o);
 }
 void orc_set_taps(orc_t *o, int mask) { o->tap_mask = mask; }
@@ -1041,12 +1051,14 @@ size_t orc_n_blocks(const orc_t *o) { return o->blocks.n; }
 const orc_block_trace *orc_blocks(const orc_t *o) { return (const orc_block_trace *)o->blocks.p; }
 size_t orc_n_tap(const orc_t *o, int kind) { return (kind >= 0 && kind < 3) ? o->tap[kind].n : 0; }
 const void *orc_tap(const orc_t *o, int kind) { return (kind >= 0 && kind < 3) ? o->tap[kind].p : NULL; }
+const uint8_t *orc_tap_chan(const orc_t *o, int kind) { return (kind >= 0 && kind < 3) ? (const uint8_t *)o->tap_ch[kind].p : NULL; }
 int orc_thresh(const orc_t *o) { return o->thresh; }
 long orc_inverted_syncs(const orc_t *o) { return o->inverted; }
 void orc_clear_results(orc_t *o)
 {
 	o->frames.n = o->records.n = o->blocks.n = 0;
 	o->tap[0].n = o->tap[1].n = o->tap[2].n = 0;
+	o->tap_ch[0].n = o->tap_ch[1].n = o->tap_ch[2].n = 0;
 }
 
 /* main.cpp:45-50 (-X): decoder::store_bytes (decoder.cpp:35-40) then flush(0) */

@@ -63,6 +63,8 @@ def lib():
         L.orc_n_tap.argtypes = [C.c_void_p, C.c_int]
         L.orc_tap.restype = C.c_void_p
         L.orc_tap.argtypes = [C.c_void_p, C.c_int]
+        L.orc_tap_chan.restype = C.c_void_p
+        L.orc_tap_chan.argtypes = [C.c_void_p, C.c_int]
         L.orc_decimate.restype = C.c_size_t
         L.orc_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.orc_fm_dev.argtypes = [C.c_int] * 4
@@ -136,6 +138,13 @@ class Oracle:
             return np.zeros(0, dtype=np.float64 if kind == 2 else np.int32)
         ct = C.c_double if kind == 2 else C.c_int32
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,)).copy()
+
+    def tap_chan(self, kind):
+        n = self.L.orc_n_tap(self.h, kind)
+        p = self.L.orc_tap_chan(self.h, kind)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).copy()
 
     def thresh(self):
         return self.L.orc_thresh(self.h)

@@ -1,0 +1,69 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/tfr.h declares; argument
+validation and the no-CPU-fallback rule work without a GPU (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import tfrec_b200 as tb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tfrec_b200 import build
+    build.build()
+    return tb.load()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "tfr.h")).read()
+    declared = set(re.findall(r"\b(tfr_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(tb.ABI_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_abi_version(lib):
+    assert lib.tfr_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # sizes the C side static_asserts / memcpy's against
+    assert C.sizeof(tb.Config) == 40
+    assert C.sizeof(tb.Frame) == 112
+    assert C.sizeof(tb.Record) == 72
+    assert C.sizeof(tb.BlockTrace) == 12
+    assert C.sizeof(tb.Stats) == 72
+
+
+def test_create_validates_arguments(lib):
+    h = C.c_void_p()
+    cfg = tb.Config(0, 0, 7, 0, 0, 1, 0, 0, 0)       # wrong struct_size
+    assert lib.tfr_create(C.byref(cfg), C.byref(h)) == -1
+    assert b"struct_size" in lib.tfr_last_error()
+    cfg = tb.Config(C.sizeof(tb.Config), 0, 7, 0, 0, 0, 0, 0, 0)   # n_streams = 0
+    assert lib.tfr_create(C.byref(cfg), C.byref(h)) == -1
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    cfg = tb.Config(C.sizeof(tb.Config), 0, 7, 0, 0, 1, 0, 0, 0)
+    rc = lib.tfr_create(C.byref(cfg), C.byref(h))
+    assert rc == -2 and not h.value     # TFR_E_NODEVICE
+    with pytest.raises(tb.TfrError):
+        tb.Receiver()
+
+
+def test_product_does_not_touch_the_oracle():
+    # the product path must never import, link or execute anything under oracle/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tfrec_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "oracle_lib" not in txt and "tfrec_oracle" not in txt, f

@@ -1,0 +1,451 @@
+// frontend.cu - raw u8 IQ -> exact two-stage FIR decimate /4 -> power trigger -> sparse window store.
+//
+// Replaces, bit-exactly, the per-block work of engine.cpp:77-78 ((u8-128)<<6), downconvert::process_iq
+// (dsp_stuff.cpp:243-264: process2x1 8 taps, then process2x 20 taps, each tap floored separately with
+// (x*tap)>>16, dsp_stuff.cpp:194-195,222-223) and the pwr=|I|+|Q| trigger test of fm_demod.cpp:45.
+//
+// One CTA = one reference block (65536 B -> 8192 decimated samples).  128 threads, each owns 512
+// consecutive raw bytes (64 outputs).  The block's bytes arrive by TMA bulk copies (one 512-byte row
+// per thread, rows padded to 528 B so that the 128-bit shared loads of a warp are conflict free)
+// signalled on one mbarrier.  Arithmetic: every tap product is ONE round-toward-minus-infinity FMA on
+// an accumulator kept inside [2^23, 2^24), where the fp32 grid is exactly the integers, so that
+//     fma.rm(x, tap/2^16, acc) == acc + floor(x*tap / 2^16)           (exact, no separate floor)
+// and I/Q share taps, so both channels ride in one fma.rm.f32x2 (SASS FFMA2.RM).  The offsets that
+// keep the accumulators inside the binade are integer multiples of the tap denominators and are
+// removed once, in integer arithmetic, when the accumulator bits are read back (see constants below).
+//
+// Output: decimated int16 I,Q are written ONLY where a demodulator can be active: [trigger,
+// trigger+t_max) for every sample with pwr > thresh_lo, plus the first t_max samples of every block
+// (they may be covered by a trigger in the previous block) and the block's last sample (lead-in for
+// the next block).  A TileDesc per block lists the segments.  The sparse buffer is direct mapped
+// (sample m of block b lives at dec[b*8192+m]) so the back-end addresses by position.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "tfr_dev.h"
+
+namespace tfr {
+
+// ------------------------------------------------------------------------------------------------
+// tap tables (dsp_stuff.cpp:61-88 narrow, :91-117 wide, :119-130 first stage)
+// ------------------------------------------------------------------------------------------------
+#define TFR_T2 { 2443, 6339, 11036, 14254, 14254, 11036, 6339, 2443 }
+#define TFR_T1N { -1087, -1082, -1065, -451, 912, 2997, 5556, 8157, 10285, 11484, 11484, 10285, 8157, 5556, 2997, 912, -451, -1065, -1082, -1087 }
+#define TFR_T1W { 546, 451, -317, -1844, -3198, -2817, 494, 6469, 13074, 17421, 17421, 13074, 6469, 494, -2817, -3198, -1844, -317, 451, 546 }
+
+__host__ __device__ constexpr int t2_tap(int n) { constexpr int t[8] = TFR_T2; return t[n]; }
+__host__ __device__ constexpr int t1_tap(bool wide, int n)
+{
+	constexpr int tn[20] = TFR_T1N;
+	constexpr int tw[20] = TFR_T1W;
+	return wide ? tw[n] : tn[n];
+}
+__host__ __device__ constexpr int t2_sum() { int s = 0; for (int n = 0; n < 8; n++) s += t2_tap(n); return s; }
+__host__ __device__ constexpr int t1_sum(bool wide, int lo, int hi) { int s = 0; for (int n = lo; n < hi; n++) s += t1_tap(wide, n); return s; }
+
+// ------------------------------------------------------------------------------------------------
+// exact-floor accumulator bookkeeping
+// ------------------------------------------------------------------------------------------------
+// byte b -> float z = 33664 + b, built by integer ops in the [32768,65536) binade (ulp 1/256): bits =
+// 0x47038000 + (b << 8).  z = 33*1024 + (b-128), so with c1 = t2/1024 every stage-1 FMA adds
+// floor((b-128)*t2/1024) + 33*t2 : the wanted floor((x*t2)>>16 for x=(b-128)<<6) plus an integer.
+constexpr uint32_t kCvtBase = 0x47038000u;
+constexpr int kCvtMul = 33;
+// stage-1 accumulator: starts at kA1, ends at kM1 + y1 with kM1 a multiple of 65536 so that the
+// offset it injects into stage 2, kM1*t1/65536 = 163*t1, is again an integer.
+constexpr int kM1Mul = 163;
+constexpr int kM1 = kM1Mul * 65536;                       // 10,682,368
+constexpr int kA1 = kM1 - kCvtMul * t2_sum();             //  8,433,616  (>= 2^23 + 8520)
+static_assert(kA1 - 8520 >= (1 << 23) && kM1 + 8520 < (1 << 24), "stage-1 accumulator leaves the integer binade");
+// stage 2 runs as two 10-tap chains (taps 0..9 and 10..19) so that each chain's offset fits the binade
+constexpr int kA2a = (1 << 23) + 1300000;
+constexpr int kA2b = (1 << 23) + 100000;
+
+__host__ __device__ constexpr bool chain_in_range(bool wide, int lo, int hi, int start)
+{
+	int s = start;
+	for (int n = lo; n < hi; n++) {
+		s += kM1Mul * t1_tap(wide, n);
+		if (s - 13000 < (1 << 23) || s + 13000 >= (1 << 24)) return false;
+	}
+	return true;
+}
+static_assert(chain_in_range(false, 0, 10, kA2a) && chain_in_range(false, 10, 20, kA2b), "narrow stage-2 chain range");
+static_assert(chain_in_range(true, 0, 10, kA2a) && chain_in_range(true, 10, 20, kA2b), "wide stage-2 chain range");
+
+// y2 = (bitsA - 0x4B000000 + 2^23 - kA2a - offA) + (same for B) with off = 163*sum(taps of the chain)
+__host__ __device__ constexpr uint32_t y2_bias(bool wide)
+{
+	return 2u * (0x4B000000u - (1u << 23)) + (uint32_t)kA2a + (uint32_t)kA2b +
+	       (uint32_t)(kM1Mul * t1_sum(wide, 0, 10)) + (uint32_t)(kM1Mul * t1_sum(wide, 10, 20));
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f2;  // packed f32x2: lo = I, hi = Q
+
+__device__ __forceinline__ f2 pack2(float lo, float hi)
+{
+	f2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, uint32_t &lo, uint32_t &hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2_rm(f2 a, f2 b, f2 c)
+{
+	f2 d;
+	asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+		     "l"(src), "r"(bytes), "r"(bar)
+		     : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared memory layout
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 128;
+constexpr int kRowBytes = 512;               // raw bytes per thread
+constexpr int kRowStride = 528;              // +16: 33 x 16 B, odd -> conflict-free LDS.128 across a quarter warp
+constexpr int kOutPerThread = 64;
+constexpr int kRow0 = 128;                   // byte offset of row 0; the 96 halo bytes sit at [16,112)
+constexpr int kHaloOff = 16;
+constexpr int kSmemBytes = kRow0 + kThreads * kRowStride;  // 67,712 B -> 3 CTAs / SM
+
+// two bytes (I,Q) of a raw sample -> packed floats 33664+b
+__device__ __forceinline__ f2 cvt_iq(uint32_t w, int half)
+{
+	uint32_t bi = __byte_perm(w, 0, half ? 0x4424 : 0x4404) + kCvtBase;
+	uint32_t bq = __byte_perm(w, 0, half ? 0x4434 : 0x4414) + kCvtBase;
+	return pack2(__uint_as_float(bi), __uint_as_float(bq));
+}
+
+template <bool WIDE>
+__device__ __forceinline__ f2 c2pair(int n)
+{
+	float c = (float)t1_tap(WIDE, n) * (1.0f / 65536.0f);
+	return pack2(c, c);
+}
+__device__ __forceinline__ f2 c1pair(int n)
+{
+	float c = (float)t2_tap(n) * (1.0f / 1024.0f);
+	return pack2(c, c);
+}
+
+// stage 1: one 8-tap output from 8 consecutive converted raw samples
+__device__ __forceinline__ f2 stage1(const f2 *x)
+{
+	f2 acc = pack2((float)kA1, (float)kA1);
+#pragma unroll
+	for (int n = 0; n < 8; n++) acc = fma2_rm(x[n], c1pair(n), acc);
+	return acc;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ int s_first[kThreads];   // first trigger (0..63) in the thread's 64 outputs, -1 if none
+	__shared__ int s_last[kThreads];
+	__shared__ int s_seg_start[kMaxSeg + 4], s_seg_end[kMaxSeg + 4];
+	__shared__ int s_nseg, s_ntrig;
+
+	const int tid = threadIdx.x;
+	const int stream = blockIdx.y;
+	const StreamJob job = p.jobs[stream];
+	const int tile = p.tile0 + blockIdx.x;            // block index inside the submit
+	if (tile >= (int)job.n_blocks) return;
+	StreamState *st = p.st + stream;
+
+	const uint32_t bar = smem_u32(smem);
+	const uint8_t *src = job.iq + (size_t)tile * kBlockBytes;
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		s_ntrig = 0;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		mbar_expect_tx(bar, kBlockBytes + kHistBytes);
+		const uint8_t *hsrc = (tile == 0) ? st->hist[st->hist_parity & 1] : src - kHistBytes;
+		tma_bulk_g2s(smem_u32(smem + kHaloOff), hsrc, kHistBytes, bar);
+	}
+	tma_bulk_g2s(smem_u32(smem + kRow0 + tid * kRowStride), src + tid * kRowBytes, kRowBytes, bar);
+
+	int thresh_lo = st->thresh;
+	if (st->thresh_mode) thresh_lo -= 2 * ((p.epoch_blocks + 3) / 4);
+
+	mbar_wait(bar, 0);
+
+	// ------------------------------------------------------------------ per-thread FIR cascade
+	uint8_t *row = smem + kRow0 + tid * kRowStride;
+	const uint4 *halo = reinterpret_cast<const uint4 *>(row - 16 - kHistBytes);  // 48 raw samples before the row
+
+	f2 ring[32];   // stage-1 outputs (kM1 + y1), slot = index mod 32
+	f2 xh[6];      // last 6 converted raw samples
+
+	{
+		// prologue: y1[-18..-1] from raw x[-42..-1]; halo holds x[-48..-1]
+		f2 hx[48];
+#pragma unroll
+		for (int q = 0; q < 6; q++) {
+			uint4 v = halo[q];
+			hx[8 * q + 0] = cvt_iq(v.x, 0); hx[8 * q + 1] = cvt_iq(v.x, 1);
+			hx[8 * q + 2] = cvt_iq(v.y, 0); hx[8 * q + 3] = cvt_iq(v.y, 1);
+			hx[8 * q + 4] = cvt_iq(v.z, 0); hx[8 * q + 5] = cvt_iq(v.z, 1);
+			hx[8 * q + 6] = cvt_iq(v.w, 0); hx[8 * q + 7] = cvt_iq(v.w, 1);
+		}
+		// y1[j] (j=-18..-1) needs x[2j-6 .. 2j+1]; hx[k] = x[k-48]  ->  hx[2j+42 .. 2j+49]
+#pragma unroll
+		for (int j = -18; j < 0; j++) ring[(j + 32) & 31] = stage1(&hx[2 * j + 42]);
+#pragma unroll
+		for (int k = 0; k < 6; k++) xh[k] = hx[42 + k];
+	}
+
+	uint32_t trig[2] = { 0u, 0u };
+	const uint4 *rowv = reinterpret_cast<const uint4 *>(row);
+	uint32_t *outw = reinterpret_cast<uint32_t *>(row);   // outputs overwrite the front of the own row
+
+#pragma unroll 1
+	for (int it = 0; it < 4; it++) {
+#pragma unroll
+		for (int s = 0; s < 8; s++) {
+			const uint4 v = rowv[it * 8 + s];
+			f2 x[14];
+#pragma unroll
+			for (int k = 0; k < 6; k++) x[k] = xh[k];
+			x[6] = cvt_iq(v.x, 0); x[7] = cvt_iq(v.x, 1);
+			x[8] = cvt_iq(v.y, 0); x[9] = cvt_iq(v.y, 1);
+			x[10] = cvt_iq(v.z, 0); x[11] = cvt_iq(v.z, 1);
+			x[12] = cvt_iq(v.w, 0); x[13] = cvt_iq(v.w, 1);
+			// four stage-1 outputs j = 4s..4s+3 (relative to the iteration), y1[j] needs x[2(j-4s) .. +7] of this window
+#pragma unroll
+			for (int jj = 0; jj < 4; jj++) ring[(4 * s + jj) & 31] = stage1(&x[2 * jj]);
+#pragma unroll
+			for (int k = 0; k < 6; k++) xh[k] = x[8 + k];
+			// two stage-2 outputs m = 2s, 2s+1: y1 indices 2m-18 .. 2m+1
+			uint32_t o[2];
+#pragma unroll
+			for (int mm = 0; mm < 2; mm++) {
+				const int m = 2 * s + mm;
+				f2 a = pack2((float)kA2a, (float)kA2a), b = pack2((float)kA2b, (float)kA2b);
+#pragma unroll
+				for (int n = 0; n < 10; n++) {
+					a = fma2_rm(ring[(2 * m - 18 + n + 32) & 31], c2pair<WIDE>(n), a);
+					b = fma2_rm(ring[(2 * m - 8 + n + 32) & 31], c2pair<WIDE>(n + 10), b);
+				}
+				uint32_t ai, aq, bi, bq;
+				unpack2(a, ai, aq);
+				unpack2(b, bi, bq);
+				const int yi = (int)(ai + bi - y2_bias(WIDE));
+				const int yq = (int)(aq + bq - y2_bias(WIDE));
+				const int pwr = abs(yi) + abs(yq);
+				const int idx = it * 16 + m;
+				if (pwr > thresh_lo) trig[idx >> 5] |= 1u << (idx & 31);
+				o[mm] = __byte_perm((uint32_t)yi, (uint32_t)yq, 0x5410);
+			}
+			*reinterpret_cast<uint2 *>(outw + it * 16 + 2 * s) = make_uint2(o[0], o[1]);
+		}
+	}
+
+	// ------------------------------------------------------------------ block-level trigger bookkeeping
+	{
+		int f = -1, l = -1;
+		if (trig[0]) f = __ffs(trig[0]) - 1;
+		else if (trig[1]) f = 32 + __ffs(trig[1]) - 1;
+		if (trig[1]) l = 63 - __clz(trig[1]);
+		else if (trig[0]) l = 31 - __clz(trig[0]);
+		s_first[tid] = (f < 0) ? -1 : tid * kOutPerThread + f;
+		s_last[tid] = (l < 0) ? -1 : tid * kOutPerThread + l;
+		const int nt = __popc(trig[0]) + __popc(trig[1]);
+		if (nt) atomicAdd(&s_ntrig, nt);
+	}
+	__syncthreads();
+
+	// warp 0: merge the per-thread trigger extents into covered segments [start, end)
+	if (tid < 32) {
+		// each lane scans 4 consecutive threads; a segment can only begin at a thread's first trigger
+		// because t_max (>= 356) exceeds the 64 samples a thread owns
+		int lastq = -1;          // last trigger seen before this lane's group (filled by the scan below)
+		int grp_last = -1;
+#pragma unroll
+		for (int k = 0; k < 4; k++) grp_last = max(grp_last, s_last[tid * 4 + k]);
+		// inclusive prefix max over lanes, then shift to exclusive
+		int pm = grp_last;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			int o = __shfl_up_sync(0xffffffffu, pm, d);
+			if (tid >= d) pm = max(pm, o);
+		}
+		lastq = __shfl_up_sync(0xffffffffu, pm, 1);
+		if (tid == 0) lastq = -1;
+		// walk the 4 threads of the group, emitting (start) markers and tracking chain ends
+		int starts[4];
+		int q = lastq;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int f = s_first[tid * 4 + k], l = s_last[tid * 4 + k];
+			starts[k] = -1;
+			if (f >= 0) {
+				if (q < 0 || f - q > p.t_max) starts[k] = f;
+				q = l;
+			}
+		}
+		// number the starts across the warp
+		int cnt = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++) cnt += (starts[k] >= 0);
+		int incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			int o = __shfl_up_sync(0xffffffffu, incl, d);
+			if (tid >= d) incl += o;
+		}
+		int base = incl - cnt;
+		const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (starts[k] >= 0) {
+				if (base < kMaxSeg + 4) s_seg_start[base] = starts[k];
+				base++;
+			}
+		if (tid == 0) s_nseg = min(total, kMaxSeg);
+		__syncwarp();
+		// segment i ends t_max after the last trigger that precedes segment i+1's start
+		const int nseg = min(total, kMaxSeg);
+		const int lastall = __shfl_sync(0xffffffffu, pm, 31);
+		if (tid < nseg) {
+			int endq;
+			if (tid == nseg - 1) {
+				endq = lastall;
+			} else {
+				// last trigger strictly before the next start: scan thread slots backwards from the owner of that start
+				const int nxt = s_seg_start[tid + 1];
+				int t = nxt / kOutPerThread - 1;
+				while (t >= 0 && s_last[t] < 0) t--;
+				endq = (t >= 0) ? s_last[t] : -1;
+			}
+			s_seg_end[tid] = endq + p.t_max;   // exclusive; may exceed the block -> carry_out
+		}
+	}
+	__syncthreads();
+
+	// ------------------------------------------------------------------ sparse store + descriptor
+	const size_t gtile = (size_t)job.dec_off + tile;
+	uint32_t *dst = p.dec + gtile * kBlockDec;
+	const int nseg = s_nseg;
+	auto sample = [&](int m) -> uint32_t {
+		return *reinterpret_cast<const uint32_t *>(smem + kRow0 + (m >> 6) * kRowStride + (m & 63) * 4);
+	};
+	if (p.keep_all) {
+		for (int m = tid; m < kBlockDec; m += kThreads) dst[m] = sample(m);
+	} else {
+		// head [0, t_max) and the last sample are always kept (needed when the previous block's trigger
+		// reaches into this one, and as the next block's lead-in sample)
+		int covered = min(p.t_max, kBlockDec);
+		for (int m = tid; m < covered; m += kThreads) dst[m] = sample(m);
+		if (tid == 0) dst[kBlockDec - 1] = sample(kBlockDec - 1);
+		for (int sgi = 0; sgi < nseg; sgi++) {
+			const int s0 = max(max(s_seg_start[sgi] - 1, covered), 0);   // one lead-in sample
+			const int e0 = min(s_seg_end[sgi], kBlockDec);
+			for (int m = s0 + tid; m < e0; m += kThreads) dst[m] = sample(m);
+			covered = max(covered, e0);
+		}
+	}
+	if (tid < kMaxSeg) {
+		TileDesc *td = p.tiles + gtile;
+		const bool on = tid < nseg;
+		const int s0 = on ? s_seg_start[tid] : 0;
+		const int e0 = on ? min(s_seg_end[tid], kBlockDec) : 0;
+		td->seg_start[tid] = (uint16_t)s0;
+		td->seg_len[tid] = (uint16_t)(e0 - s0);
+		if (tid == 0) {
+			td->n_seg = (uint16_t)nseg;
+			const int over = nseg ? s_seg_end[nseg - 1] - kBlockDec : 0;
+			td->carry_out = (uint16_t)max(over, 0);
+			td->n_trig = (uint32_t)s_ntrig;
+			td->pad = 0;
+		}
+	}
+}
+
+// after the last epoch of a submit: remember the FIR history for the next submit (other parity)
+__global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int n_streams)
+{
+	const int stream = blockIdx.x;
+	if (stream >= n_streams) return;
+	const StreamJob job = jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *s = st + stream;
+	const int par = (s->hist_parity & 1) ^ 1;
+	const uint8_t *src = job.iq + (size_t)job.n_blocks * kBlockBytes - kHistBytes;
+	if (threadIdx.x < kHistBytes) s->hist[par][threadIdx.x] = src[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x == 0) s->hist_parity = par;
+}
+
+cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaStream_t stream)
+{
+	// the opt-in shared-memory size is a per-device function attribute: set it on every device we meet
+	static bool attr_done[64] = { false };
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 64 && !attr_done[dev]) {
+		e = cudaFuncSetAttribute(frontend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(frontend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (e != cudaSuccess) return e;
+		attr_done[dev] = true;
+	}
+	if (p.n_tiles <= 0 || n_streams <= 0) return cudaSuccess;
+	if (getenv("TFR_DEBUG"))
+		fprintf(stderr, "[tfr] frontend grid=(%d,%d) tile0=%d t_max=%d keep_all=%d wide=%d smem=%d\n", p.n_tiles, n_streams,
+			p.tile0, p.t_max, p.keep_all, wide, kSmemBytes);
+	dim3 grid(p.n_tiles, n_streams);
+	if (wide)
+		frontend_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
+	else
+		frontend_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream)
+{
+	save_history_kernel<<<n_streams, 128, 0, stream>>>(jobs, st, n_streams);
+	return cudaGetLastError();
+}
+
+}  // namespace tfr

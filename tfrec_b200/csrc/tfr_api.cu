@@ -1,0 +1,756 @@
+// tfr_api.cu - the C ABI declared in include/tfr.h: handle management, the submit/process/poll pump
+// that stands in for the loop body of engine::run (engine.cpp:63-93), and the host-side finalisation
+// of results (ordering, 10*log10 RSSI with the host libm, sensordata_t mirror).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tfr.h"
+#include "tfr_dev.h"
+
+namespace tfr {
+cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaStream_t stream);
+cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream);
+cudaError_t launch_thresh(const BackParams &p, cudaStream_t s);
+cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
+cudaError_t launch_parse(const BackParams &p, cudaStream_t s);
+}  // namespace tfr
+
+using namespace tfr;
+
+static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 72,
+	      "public struct layout changed: bump TFR_ABI_VERSION");
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+	g_err = msg;
+	return code;
+}
+#define CU(call)                                                                                      \
+	do {                                                                                          \
+		cudaError_t e_ = (call);                                                              \
+		if (e_ != cudaSuccess)                                                                \
+			return fail(TFR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+	} while (0)
+
+// iir2 coefficients exactly as the reference binary (x86-64, -ffast-math) computes them in iir2::set
+// (dsp_stuff.cpp:36-45) for the cutoffs main.cpp registers; tests/test_abi.py checks them against the
+// values read out of the reference object (tests/golden/biquad_coeffs.json).
+static BiquadCoef coef_from_bits(const uint64_t b[5])
+{
+	BiquadCoef c;
+	double v[5];
+	memcpy(v, b, sizeof(v));
+	c.b0 = v[0]; c.b1 = v[1]; c.b2 = v[2]; c.a1 = v[3]; c.a2 = v[4];
+	return c;
+}
+static const uint64_t kCoefTfa2[5] = { 0x3f727f98b1037a14ull, 0x3f827f98b1037a14ull, 0x3f727f98b1037a14ull, 0x3ffcd1527f4a26e2ull, 0xbfea36a1c41c6995ull };
+static const uint64_t kCoefTfa3[5] = { 0x3f57ed02b18a270dull, 0x3f67ed02b18a270dull, 0x3f57ed02b18a270dull, 0x3ffe397ac010fc89ull, 0xbfeca2cf85850d62ull };
+static const uint64_t kCoefTx22[5] = { 0x3f5461fa1a309718ull, 0x3f6461fa1a309718ull, 0x3f5461fa1a309718ull, 0x3ffe5d4f47377e30ull, 0xbfece36282a35d90ull };
+static const uint64_t kCoefWhbPulse[5] = { 0x3f814a67102a1ffdull, 0x3f914a67102a1ffdull, 0x3f814a67102a1ffdull, 0x3ffb949652fa3970ull, 0xbfe83dd316f714e0ull };
+static const uint64_t kCoefWhbAvg[5] = { 0x3e502ae4cfc8910aull, 0x3e602ae4cfc8910aull, 0x3e502ae4cfc8910aull, 0x3ffffe9409fe171bull, 0xbfeffd283451f7d3ull };
+
+struct PendingSubmit {
+	const uint8_t *dev_ptr = nullptr;
+	size_t nbytes = 0;
+	bool pending = false;
+};
+
+struct tfr_handle {
+	tfr_config cfg;
+	DevConfig dcfg;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	// persistent device state
+	DevConfig *d_cfg = nullptr;
+	StreamState *d_state = nullptr;
+	StreamJob *d_jobs = nullptr;
+	Counters *d_counters = nullptr;
+	DevFrame *d_frames = nullptr;
+	DevRecord *d_records = nullptr;
+	uint32_t max_frames = 0, max_records = 0;
+	// per-process work buffers (grown on demand)
+	size_t cap_blocks = 0;
+	TileDesc *d_tiles = nullptr;
+	uint32_t *d_dec = nullptr;
+	BlockTrace *d_trace = nullptr;
+	// input arena for host submits: normally one chunk; more are added when a later submit does not
+	// fit while earlier ones are still pending, and merged into one the next time the arena is idle
+	struct Chunk { uint8_t *ptr; size_t cap, used; };
+	std::vector<Chunk> arena;
+	// taps
+	uint32_t tap_cap = 0;
+	int32_t *d_tap_i32[2] = { nullptr, nullptr };
+	double *d_tap_f64 = nullptr;
+	uint32_t *d_tap_cnt = nullptr;
+	// bookkeeping
+	std::vector<PendingSubmit> pend;
+	std::vector<StreamJob> jobs;       // jobs of the last tfr_process
+	std::vector<cudaEvent_t> ev;       // front-end start/stop pairs then back-end pairs, per epoch
+	int n_epochs_last = 0;
+	cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
+	bool h2d_timed = false;
+	tfr_stats stats;
+	// host copies of results
+	bool results_valid = false;
+	std::vector<tfr_frame> frames;
+	std::vector<tfr_record> records;
+};
+
+static const char *kind_name(int k)
+{
+	static const char *n[] = { "TFA_1", "TFA_2", "TFA_3", "TX22", "WHB" };
+	return n[k];
+}
+
+// demod registration in the reference's order with its spb constants, main.cpp:171-218
+static void build_config(const tfr_config &c, DevConfig &d)
+{
+	memset(&d, 0, sizeof(d));
+	d.filter = c.filter ? 1 : 0;
+	d.thresh_cfg = c.thresh;
+	d.flags = (int32_t)c.flags;
+	d.n_streams = c.n_streams;
+	auto add = [&](int kind, int type, double spb, int timeout, const uint64_t *lp, const uint64_t *lp_avg) {
+		DemodCfg &q = d.d[d.n_demods++];
+		q.kind = kind;
+		q.type = type;
+		q.spb = spb;
+		q.timeout = timeout;
+		if (lp) q.lp = coef_from_bits(lp);
+		if (lp_avg) q.lp_avg = coef_from_bits(lp_avg);
+		d.t_max = std::max(d.t_max, timeout);
+	};
+	if (c.types & (1 << TFR_TFA_1)) add(K_TFA1, TFR_TFA_1, 10.0, 400, nullptr, nullptr);   // 40*BITPERIOD, tfa1.cpp:34,148
+	if (c.types & (1 << TFR_TFA_2)) { const double spb = (1536000 / 4.0) / 17240; add(K_TFA2, TFR_TFA_2, spb, (int)(16 * spb), kCoefTfa2, nullptr); }
+	if (c.types & (1 << TFR_TFA_3)) { const double spb = (1536000 / 4.0) / 9600; add(K_TFA3, TFR_TFA_3, spb, (int)(16 * spb), kCoefTfa3, nullptr); }
+	if (c.types & (1 << TFR_TX22)) { const double spb = (1536000 / 4.0) / 8842; add(K_TX22, TFR_TX22, spb, (int)(16 * spb), kCoefTx22, nullptr); }
+	if (c.types & (1 << TFR_TFA_WHB)) { const double spb = (1536000 / 4.0) / 6000; add(K_WHB, TFR_TFA_WHB, spb, (int)(8 * spb), kCoefWhbPulse, kCoefWhbAvg); }
+	if (d.n_demods == 0) d.t_max = 400;   // -T 0: decimator + trigger bookkeeping only
+}
+
+static void init_state(const DevConfig &d, StreamState &s)
+{
+	memset(&s, 0, sizeof(s));
+	memset(s.hist, 128, sizeof(s.hist));   // zero FIR history == byte 128 (decimate::decimate, dsp_stuff.cpp:145-152)
+	// fsk_demod::fsk_demod, fm_demod.cpp:19-32
+	s.thresh = d.thresh_cfg;
+	s.thresh_mode = 0;
+	if (d.thresh_cfg == 0) {
+		s.thresh = 500;
+		s.thresh_mode = 1;
+	}
+	for (int k = 0; k < d.n_demods; k++) {
+		DemodState &q = s.d[k];
+		q.sr_cnt = -1;
+		if (d.d[k].kind != K_TFA1) {   // tfa2_demod::reset (tfa2.cpp:325-334) / whb_demod::reset run in the constructors
+			q.dmin = 32767;
+			q.dmax = -32767;
+		}
+	}
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_abi_version(void) { return TFR_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char *tfr_last_error(void) { return g_err.c_str(); }
+
+extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_jobs); cudaFree(h->d_counters);
+	cudaFree(h->d_frames); cudaFree(h->d_records); cudaFree(h->d_tiles); cudaFree(h->d_dec);
+	cudaFree(h->d_trace); for (auto &c : h->arena) cudaFree(c.ptr); cudaFree(h->d_tap_i32[0]); cudaFree(h->d_tap_i32[1]);
+	cudaFree(h->d_tap_f64); cudaFree(h->d_tap_cnt);
+	for (auto e : h->ev) cudaEventDestroy(e);
+	if (h->ev_h2d0) cudaEventDestroy(h->ev_h2d0);
+	if (h->ev_h2d1) cudaEventDestroy(h->ev_h2d1);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_config *cfg, tfr_handle **out)
+{
+	if (!cfg || !out) return fail(TFR_E_INVAL, "tfr_create: null argument");
+	if (cfg->struct_size != sizeof(tfr_config)) return fail(TFR_E_INVAL, "tfr_create: struct_size mismatch (ABI version?)");
+	if (cfg->n_streams < 1 || cfg->n_streams > 65535) return fail(TFR_E_INVAL, "tfr_create: n_streams out of range");
+	if (cfg->thresh < 0) return fail(TFR_E_INVAL, "tfr_create: negative threshold");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(TFR_E_NODEVICE, "no CUDA device (this library has no CPU fallback)");
+	if (cfg->device < 0 || cfg->device >= ndev) return fail(TFR_E_NODEVICE, "tfr_create: device ordinal out of range");
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, cfg->device));
+	if (prop.major != 10)
+		return fail(TFR_E_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+						    ", kernels are built for sm_100a only");
+	CU(cudaSetDevice(cfg->device));
+
+	tfr_handle *h = new tfr_handle();
+	h->cfg = *cfg;
+	h->device = cfg->device;
+	memset(&h->stats, 0, sizeof(h->stats));
+	build_config(*cfg, h->dcfg);
+	h->pend.resize(cfg->n_streams);
+	h->max_frames = cfg->max_frames ? cfg->max_frames : 65536u;
+	h->max_records = h->max_frames * 5u;
+	auto bail = [&](int code) { tfr_destroy(h); return code; };
+#define CUH(call)                                                                                          \
+	do {                                                                                               \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return bail(fail(e_ == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA,       \
+					 std::string(#call) + ": " + cudaGetErrorString(e_)));             \
+	} while (0)
+	CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CUH(cudaEventCreate(&h->ev_h2d0));
+	CUH(cudaEventCreate(&h->ev_h2d1));
+	CUH(cudaMalloc(&h->d_cfg, sizeof(DevConfig)));
+	CUH(cudaMemcpy(h->d_cfg, &h->dcfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
+	CUH(cudaMalloc(&h->d_state, sizeof(StreamState) * cfg->n_streams));
+	{
+		std::vector<StreamState> init(cfg->n_streams);
+		for (auto &s : init) init_state(h->dcfg, s);
+		CUH(cudaMemcpy(h->d_state, init.data(), sizeof(StreamState) * cfg->n_streams, cudaMemcpyHostToDevice));
+	}
+	CUH(cudaMalloc(&h->d_jobs, sizeof(StreamJob) * cfg->n_streams));
+	CUH(cudaMalloc(&h->d_counters, sizeof(Counters)));
+	CUH(cudaMemset(h->d_counters, 0, sizeof(Counters)));
+	CUH(cudaMalloc(&h->d_frames, sizeof(DevFrame) * h->max_frames));
+	CUH(cudaMalloc(&h->d_records, sizeof(DevRecord) * h->max_records));
+	if (cfg->flags & TFR_FLAG_TAPS) {
+		h->tap_cap = 1u << 23;
+		const size_t n = (size_t)cfg->n_streams * kMaxDemods * h->tap_cap;
+		CUH(cudaMalloc(&h->d_tap_i32[0], n * sizeof(int32_t)));
+		CUH(cudaMalloc(&h->d_tap_i32[1], n * sizeof(int32_t)));
+		CUH(cudaMalloc(&h->d_tap_f64, n * sizeof(double)));
+		CUH(cudaMalloc(&h->d_tap_cnt, (size_t)cfg->n_streams * kMaxDemods * 3 * sizeof(uint32_t)));
+		CUH(cudaMemset(h->d_tap_cnt, 0, (size_t)cfg->n_streams * kMaxDemods * 3 * sizeof(uint32_t)));
+	}
+#undef CUH
+	*out = h;
+	return TFR_OK;
+}
+
+static int ensure_blocks(tfr_handle *h, size_t blocks)
+{
+	if (blocks <= h->cap_blocks) return TFR_OK;
+	CU(cudaStreamSynchronize(h->stream));
+	cudaFree(h->d_tiles); cudaFree(h->d_dec); cudaFree(h->d_trace);
+	h->d_tiles = nullptr; h->d_dec = nullptr; h->d_trace = nullptr;
+	h->cap_blocks = 0;
+	cudaError_t e = cudaMalloc(&h->d_tiles, blocks * sizeof(TileDesc));
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_trace, blocks * sizeof(BlockTrace));
+	if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA,
+					  std::string("work buffers: ") + cudaGetErrorString(e));
+	h->cap_blocks = blocks;
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_submit(tfr_handle *h, int stream, const uint8_t *iq, size_t nbytes, int mem)
+{
+	if (!h || !iq) return fail(TFR_E_INVAL, "tfr_submit: null argument");
+	if (stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_submit: stream out of range");
+	if (nbytes == 0 || nbytes % TFR_BLOCK_BYTES) return fail(TFR_E_INVAL, "tfr_submit: nbytes must be a positive multiple of 65536");
+	if (nbytes / TFR_BLOCK_BYTES > 0x7fffffffull) return fail(TFR_E_INVAL, "tfr_submit: too many blocks");
+	PendingSubmit &ps = h->pend[stream];
+	if (ps.pending) return fail(TFR_E_BUSY, "tfr_submit: stream already has a pending submit");
+	CU(cudaSetDevice(h->device));
+	if (mem == TFR_MEM_DEVICE) {
+		if ((uintptr_t)iq & 15) return fail(TFR_E_INVAL, "tfr_submit: device pointer must be 16-byte aligned");
+		ps.dev_ptr = iq;
+	} else if (mem == TFR_MEM_HOST) {
+		bool idle = true;
+		for (auto &q : h->pend) idle &= !q.pending;
+		if (idle && h->arena.size() > 1) {   // merge the chunks of the previous round into one
+			size_t tot = 0;
+			for (auto &c : h->arena) tot += c.cap;
+			CU(cudaStreamSynchronize(h->stream));
+			for (auto &c : h->arena) cudaFree(c.ptr);
+			h->arena.clear();
+			uint8_t *ptr = nullptr;
+			if (cudaMalloc(&ptr, tot) != cudaSuccess) { cudaGetLastError(); return fail(TFR_E_NOMEM, "tfr_submit: input arena"); }
+			h->arena.push_back({ ptr, tot, 0 });
+		}
+		tfr_handle::Chunk *ck = nullptr;
+		for (auto &c : h->arena)
+			if (c.used + nbytes <= c.cap) { ck = &c; break; }
+		if (!ck) {
+			size_t want = std::max(nbytes, (size_t)h->cfg.max_blocks_per_submit * TFR_BLOCK_BYTES);
+			if (h->arena.empty()) want *= (size_t)h->cfg.n_streams;
+			if (idle && !h->arena.empty()) {   // nothing points into the old chunk: replace it
+				CU(cudaStreamSynchronize(h->stream));
+				for (auto &c : h->arena) cudaFree(c.ptr);
+				h->arena.clear();
+			}
+			uint8_t *ptr = nullptr;
+			cudaError_t e = cudaMalloc(&ptr, want);
+			if (e != cudaSuccess) { cudaGetLastError(); return fail(TFR_E_NOMEM, std::string("tfr_submit: input arena: ") + cudaGetErrorString(e)); }
+			h->arena.push_back({ ptr, want, 0 });
+			ck = &h->arena.back();
+		}
+		uint8_t *dst = ck->ptr + ck->used;
+		if (!h->h2d_timed) {
+			CU(cudaEventRecord(h->ev_h2d0, h->stream));
+			h->h2d_timed = true;
+		}
+		CU(cudaMemcpyAsync(dst, iq, nbytes, cudaMemcpyHostToDevice, h->stream));
+		CU(cudaEventRecord(h->ev_h2d1, h->stream));
+		ck->used += nbytes;
+		ps.dev_ptr = dst;
+	} else {
+		return fail(TFR_E_INVAL, "tfr_submit: mem must be TFR_MEM_HOST or TFR_MEM_DEVICE");
+	}
+	ps.nbytes = nbytes;
+	ps.pending = true;
+	return TFR_OK;
+}
+
+static int ensure_events(tfr_handle *h, size_t n)
+{
+	while (h->ev.size() < n) {
+		cudaEvent_t e;
+		CU(cudaEventCreate(&e));
+		h->ev.push_back(e);
+	}
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
+{
+	if (!h) return fail(TFR_E_INVAL, "tfr_process: null handle");
+	CU(cudaSetDevice(h->device));
+	cudaGetLastError();   // do not inherit a stale error from another user of the runtime
+	const int ns = h->cfg.n_streams;
+	h->jobs.assign(ns, StreamJob{ nullptr, 0, 0 });
+	size_t total = 0;
+	uint32_t max_blocks = 0;
+	for (int s = 0; s < ns; s++) {
+		PendingSubmit &ps = h->pend[s];
+		if (!ps.pending) continue;
+		StreamJob &j = h->jobs[s];
+		j.iq = ps.dev_ptr;
+		j.n_blocks = (uint32_t)(ps.nbytes / TFR_BLOCK_BYTES);
+		j.dec_off = (uint32_t)total;
+		total += j.n_blocks;
+		max_blocks = std::max(max_blocks, j.n_blocks);
+		ps.pending = false;
+	}
+	for (auto &c : h->arena) c.used = 0;   // contents stay valid until the next submit overwrites them (stream ordered)
+	h->n_epochs_last = 0;
+	if (total == 0) return TFR_OK;
+	if (total > 0xffffffffull) return fail(TFR_E_INVAL, "tfr_process: too many blocks in one call");
+	int rc = ensure_blocks(h, total);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(h->d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, h->stream));
+
+	// In auto-threshold mode the threshold may drift by 2 every 4th block (fm_demod.cpp:63-72); the
+	// front-end keeps windows for a lower bound that holds for one epoch, then the threshold kernel
+	// publishes the exact per-block values before the next epoch's front-end launch reads them.
+	const bool auto_mode = (h->dcfg.thresh_cfg == 0);
+	const uint32_t epoch = auto_mode ? 64u : max_blocks;
+	const int n_epochs = (int)((max_blocks + epoch - 1) / epoch);
+	rc = ensure_events(h, (size_t)n_epochs * 4);
+	if (rc) return rc;
+
+	FrontParams fp;
+	fp.jobs = h->d_jobs;
+	fp.st = h->d_state;
+	fp.tiles = h->d_tiles;
+	fp.dec = h->d_dec;
+	fp.t_max = h->dcfg.t_max;
+	fp.keep_all = (h->cfg.flags & TFR_FLAG_KEEP_DECIM) ? 1 : 0;
+	fp.epoch_blocks = (int)epoch;
+	BackParams bp;
+	memset(&bp, 0, sizeof(bp));
+	bp.cfg = h->d_cfg;
+	bp.jobs = h->d_jobs;
+	bp.st = h->d_state;
+	bp.tiles = h->d_tiles;
+	bp.dec = h->d_dec;
+	bp.trace = h->d_trace;
+	bp.frames = h->d_frames;
+	bp.records = h->d_records;
+	bp.counters = h->d_counters;
+	bp.tap_i32[0] = h->d_tap_i32[0];
+	bp.tap_i32[1] = h->d_tap_i32[1];
+	bp.tap_f64 = h->d_tap_f64;
+	bp.tap_cnt = h->d_tap_cnt;
+	bp.tap_cap = h->tap_cap;
+	bp.max_frames = h->max_frames;
+	bp.max_records = h->max_records;
+	bp.n_streams = ns;
+
+	for (int e = 0; e < n_epochs; e++) {
+		const int tile0 = (int)(e * epoch);
+		const int nt = (int)std::min<uint32_t>(epoch, max_blocks - tile0);
+		fp.tile0 = tile0;
+		fp.n_tiles = nt;
+		bp.tile0 = tile0;
+		bp.n_tiles = nt;
+		bp.last_epoch = (e == n_epochs - 1);
+		CU(cudaEventRecord(h->ev[4 * e + 0], h->stream));
+		CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
+		CU(cudaEventRecord(h->ev[4 * e + 1], h->stream));
+		CU(cudaEventRecord(h->ev[4 * e + 2], h->stream));
+		CU(launch_thresh(bp, h->stream));
+		h->stats.kernel_launches += 2;
+		if (h->dcfg.n_demods) {
+			CU(launch_walk(bp, h->dcfg.n_demods, h->stream));
+			h->stats.kernel_launches += 1;
+		}
+		if (e == n_epochs - 1) {
+			CU(launch_submit_epilogue(bp, h->stream));
+			CU(launch_save_history(h->d_jobs, h->d_state, ns, h->stream));
+			CU(launch_parse(bp, h->stream));
+			h->stats.kernel_launches += 3;
+		}
+		CU(cudaEventRecord(h->ev[4 * e + 3], h->stream));
+	}
+	h->n_epochs_last = n_epochs;
+	h->stats.blocks += total;
+	h->stats.raw_samples += total * (uint64_t)kBlockRaw;
+	h->results_valid = false;
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_sync(tfr_handle *h)
+{
+	if (!h) return fail(TFR_E_INVAL, "tfr_sync: null handle");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	if (h->n_epochs_last) {
+		double fe = 0, be = 0;
+		for (int e = 0; e < h->n_epochs_last; e++) {
+			float a = 0, b = 0;
+			CU(cudaEventElapsedTime(&a, h->ev[4 * e + 0], h->ev[4 * e + 1]));
+			CU(cudaEventElapsedTime(&b, h->ev[4 * e + 2], h->ev[4 * e + 3]));
+			fe += a;
+			be += b;
+		}
+		h->stats.last_frontend_ms = fe;
+		h->stats.last_backend_ms = be;
+		h->n_epochs_last = 0;
+	}
+	if (h->h2d_timed) {
+		float a = 0;
+		CU(cudaEventElapsedTime(&a, h->ev_h2d0, h->ev_h2d1));
+		h->stats.last_h2d_ms = a;
+		h->h2d_timed = false;
+	}
+	return TFR_OK;
+}
+
+// (int) of a double the way the reference's x86 cvttsd2si does it (tfa1.cpp:180 feeds it log10(0) = -inf)
+static int d2i_x86(double v)
+{
+	if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+	return (int)v;
+}
+
+static int fetch_results(tfr_handle *h)
+{
+	if (h->results_valid) return TFR_OK;
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	Counters c;
+	CU(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+	const uint32_t nf = std::min(c.n_frames, h->max_frames);
+	const uint32_t nr = std::min(c.n_records, h->max_records);
+	std::vector<DevFrame> df(nf);
+	std::vector<DevRecord> dr(nr);
+	if (nf) CU(cudaMemcpy(df.data(), h->d_frames, sizeof(DevFrame) * nf, cudaMemcpyDeviceToHost));
+	if (nr) CU(cudaMemcpy(dr.data(), h->d_records, sizeof(DevRecord) * nr, cudaMemcpyDeviceToHost));
+	// reference output order: time, then registration order (SURVEY.md §8b "Threading")
+	std::vector<uint32_t> order(nf);
+	for (uint32_t k = 0; k < nf; k++) order[k] = k;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+		const DevFrame &x = df[a], &y = df[b];
+		if (x.stream != y.stream) return x.stream < y.stream;
+		if (x.pos != y.pos) return x.pos < y.pos;
+		return x.demod < y.demod;
+	});
+	h->frames.clear();
+	h->records.clear();
+	const int64_t now = (int64_t)time(nullptr);
+	for (uint32_t k : order) {
+		const DevFrame &x = df[k];
+		tfr_frame f;
+		memset(&f, 0, sizeof(f));
+		f.stream = x.stream;
+		f.type = x.type;
+		f.status = x.status;
+		f.byte_cnt = x.byte_cnt;
+		f.pos = x.pos;
+		f.offset = x.offset;
+		f.rssi_raw = x.rssi_raw;
+		// the dB conversion happens here with the host libm: tfa1.cpp:180, tfa2.cpp:434, whb.cpp:696 (as built: rssi*0.00025)
+		if (x.type == TFR_TFA_WHB) f.rssi = d2i_x86(10 * log10(1 + x.rssi_raw * 0.00025));
+		else f.rssi = d2i_x86(10 * log10(x.rssi_raw));
+		f.n_records = 0;
+		f.first_record = (int32_t)h->records.size();
+		memcpy(f.rdata, x.rdata, TFR_MAX_RDATA);
+		const int fidx = (int)h->frames.size();
+		for (int r = 0; r < x.n_records; r++) {
+			const uint32_t ri = (uint32_t)x.first_record + r;
+			if (ri >= nr) break;
+			const DevRecord &y = dr[ri];
+			tfr_record o;
+			memset(&o, 0, sizeof(o));
+			o.stream = y.stream;
+			o.type = y.type;
+			o.id = y.id;
+			o.temp = y.temp;
+			o.humidity = y.humidity;
+			o.alarm = y.alarm;
+			o.flags = y.flags;
+			o.sequence = y.sequence;
+			o.rssi = f.rssi;
+			o.ts = now;
+			o.pos = y.pos;
+			o.frame = fidx;
+			h->records.push_back(o);
+			f.n_records++;
+		}
+		h->frames.push_back(f);
+	}
+	h->stats.frames = h->frames.size();
+	h->stats.records = h->records.size();
+	h->stats.active_samples = c.active_samples;
+	h->results_valid = true;
+	if (c.overflow) return fail(TFR_E_OVERFLOW, "frame/record buffer overflowed; raise tfr_config.max_frames");
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_poll_frames(tfr_handle *h, tfr_frame *out, size_t cap)
+{
+	if (!h) return fail(TFR_E_INVAL, "tfr_poll_frames: null handle");
+	int rc = fetch_results(h);
+	if (rc && rc != TFR_E_OVERFLOW) return rc;
+	if (!out) return (long)h->frames.size();
+	const size_t n = std::min(cap, h->frames.size());
+	if (n) memcpy(out, h->frames.data(), n * sizeof(tfr_frame));
+	return (long)n;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_poll_records(tfr_handle *h, tfr_record *out, size_t cap)
+{
+	if (!h) return fail(TFR_E_INVAL, "tfr_poll_records: null handle");
+	int rc = fetch_results(h);
+	if (rc && rc != TFR_E_OVERFLOW) return rc;
+	if (!out) return (long)h->records.size();
+	const size_t n = std::min(cap, h->records.size());
+	if (n) memcpy(out, h->records.data(), n * sizeof(tfr_record));
+	return (long)n;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_clear_results(tfr_handle *h)
+{
+	if (!h) return fail(TFR_E_INVAL, "tfr_clear_results: null handle");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	// keep active_samples running; zero the frame/record cursors
+	Counters c;
+	CU(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+	c.n_frames = c.n_records = c.overflow = 0;
+	CU(cudaMemcpy(h->d_counters, &c, sizeof(c), cudaMemcpyHostToDevice));
+	if (h->d_tap_cnt) CU(cudaMemset(h->d_tap_cnt, 0, (size_t)h->cfg.n_streams * kMaxDemods * 3 * sizeof(uint32_t)));
+	h->frames.clear();
+	h->records.clear();
+	h->results_valid = false;
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_get_thresh(tfr_handle *h, int stream, int32_t *thresh)
+{
+	if (!h || !thresh || stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_get_thresh: bad argument");
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	CU(cudaMemcpy(thresh, (const char *)(h->d_state + stream) + offsetof(StreamState, thresh), sizeof(int32_t), cudaMemcpyDeviceToHost));
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_read_block_trace(tfr_handle *h, int stream, tfr_block_trace *out, size_t cap)
+{
+	if (!h || stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_read_block_trace: bad argument");
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	if (h->jobs.empty()) return 0;
+	const StreamJob &j = h->jobs[stream];
+	if (!out) return (long)j.n_blocks;
+	const size_t n = std::min<size_t>(cap, j.n_blocks);
+	static_assert(sizeof(tfr_block_trace) == sizeof(BlockTrace), "trace layout");
+	if (n) CU(cudaMemcpy(out, h->d_trace + j.dec_off, n * sizeof(BlockTrace), cudaMemcpyDeviceToHost));
+	return (long)n;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_read_taps(tfr_handle *h, int stream, int demod, int kind, void *out, size_t cap_elems)
+{
+	if (!h || stream < 0 || stream >= h->cfg.n_streams || demod < 0 || demod >= h->dcfg.n_demods || kind < 0 || kind > 2)
+		return fail(TFR_E_INVAL, "tfr_read_taps: bad argument");
+	if (!h->tap_cap) return fail(TFR_E_INVAL, "tfr_read_taps: handle was created without TFR_FLAG_TAPS");
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	uint32_t cnt = 0;
+	const size_t slot = (size_t)stream * kMaxDemods + demod;
+	CU(cudaMemcpy(&cnt, h->d_tap_cnt + slot * 3 + kind, sizeof(cnt), cudaMemcpyDeviceToHost));
+	if (cnt > h->tap_cap) return fail(TFR_E_OVERFLOW, "tap buffer overflowed");
+	if (!out) return (long)cnt;
+	const size_t n = std::min<size_t>(cap_elems, cnt);
+	if (n) {
+		if (kind == 2) CU(cudaMemcpy(out, h->d_tap_f64 + slot * h->tap_cap, n * sizeof(double), cudaMemcpyDeviceToHost));
+		else CU(cudaMemcpy(out, h->d_tap_i32[kind] + slot * h->tap_cap, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+	}
+	return (long)n;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_read_decimated(tfr_handle *h, int stream, int16_t *out, size_t cap_int16)
+{
+	if (!h || stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_read_decimated: bad argument");
+	if (!(h->cfg.flags & TFR_FLAG_KEEP_DECIM)) return fail(TFR_E_INVAL, "tfr_read_decimated: handle was created without TFR_FLAG_KEEP_DECIM");
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	if (h->jobs.empty()) return 0;
+	const StreamJob &j = h->jobs[stream];
+	const size_t avail = (size_t)j.n_blocks * kBlockDec * 2;
+	if (!out) return (long)avail;
+	const size_t n = std::min(cap_int16, avail) & ~(size_t)1;
+	if (n) CU(cudaMemcpy(out, h->d_dec + (size_t)j.dec_off * kBlockDec, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+	return (long)n;
+}
+
+extern "C" __attribute__((visibility("default"))) long tfr_decimate(int device, const uint8_t *iq, size_t nbytes, int filter, int16_t *out, int mem)
+{
+	if (!iq || !out || nbytes < 4) return fail(TFR_E_INVAL, "tfr_decimate: bad argument");
+	tfr_config c;
+	memset(&c, 0, sizeof(c));
+	c.struct_size = sizeof(c);
+	c.device = device;
+	c.types = 0;
+	c.filter = filter;
+	c.thresh = 32767;
+	c.n_streams = 1;
+	c.flags = TFR_FLAG_KEEP_DECIM;
+	tfr_handle *h = nullptr;
+	int rc = tfr_create(&c, &h);
+	if (rc) return rc;
+	// pad to whole blocks with zero-signal bytes; only the first nbytes/4 outputs are returned
+	const size_t padded = (nbytes + TFR_BLOCK_BYTES - 1) / TFR_BLOCK_BYTES * TFR_BLOCK_BYTES;
+	uint8_t *d_in = nullptr;
+	long ret = 0;
+	auto cuda_fail = [&](const char *what, cudaError_t e) { return (long)fail(TFR_E_CUDA, std::string("tfr_decimate: ") + what + ": " + cudaGetErrorString(e)); };
+	do {
+		cudaError_t e;
+		if ((e = cudaMalloc(&d_in, padded)) != cudaSuccess) { ret = fail(TFR_E_NOMEM, std::string("tfr_decimate: input buffer: ") + cudaGetErrorString(e)); break; }
+		if ((e = cudaMemset(d_in, 128, padded)) != cudaSuccess) { ret = cuda_fail("memset", e); break; }
+		if ((e = cudaMemcpy(d_in, iq, nbytes, mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)) != cudaSuccess) { ret = cuda_fail("copy in", e); break; }
+		if ((rc = tfr_submit(h, 0, d_in, padded, TFR_MEM_DEVICE)) || (rc = tfr_process(h)) || (rc = tfr_sync(h))) { ret = rc; break; }
+		const size_t n_out = (nbytes / 8) * 2;   // nbytes/2 raw samples -> /4 decimated -> 2 int16 each
+		if ((e = cudaMemcpy(out, h->d_dec, n_out * sizeof(int16_t), mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost)) != cudaSuccess) { ret = cuda_fail("copy out", e); break; }
+		ret = (long)n_out;
+	} while (0);
+	cudaFree(d_in);
+	std::string keep = g_err;
+	tfr_destroy(h);
+	g_err = keep;
+	return ret;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_parse_bytes(tfr_handle *h, int type, const uint8_t *bytes, int len, tfr_frame *frame,
+			       tfr_record *recs, int max_recs)
+{
+	if (!h || !bytes || len < 0) return fail(TFR_E_INVAL, "tfr_parse_bytes: bad argument");
+	int demod = -1;
+	for (int k = 0; k < h->dcfg.n_demods; k++)
+		if (h->dcfg.d[k].type == type) demod = k;
+	if (demod < 0) return fail(TFR_E_INVAL, "tfr_parse_bytes: sensor type not registered in this handle");
+	CU(cudaSetDevice(h->device));
+	// decoder::store_bytes (decoder.cpp:35-40) then the length gate of the type's flush()
+	const int kind = h->dcfg.d[demod].kind;
+	const int bc = std::min(len, 256);
+	bool gate;
+	if (kind == K_TFA1) gate = bc >= 10;
+	else if (kind == K_TX22) gate = bc >= 7 && bc < 64;
+	else if (kind == K_WHB) gate = !(bc < 11 || bc > 60);
+	else gate = bc >= 7;
+	if (!gate) return -1;
+	DevFrame f;
+	memset(&f, 0, sizeof(f));
+	f.stream = 0;
+	f.demod = demod;
+	f.type = type;
+	f.status = -1;
+	f.byte_cnt = bc;
+	f.pos = -1;
+	f.rssi_raw = 1.0;   // flush(0): 10*log10(1) == 0
+	memcpy(f.rdata, bytes, std::min(bc, (int)kMaxRdata));
+	DevFrame *d_f = nullptr;
+	DevRecord *d_r = nullptr;
+	Counters *d_c = nullptr;
+	Counters c;
+	memset(&c, 0, sizeof(c));
+	c.n_frames = 1;
+	CU(cudaMalloc(&d_f, sizeof(DevFrame)));
+	CU(cudaMalloc(&d_r, sizeof(DevRecord) * 8));
+	CU(cudaMalloc(&d_c, sizeof(Counters)));
+	CU(cudaMemcpy(d_f, &f, sizeof(f), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d_c, &c, sizeof(c), cudaMemcpyHostToDevice));
+	BackParams bp;
+	memset(&bp, 0, sizeof(bp));
+	bp.cfg = h->d_cfg;
+	bp.frames = d_f;
+	bp.records = d_r;
+	bp.counters = d_c;
+	bp.max_frames = 1;
+	bp.max_records = 8;
+	CU(launch_parse(bp, h->stream));
+	h->stats.kernel_launches += 1;
+	CU(cudaStreamSynchronize(h->stream));
+	DevRecord r[8];
+	CU(cudaMemcpy(&f, d_f, sizeof(f), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(r, d_r, sizeof(r), cudaMemcpyDeviceToHost));
+	cudaFree(d_f); cudaFree(d_r); cudaFree(d_c);
+	if (frame) {
+		memset(frame, 0, sizeof(*frame));
+		frame->type = type;
+		frame->status = f.status;
+		frame->byte_cnt = bc;
+		frame->pos = -1;
+		frame->rssi = 0;
+		frame->rssi_raw = 1.0;
+		frame->n_records = f.n_records;
+		memcpy(frame->rdata, f.rdata, TFR_MAX_RDATA);
+	}
+	for (int k = 0; k < f.n_records && k < max_recs; k++) {
+		const DevRecord &y = r[f.first_record + k];
+		tfr_record &o = recs[k];
+		memset(&o, 0, sizeof(o));
+		o.type = y.type;
+		o.id = y.id;
+		o.temp = y.temp;
+		o.humidity = y.humidity;
+		o.alarm = y.alarm;
+		o.flags = y.flags;
+		o.sequence = y.sequence;
+		o.rssi = 0;
+		o.ts = (int64_t)time(nullptr);
+		o.pos = -1;
+	}
+	return f.n_records;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_get_stats(tfr_handle *h, tfr_stats *out)
+{
+	if (!h || !out) return fail(TFR_E_INVAL, "tfr_get_stats: null argument");
+	*out = h->stats;
+	return TFR_OK;
+}

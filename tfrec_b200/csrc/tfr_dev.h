@@ -1,0 +1,174 @@
+// tfr_dev.h - device-side data layout shared by the front-end, the back-end and the C-ABI host code.
+//
+// Vocabulary follows the reference: a *stream* is one stick's IQ feed (one engine instance), a
+// *block* is one 65536-byte replay block (engine.cpp:68) = 32768 raw IQ samples = 8192 decimated
+// samples, a *demod* is one registered demodulator+decoder pair (main.cpp:171-218), a *window* is
+// one retriggerable timeout interval of a demod (tfa1.cpp:147-148, tfa2.cpp:351-356, whb.cpp:636-642),
+// a *frame* is one decoder::flush(), a *record* is one sensordata_t (decoder.h:21-31).
+#pragma once
+#include <stdint.h>
+
+namespace tfr {
+
+constexpr int kBlockBytes = 65536;      // engine.cpp:68
+constexpr int kBlockRaw = 32768;        // raw IQ samples per block
+constexpr int kBlockDec = 8192;         // decimated (384 kS/s) samples per block
+constexpr int kIdxPerBlock = 16384;     // `len` of fsk_demod::process, index += 2 per sample (fm_demod.cpp:42)
+constexpr int kHistBytes = 96;          // raw bytes of FIR history carried between submits (needs 92)
+constexpr int kMaxSeg = 28;             // trigger segments per block (>= 8192/357 + 2)
+constexpr int kMaxDemods = 5;
+constexpr int kMaxRdata = 64;
+constexpr int kRdataBytes = 256;        // decoder::rdata (decoder.h:52)
+
+// demod kinds, in the reference's registration order (main.cpp:173-218)
+enum Kind : int { K_TFA1 = 0, K_TFA2 = 1, K_TFA3 = 2, K_TX22 = 3, K_WHB = 4 };
+
+struct Biquad {          // iir2 (dsp_stuff.h:18-27): direct form I, double state
+	double d1, d2, y0, y1;
+};
+
+struct BiquadCoef { double b0, b1, b2, a1, a2; };
+
+struct DemodCfg {
+	int32_t kind;        // Kind
+	int32_t type;        // sensor_e value reported in frames/records
+	int32_t timeout;     // samples a trigger keeps the demod active: 400 / (int)(16*spb) / (int)(8*spb)
+	int32_t pad;
+	double spb;          // samples per bit at 384 kS/s (main.cpp:186,194,202,217)
+	BiquadCoef lp;       // tfa2: 0.5/spb (tfa2.cpp:321); whb pulse filter 2.0/spb (whb.cpp:610)
+	BiquadCoef lp_avg;   // whb: 0.0025/spb (whb.cpp:611)
+};
+
+struct DevConfig {
+	int32_t n_demods;
+	int32_t t_max;       // max timeout over the registered demods
+	int32_t filter;      // 0 narrow, 1 wide
+	int32_t thresh_cfg;  // -t value, 0 = auto
+	int32_t flags;
+	int32_t n_streams;
+	DemodCfg d[kMaxDemods];
+};
+
+// everything one registered demodulator + decoder carries from sample to sample
+struct DemodState {
+	// demodulator base (decoder.h:61-73)
+	int32_t last_bit_idx;
+	int32_t timeout_cnt;
+	// tfa1_demod (tfa1.h:23-33)
+	int32_t mark_lvl;
+	int32_t rssi_i;      // tfa1: peak hold; tfa2: power accumulator
+	// tfa2_demod (tfa2.h:29-44)
+	int32_t bitcnt, dmin, dmax, offset, last_bit;
+	// whb_demod (whb.h:45-61)
+	int32_t last_dev, avg_of;
+	uint32_t step_lo;    // `step` is uint64 in the reference but reset per window; 32 bits suffice for tdiff
+	uint32_t last_peak;
+	double rssi_d;
+	Biquad lp, lp_avg;
+	// decoder side: shift register framer (tfa1.cpp:120-134, tfa2.cpp:281-314, whb.cpp:566-603)
+	uint32_t sr;
+	int32_t sr_cnt;
+	int32_t byte_cnt;
+	int32_t synced;
+	int32_t invert;
+	int32_t w_last_bit, w_psk, w_last_psk, w_nrzs;
+	uint32_t w_lfsr;
+	uint8_t rdata[kRdataBytes];
+};
+
+struct alignas(128) StreamState {
+	alignas(16) uint8_t hist[2][kHistBytes];  // FIR history (last raw bytes of the previous submit), double buffered
+	int64_t blocks_done;          // blocks fully decoded -> position base = blocks_done * 8192
+	// fsk_demod (fm_demod.h:24-30)
+	int32_t thresh;
+	int32_t thresh_mode;          // 1 = auto
+	int32_t triggered_avg;
+	int32_t runs;
+	// trigger bookkeeping carried between blocks
+	int32_t any_timeout;          // remaining samples for which "any demod active" holds (T_max logic)
+	int32_t carry_in;             // decimated samples at the head of the next block covered by earlier triggers
+	int16_t last_i, last_q;       // previous decimated sample (every demod's last_i/last_q)
+	int32_t hist_parity;
+	int32_t pad;
+	DemodState d[kMaxDemods];
+};
+
+// one entry per (stream, block) of a process() call, written by the front-end
+struct TileDesc {
+	uint16_t n_seg;               // trigger segments that start inside this block
+	uint16_t carry_out;           // samples of the NEXT block still covered by this block's last trigger
+	uint16_t seg_start[kMaxSeg];  // first covered sample (the trigger itself)
+	uint16_t seg_len[kMaxSeg];    // covered samples, clipped to the block end
+	uint32_t n_trig;              // samples with pwr > thresh_lo
+	uint32_t pad;
+};
+static_assert(sizeof(TileDesc) == 2 * 2 + 4 * kMaxSeg + 8, "TileDesc layout");
+
+struct StreamJob {
+	const uint8_t *iq;            // device pointer to this stream's submitted bytes
+	uint32_t n_blocks;            // blocks in this submit
+	uint32_t dec_off;             // offset (in blocks) of this stream inside the sparse decimated buffer
+};
+
+// device-side frame / record (converted to tfr_frame / tfr_record on the host)
+struct DevFrame {
+	int32_t stream, demod, type, status;
+	int32_t byte_cnt, offset, n_records, first_record;
+	int64_t pos;
+	double rssi_raw;
+	uint8_t rdata[kMaxRdata];
+};
+
+struct DevRecord {
+	int32_t stream, type;
+	uint64_t id;
+	double temp, humidity;
+	int32_t alarm, flags, sequence, frame;
+	int64_t pos;
+};
+
+struct BlockTrace { int32_t thresh, triggered, triggered_avg; };
+
+struct Counters {
+	uint32_t n_frames;
+	uint32_t n_records;
+	uint32_t overflow;
+	uint32_t pad;
+	unsigned long long active_samples;
+};
+
+struct FrontParams {
+	const StreamJob *jobs;
+	StreamState *st;
+	TileDesc *tiles;
+	uint32_t *dec;         // sparse decimated buffer, one uint32 (I lo16, Q hi16) per sample
+	int tile0;             // first block of this epoch inside the submit
+	int n_tiles;           // blocks in this epoch (grid.x)
+	int t_max;
+	int keep_all;          // TFR_FLAG_KEEP_DECIM: write every sample
+	int epoch_blocks;      // bound on threshold drift: thresh_lo = thresh - 2*ceil(epoch_blocks/4) in auto mode
+};
+
+struct BackParams {
+	const DevConfig *cfg;
+	const StreamJob *jobs;
+	StreamState *st;
+	const TileDesc *tiles;
+	const uint32_t *dec;
+	BlockTrace *trace;       // [gtile]
+	DevFrame *frames;
+	DevRecord *records;
+	Counters *counters;
+	int32_t *tap_i32[2];     // kind 0 fm_dev, kind 1 fm_dev_nrzs: [stream][demod][tap_cap]
+	double *tap_f64;         // kind 2 iir2::step outputs
+	uint32_t *tap_cnt;       // [stream][demod][3]
+	uint32_t tap_cap;
+	uint32_t max_frames, max_records;
+	int tile0, n_tiles;      // epoch range inside the submit
+	int n_streams;
+	int last_epoch;          // 1: this epoch ends the submit -> roll stream state forward
+};
+
+}  // namespace tfr
+
+

@@ -1,0 +1,34 @@
+"""Quick front-end / back-end timing probe on synthetic noise (not the bench; used while iterating)."""
+import sys, os, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np, torch
+import tfrec_b200 as tb
+
+def main():
+    n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    mib = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    thresh = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+    types = int(sys.argv[4], 16) if len(sys.argv) > 4 else 7
+    sigma = float(sys.argv[5]) if len(sys.argv) > 5 else 4.0
+    nbytes = mib << 20
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    bufs = []
+    for s in range(n_streams):
+        x = torch.randn(nbytes, device="cuda", generator=g) * sigma + 128.0
+        bufs.append(x.round_().clamp_(0, 255).to(torch.uint8))
+        del x
+    rx = tb.Receiver(types=types, thresh=thresh, n_streams=n_streams)
+    for it in range(4):
+        for s in range(n_streams):
+            rx.submit(s, bufs[s].data_ptr(), nbytes=nbytes)
+        t0 = time.time(); rx.process(); rx.sync(); dt = time.time() - t0
+        st = rx.stats()
+        samples = n_streams * nbytes / 2
+        print("iter %d wall %.3f ms  frontend %.3f ms (%.1f GS/s, %.1f GB/s)  backend %.3f ms  active %.2f%% frames %d thresh %d" % (
+            it, dt * 1e3, st["last_frontend_ms"], samples / st["last_frontend_ms"] / 1e6, 2 * samples / st["last_frontend_ms"] / 1e6,
+            st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)))
+        rx.clear()
+
+if __name__ == "__main__":
+    main()
