@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py - IQ MSamples/s (+ telegrams/s) of the IQ->telegram decode path on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     the unmodified reference CPU path (oracle/_ref/tfrec)
+
+Workload (BASELINE.json configs[1]): `-T 7` (TFA_1 + TFA_2 + TFA_3), default auto threshold, continuous
+1.536 MS/s synthetic IQ per stream ("stick") with one telegram every 10 s (15.36 M samples), types rotated.
+One step = one pass of the hot path over every stream's buffer.  Streams are independent, so they shard
+across ranks with no data-path collective (weak scaling: per-GPU work is fixed).
+
+`value`   whole-job throughput with the IQ bytes already resident in HBM (device time, lib CUDA events)
+`e2e`     the same pass through the public C ABI with HOST (pinned) buffers: H2D of every step's input and
+          D2H of its results inside the timed region
+`roofline` the front-end kernel: 2 algorithmic bytes per raw IQ sample / its CUDA-event time, vs the measured
+          HBM peak in MEASURED_PEAKS.json
+`cpu_baseline` the unmodified reference binary on the box's host cores, one process per core, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+FS = 1536000
+PERIOD = 10 * FS               # one telegram every 10 s
+TYPES_MASK = 0x07
+SENSORS = (0, 1, 2)            # TFA_1, TFA_2, TFA_3
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "tfrec")
+
+
+def workload_name(args):
+    return ("T7 default mix, auto threshold, %d streams x %d MiB u8 IQ per GPU, 1.536 MS/s, telegram every 10 s, "
+            "noise sigma %.1f LSB" % (args.streams, args.mib, args.sigma))
+
+
+# ------------------------------------------------------------------------------------------------- data
+def stream_bursts(stream_id, n_samples):
+    """telegram schedule of one stream: (raw sample offset, sensor, frame bytes)"""
+    import iqsynth as g
+    rng = np.random.default_rng(1000 + stream_id)
+    out, at, k = [], (stream_id * 60000) % PERIOD + 100000, stream_id
+    while at + 400000 < n_samples:
+        s = SENSORS[k % len(SENSORS)]
+        out.append(g.Burst(at, s, g.random_frame(s, rng), {"amp": 100}))
+        at += PERIOD
+        k += 1
+    return out
+
+
+def make_stream_gpu(stream_id, nbytes, sigma, device):
+    """u8 IQ on the GPU: rounded Gaussian noise (torch generator, seeded per stream) + integer-exact bursts"""
+    import torch
+    import iqsynth as g
+    gen = torch.Generator(device=device)
+    gen.manual_seed(77000 + stream_id)
+    n_samples = nbytes // 2
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    chunk = 1 << 26
+    bursts = stream_bursts(stream_id, n_samples)
+    rendered = [(b.at, *g.render_burst(b)) for b in bursts]
+    for off in range(0, nbytes, chunk):
+        n = min(chunk, nbytes - off)
+        x = torch.randn(n, device=device, generator=gen).mul_(sigma).round_().to(torch.int16)
+        for at, bi, bq in rendered:
+            lo, hi = 2 * at, 2 * (at + len(bi))
+            a, b = max(lo, off), min(hi, off + n)
+            if a >= b:
+                continue
+            iq = np.empty(2 * len(bi), dtype=np.int16)
+            iq[0::2], iq[1::2] = bi, bq
+            x[a - off:b - off] += torch.from_numpy(iq[a - lo:b - lo]).to(device)
+        buf[off:off + n] = (x + 128).clamp_(0, 255).to(torch.uint8)
+        del x
+    return buf, len(bursts)
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def n_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def write_sample_files(td, n_files, nbytes, sigma):
+    """bounded CPU sample: stream k's first nbytes, regenerated on the host with the same schedule"""
+    import iqsynth as g
+    paths = []
+    for k in range(n_files):
+        iq = g.make_stream(nbytes // 2, [b for b in stream_bursts(k, nbytes // 2)], seed=77000 + k, sigma=sigma)
+        p = os.path.join(td, "s%d.iq" % k)
+        iq.tofile(p)
+        paths.append(p)
+    return paths
+
+
+def run_reference_once(paths):
+    """one reference process per file/core, all in parallel; returns (wall seconds, decoded telegram lines)"""
+    t0 = time.perf_counter()
+    procs = []
+    for k, p in enumerate(paths):
+        cmd = [REF_BIN, "-T", "%x" % TYPES_MASK, "-L", p]
+        if os.path.exists("/usr/bin/taskset"):
+            cmd = ["taskset", "-c", str(sorted(os.sched_getaffinity(0))[k % n_cores()])] + cmd
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL))
+    outs = [pr.communicate()[0] for pr in procs]
+    dt = time.perf_counter() - t0
+    lines = sum(sum(1 for ln in o.decode("latin1").splitlines() if ln.startswith(("TFA1 ID", "TFA2 ID", "TFA3 ID")))
+                for o in outs)
+    return dt, lines
+
+
+def cpu_baseline(sigma, sample_mib=256, gpu_bufs=None):
+    """the unmodified reference on all host cores, one process per core, each on the first sample_mib MiB of one
+    of THIS run's stream buffers (copied back from the GPU, so the bytes are the ones the GPU decoded)"""
+    cores = n_cores()
+    sample_mib = max(16, min(sample_mib, 8192 // cores))
+    if not os.path.exists(REF_BIN):
+        return {"value": None, "unit": "MSamples/s", "cores": cores, "kind": "reference",
+                "sample": "oracle/_ref/tfrec missing (build it with `make -C oracle ref` where /root/reference exists)"}
+    nbytes = sample_mib << 20
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        if gpu_bufs:
+            paths = []
+            nbytes = min(nbytes, int(gpu_bufs[0].numel()))
+            for k in range(cores):
+                p = os.path.join(td, "s%d.iq" % k)
+                gpu_bufs[k % len(gpu_bufs)][:nbytes].cpu().numpy().tofile(p)
+                paths.append(p)
+        else:
+            paths = write_sample_files(td, cores, nbytes, sigma)
+        run_reference_once(paths[:1])                    # page cache / binary warm-up
+        dt, lines = run_reference_once(paths)
+    sample_mib = nbytes >> 20
+    samples = cores * (nbytes // 2)
+    return {"value": round(samples / dt / 1e6, 2), "unit": "MSamples/s", "cores": cores, "kind": "reference",
+            "telegrams_per_s": round(lines / dt, 3),
+            "sample": "unmodified reference `tfrec -T 7 -L` (auto threshold), %d processes x %d MiB (first %d MiB of "
+                      "streams 0..%d of this workload), wall %.2f s" % (cores, sample_mib, sample_mib, cores - 1, dt)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = n_cores()
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tfrec not built"}))
+        return
+    sample_mib = max(8, min(args.ref_mib, 8192 // cores))
+    nbytes = sample_mib << 20
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        paths = write_sample_files(td, cores, nbytes, args.sigma)
+        for _ in range(args.warmup):
+            run_reference_once(paths)
+        tot, lines = 0.0, 0
+        for _ in range(args.steps):
+            dt, ln = run_reference_once(paths)
+            tot += dt
+            lines += ln
+    samples = cores * (nbytes // 2) * args.steps
+    v = samples / tot / 1e6
+    out = {"impl": "reference", "metric": "iq_msamples_per_s", "value": round(v, 2), "unit": "MSamples/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * tot / args.steps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/f64", "data": "synthetic",
+           "telegrams_per_s": round(lines / tot, 3),
+           "config": {"workload": workload_name(args), "step": "bounded sample: %d processes x %d MiB" % (cores, sample_mib)},
+           "cpu_baseline": {"value": round(v, 2), "unit": "MSamples/s", "cores": cores, "kind": "reference",
+                            "sample": "unmodified reference `tfrec -T 7 -L`, %d processes x %d MiB per step" % (cores, sample_mib)},
+           "e2e": {"value": round(v, 2), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=32, help="streams per GPU")
+    ap.add_argument("--mib", type=int, default=128, help="MiB of u8 IQ per stream per step")
+    ap.add_argument("--sigma", type=float, default=4.0)
+    ap.add_argument("--thresh", type=int, default=0, help="0 = auto (reference default)")
+    ap.add_argument("--ref-mib", type=int, default=64, help="reference arm: MiB per process per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import tfrec_b200 as tb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: the decode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nbytes = args.mib << 20
+    S = args.streams
+    bufs, sent = [], 0
+    for s in range(S):
+        b, n = make_stream_gpu(rank * S + s, nbytes, args.sigma, dev)
+        bufs.append(b)
+        sent += n
+    samples_per_step = S * (nbytes // 2)
+
+    rx = tb.Receiver(types=TYPES_MASK, thresh=args.thresh, n_streams=S, device=local, max_blocks_per_submit=nbytes // 65536)
+
+    def step_device():
+        for s in range(S):
+            rx.submit(s, bufs[s].data_ptr(), nbytes=nbytes)
+        rx.process()
+
+    # ---- resident-in-HBM pass ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+        rx.sync()
+        rx.clear()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = rx.stats()["kernel_launches"]
+    dev_ms = fe_ms = be_ms = 0.0
+    decoded = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+        rx.sync()
+        st = rx.stats()
+        dev_ms += st["last_total_ms"]
+        fe_ms += st["last_frontend_ms"]
+        be_ms += st["last_backend_ms"]
+        decoded += rx.n_records()
+        rx.clear()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = rx.stats()["kernel_launches"] - l0
+    t_dev = allmax(dev_ms / 1e3)
+    t_wall = allmax(wall)
+    total_samples = allsum(float(samples_per_step)) * args.steps
+    total_decoded = allsum(float(decoded))
+    total_sent = allsum(float(sent)) * args.steps
+    value = total_samples / t_dev / 1e6
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [b.cpu().pin_memory() for b in bufs]
+        for _ in range(2):
+            for s in range(S):
+                rx.submit_host_ptr(s, host[s].data_ptr(), nbytes)
+            rx.process()
+            rx.records()
+            rx.clear()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            for s in range(S):
+                rx.submit_host_ptr(s, host[s].data_ptr(), nbytes)
+            rx.process()
+            fr = rx.frames()
+            rc = rx.records()
+            d2h += 112 * len(fr) + 64 * len(rc) + 24
+            rx.clear()
+        barrier()
+        t_e2e = allmax(time.perf_counter() - t0)
+        e2e = {"value": round(total_samples / t_e2e / 1e6, 2), "unit": "MSamples/s",
+               "h2d_bytes_per_step": int(S * nbytes), "d2h_bytes_per_step": int(d2h // max(args.steps, 1)),
+               "ms_per_step": round(1e3 * t_e2e / args.steps, 3)}
+        del host
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the front-end kernel -------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = 2.0 * samples_per_step * args.steps / (fe_ms / 1e3) / 1e9   # rank 0's kernel
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "frontend_traffic.json")))
+        traffic = tj.get("dram_bytes_per_algorithmic_byte")
+    except Exception:
+        pass
+    roofline = {"kernel": "frontend_kernel<narrow>", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "traffic": (None if traffic is None else round(traffic * 2.0 * samples_per_step, 0)),
+                "algorithmic_bytes_per_step": int(2 * samples_per_step),
+                "frontend_ms_per_step": round(fe_ms / args.steps, 4), "backend_ms_per_step": round(be_ms / args.steps, 4)}
+
+    out = {"metric": "iq_msamples_per_s", "value": round(value, 2), "unit": "MSamples/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_dev / args.steps, 4),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->i16 (exact fp32 FMA.RM), f64 demod",
+           "data": "synthetic",
+           "config": {"workload": workload_name(args), "streams_per_gpu": S, "bytes_per_stream": nbytes,
+                      "l2": "inputs (%.1f GiB per GPU) are far larger than the 126 MB L2" % (S * nbytes / 2**30),
+                      "types": "0x07", "thresh": args.thresh},
+           "telegrams_per_s": round(total_decoded / t_dev, 2), "telegrams_decoded": int(total_decoded),
+           "telegrams_sent": int(total_sent), "wall_ms_per_step": round(1e3 * t_wall / args.steps, 4),
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.sigma, gpu_bufs=bufs)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

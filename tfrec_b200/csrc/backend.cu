@@ -19,50 +19,9 @@
 #include <math.h>
 #include <stdint.h>
 
-#include "tfr_dev.h"
+#include "demod_dev.cuh"
 
 namespace tfr {
-
-// carry_in (samples at the head of the first block of this epoch that an earlier trigger still covers)
-// as it stood when the epoch began: from the stream state for the first block of a submit, else from the
-// previous block's descriptor.  Only submit_epilogue_kernel advances the stream-level copy.
-__device__ __forceinline__ int entry_carry(const BackParams &p, const StreamJob &job, const StreamState *st)
-{
-	if (p.tile0 == 0) return st->carry_in;
-	return p.tiles[(size_t)job.dec_off + p.tile0 - 1].carry_out;
-}
-
-// ------------------------------------------------------------------------------------------------
-// region enumeration: the samples of a block the front-end kept = [0, carry_in) U segments
-// ------------------------------------------------------------------------------------------------
-struct Regions {
-	int n;
-	int start[kMaxSeg + 1];
-	int end[kMaxSeg + 1];
-};
-__device__ __forceinline__ void build_regions(const TileDesc &td, int carry_in, Regions &r)
-{
-	r.n = 0;
-	int cur_s = 0, cur_e = carry_in;   // may be empty
-	const int ns = td.n_seg;
-	for (int k = 0; k < ns; k++) {
-		const int s = td.seg_start[k], e = s + td.seg_len[k];
-		if (cur_e > cur_s && s <= cur_e) {
-			cur_e = max(cur_e, e);
-		} else {
-			if (cur_e > cur_s) { r.start[r.n] = cur_s; r.end[r.n] = cur_e; r.n++; }
-			cur_s = s;
-			cur_e = e;
-		}
-	}
-	if (cur_e > cur_s) { r.start[r.n] = cur_s; r.end[r.n] = cur_e; r.n++; }
-}
-
-__device__ __forceinline__ int pwr_of(uint32_t w)
-{
-	const int i = (int)(int16_t)(w & 0xffff), q = (int)(int16_t)(w >> 16);
-	return abs(i) + abs(q);
-}
 
 // ------------------------------------------------------------------------------------------------
 // thresh_kernel: one warp per stream
@@ -147,329 +106,6 @@ __global__ void thresh_kernel(const BackParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// discriminators and biquad
-// ------------------------------------------------------------------------------------------------
-// fm_dev_nrzs, dsp_stuff.cpp:269-279
-__device__ __forceinline__ int fm_dev_nrzs(int ar, int aj, int br, int bj)
-{
-	int cr = ar * br + aj * bj;
-	if (cr > 1000000000) cr = 1000000000;
-	if (cr < -1000000000) cr = -1000000000;
-	return cr;
-}
-
-// fm_dev, dsp_stuff.cpp:284-292.  The products are exact in double; what matters is the sign of a zero
-// result (decides the +-pi branch) and the value atan2 returns on the axes and diagonals, where
-// angle*16384/pi lands exactly on an integer before truncation.  Those cases return glibc's values.
-__device__ __forceinline__ int fm_dev(int ar, int aj, int br, int bj)
-{
-	const double cr = __dadd_rn(__dmul_rn((double)aj, (double)bj), __dmul_rn((double)ar, (double)br));
-	const double cj = __dsub_rn(__dmul_rn((double)br, (double)aj), __dmul_rn((double)ar, (double)bj));
-	// what glibc's atan2 returns for (0,-1), (1,0), (1,1), (1,-1)
-	const double PI = 0x1.921fb54442d18p+1, PI_2 = 0x1.921fb54442d18p+0, PI_4 = 0x1.921fb54442d18p-1,
-		     PI3_4 = 0x1.2d97c7f3321d2p+1;
-	double ang;
-	if (cj == 0.0) {
-		ang = (cr > 0.0 || (cr == 0.0 && !signbit(cr))) ? cj : copysign(PI, cj);
-	} else if (cr == 0.0) {
-		ang = copysign(PI_2, cj);
-	} else if (fabs(cj) == fabs(cr)) {
-		ang = copysign(cr > 0.0 ? PI_4 : PI3_4, cj);
-	} else {
-		ang = atan2(cj, cr);
-	}
-	return __double2int_rz(__dmul_rn(ang, 5215.189175235227));   // fl(16384/pi), see header
-}
-
-// iir2::step, dsp_stuff.cpp:47-55, association as built
-__device__ __forceinline__ double biquad_step(Biquad &f, const BiquadCoef &k, double dn)
-{
-	const double t1 = __dadd_rn(__dmul_rn(k.b2, f.d2), __dmul_rn(k.a1, f.y0));
-	const double t2 = __dadd_rn(__dmul_rn(k.b0, dn), __dmul_rn(k.b1, f.d1));
-	const double y = __dadd_rn(__dadd_rn(t1, t2), __dmul_rn(k.a2, f.y1));
-	f.y1 = f.y0;
-	f.y0 = y;
-	f.d2 = f.d1;
-	f.d1 = dn;
-	return y;
-}
-
-// ------------------------------------------------------------------------------------------------
-// walker context
-// ------------------------------------------------------------------------------------------------
-struct Walk {
-	const BackParams *p;
-	int stream, demod;
-	int64_t pos;          // 384 kS/s position of the current sample
-	DemodState s;
-	uint32_t tap_n[3];
-};
-
-__device__ __forceinline__ void tap_i32(Walk &w, int kind, int v)
-{
-	if (!w.p->tap_cap) return;
-	const uint32_t n = w.tap_n[kind]++;
-	if (n < w.p->tap_cap)
-		w.p->tap_i32[kind][((size_t)w.stream * kMaxDemods + w.demod) * w.p->tap_cap + n] = v;
-}
-__device__ __forceinline__ void tap_f64(Walk &w, double v)
-{
-	if (!w.p->tap_cap) return;
-	const uint32_t n = w.tap_n[2]++;
-	if (n < w.p->tap_cap) w.p->tap_f64[((size_t)w.stream * kMaxDemods + w.demod) * w.p->tap_cap + n] = v;
-}
-
-// a decoder::flush that passed its length gate becomes a candidate frame for parse_kernel
-__device__ void emit_frame(Walk &w, double rssi_raw, int offset)
-{
-	const uint32_t k = atomicAdd(&w.p->counters->n_frames, 1u);
-	if (k >= w.p->max_frames) {
-		w.p->counters->overflow = 1;
-		return;
-	}
-	DevFrame &f = w.p->frames[k];
-	f.stream = w.stream;
-	f.demod = w.demod;
-	f.type = w.p->cfg->d[w.demod].type;
-	f.status = -1;
-	f.byte_cnt = w.s.byte_cnt;
-	f.offset = offset;
-	f.n_records = 0;
-	f.first_record = 0;
-	f.pos = w.pos;
-	f.rssi_raw = rssi_raw;
-	for (int n = 0; n < kMaxRdata; n++) f.rdata[n] = w.s.rdata[n];
-}
-
-// ---- TFA_1 ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void tfa1_bit(DemodState &s, int bit)
-{
-	s.sr = (s.sr >> 1) | ((uint32_t)bit << 31);
-	if ((s.sr & 0xffff) == 0xd42d) {
-		s.sr_cnt = 0;
-		s.byte_cnt = 0;
-	}
-	if (s.sr_cnt == 0) {
-		if (s.byte_cnt < kRdataBytes) s.rdata[s.byte_cnt] = (uint8_t)(s.sr & 0xff);
-		s.byte_cnt++;
-	}
-	if (s.sr_cnt >= 0) s.sr_cnt = (s.sr_cnt + 1) & 7;
-}
-__device__ void tfa1_flush(Walk &w)
-{
-	DemodState &s = w.s;
-	if (s.byte_cnt >= 10) emit_frame(w, (double)s.rssi_i, 0);
-	s.sr_cnt = -1;
-	s.byte_cnt = 0;
-	s.rdata[10] = 0;
-}
-__device__ __forceinline__ void tfa1_sample(Walk &w, int thresh, int pwr, int index, int i, int q, int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) s.timeout_cnt = 400;   // 40*BITPERIOD, tfa1.cpp:34,148
-	if (!s.timeout_cnt) return;
-	const int dev = fm_dev_nrzs(i, q, li, lq);
-	tap_i32(w, 1, dev);
-	if (dev > s.mark_lvl) s.mark_lvl = dev;
-	else s.mark_lvl = __double2int_rz(__dmul_rn((double)s.mark_lvl, 0.95));
-	if (s.mark_lvl > s.rssi_i) s.rssi_i = s.mark_lvl;
-	s.timeout_cnt--;
-	if (dev < s.mark_lvl / 2) {
-		if (s.last_bit_idx) {
-			const int gap = index - s.last_bit_idx;
-			if (gap > 4) {
-				for (int n = 22; n <= gap; n += 20) tfa1_bit(s, 1);
-				tfa1_bit(s, 0);
-			}
-		}
-		if (index - s.last_bit_idx > 2) s.last_bit_idx = index;
-	}
-	if (!s.timeout_cnt) {
-		tfa1_flush(w);
-		s.mark_lvl = 0;
-		s.rssi_i = 0;
-		s.last_bit_idx = 0;
-	}
-}
-
-// ---- TFA_2 / TFA_3 / TX22 ---------------------------------------------------------------------------
-__device__ __forceinline__ void tfa2_bit(DemodState &s, int bit)
-{
-	s.sr = (s.sr << 1) | (uint32_t)bit;
-	if ((s.sr & 0xffff) == 0x2dd4) {
-		s.sr_cnt = 0;
-		s.rdata[0] = (uint8_t)((s.sr >> 8) & 0xff);
-		s.byte_cnt = 1;
-		s.invert = 0;
-	}
-	if (((~s.sr) & 0xffff) == 0x2dd4) {
-		s.sr_cnt = 0;
-		s.rdata[0] = (uint8_t)~((s.sr >> 8) & 0xff);
-		s.byte_cnt = 1;
-		s.invert = 1;
-	}
-	if (s.sr_cnt == 0) {
-		if (s.byte_cnt < kRdataBytes)
-			s.rdata[s.byte_cnt] = s.invert ? (uint8_t)~(s.sr & 0xff) : (uint8_t)(s.sr & 0xff);
-		s.byte_cnt++;
-	}
-	if (s.sr_cnt >= 0) s.sr_cnt = (s.sr_cnt + 1) & 7;
-}
-__device__ __forceinline__ void tfa2_reset(DemodState &s)
-{
-	s.offset = 0;
-	s.bitcnt = 0;
-	s.dmin = 32767;
-	s.dmax = -32767;
-	s.last_bit = 0;
-	s.rssi_i = 0;
-}
-__device__ void tfa2_flush(Walk &w, int kind)
-{
-	DemodState &s = w.s;
-	const bool gate = (kind == K_TX22) ? (s.byte_cnt >= 7 && s.byte_cnt < 64) : (s.byte_cnt >= 7);
-	if (gate) emit_frame(w, (double)s.rssi_i, s.offset);
-	s.sr_cnt = -1;
-	s.sr = 0;
-	s.byte_cnt = 0;
-}
-__device__ __forceinline__ void tfa2_sample(Walk &w, const DemodCfg &cfg, int thresh, int pwr, int index, int i, int q,
-					    int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) {
-		if (!s.timeout_cnt) tfa2_reset(s);
-		s.timeout_cnt = cfg.timeout;
-	}
-	if (!s.timeout_cnt) return;
-	const int dev0 = fm_dev(i, q, li, lq);
-	tap_i32(w, 0, dev0);
-	const double y = biquad_step(s.lp, cfg.lp, (double)dev0);
-	tap_f64(w, y);
-	const int ld = __double2int_rz(y);
-	if (s.bitcnt < 10) {
-		if (ld > s.dmax) s.dmax = (7 * s.dmax + ld) / 8;
-		if (ld < s.dmin) s.dmin = (7 * s.dmin + ld) / 8;
-		s.offset = (s.dmax + s.dmin) / 2;
-		if (s.bitcnt > 4) {
-			const uint32_t sum = (uint32_t)s.rssi_i + (uint32_t)(i * i) + (uint32_t)(q * q);
-			s.rssi_i = (int)((uint32_t)s.rssi_i + (uint32_t)((int)sum / 100));
-		}
-	}
-	s.timeout_cnt--;
-	const int dev = ld;
-	const int noffset = __double2int_rz(__dmul_rn(0.9, (double)s.offset));
-	const int hi = noffset + s.dmax / 32, lo = noffset + s.dmin / 32;
-	const int bit = dev > hi ? 1 : 0;
-	if ((dev > hi || dev < lo) && bit != s.last_bit) {
-		if (index > s.last_bit_idx + 8) {
-			s.bitcnt++;
-			const int tdiff = index - s.last_bit_idx;
-			if ((double)tdiff > __dmul_rn(cfg.spb, 0.25) && (double)tdiff < __dmul_rn(32.0, cfg.spb)) {
-				const int bit_diff = tdiff / 2;
-				const int numbits =
-					__double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, __dmul_rn(cfg.spb, 0.5)), cfg.spb));
-				if (numbits < 32)
-					for (int n = 1; n < numbits; n++) tfa2_bit(s, s.last_bit);
-				tfa2_bit(s, bit);
-				s.last_bit = bit;
-			}
-		}
-		if (index - s.last_bit_idx > 2) s.last_bit_idx = index;
-	}
-	if (!s.timeout_cnt) {
-		for (int n = 0; n < 16; n++) tfa2_bit(s, s.last_bit);
-		tfa2_flush(w, cfg.kind);
-		tfa2_reset(s);
-	}
-}
-
-// ---- WeatherHub ---------------------------------------------------------------------------------
-__device__ __forceinline__ void whb_bit(DemodState &s, int bit)
-{
-	if (bit == s.w_last_bit) s.w_psk = 1 - s.w_psk;
-	if (s.w_psk == s.w_last_psk) s.w_nrzs = 1 - s.w_nrzs;
-	s.w_last_bit = bit;
-	s.w_last_psk = s.w_psk;
-	const int d = s.w_nrzs ^ ((s.w_lfsr >> 16) & 1) ^ ((s.w_lfsr >> 11) & 1);
-	s.w_lfsr = (s.w_lfsr << 1) | (uint32_t)s.w_nrzs;
-	s.sr = (s.sr >> 1) | ((uint32_t)d << 31);
-	if (s.sr == 0x2bd42d4bu) {
-		s.synced = 1;
-		s.sr_cnt = 0;
-		s.rdata[0] = (uint8_t)(s.sr & 0xff);
-		s.rdata[1] = (uint8_t)((s.sr >> 8) & 0xff);
-		s.rdata[2] = (uint8_t)((s.sr >> 16) & 0xff);
-		s.byte_cnt = 3;
-	}
-	if (s.sr_cnt == 0) {
-		if (s.byte_cnt < kRdataBytes) s.rdata[s.byte_cnt] = (uint8_t)((s.sr >> 24) & 0xff);
-		s.byte_cnt++;
-	}
-	if (s.sr_cnt >= 0) s.sr_cnt = (s.sr_cnt + 1) & 7;
-}
-__device__ __forceinline__ void whb_reset(DemodState &s)
-{
-	s.offset = 0;
-	s.bitcnt = 0;
-	s.rssi_d = 0.0;
-	s.step_lo = 0;
-	s.last_peak = 0;
-}
-__device__ void whb_flush(Walk &w)
-{
-	DemodState &s = w.s;
-	if (!(s.byte_cnt < 11 || s.byte_cnt > 60)) emit_frame(w, s.rssi_d, s.offset);
-	s.sr_cnt = -1;
-	s.sr = 0;
-	s.byte_cnt = 0;
-	s.synced = 0;
-}
-__device__ __forceinline__ void whb_sample(Walk &w, const DemodCfg &cfg, int thresh, int pwr, int i, int q, int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) {
-		if (!s.timeout_cnt) whb_reset(s);
-		s.timeout_cnt = cfg.timeout;
-	}
-	if (s.timeout_cnt) {
-		const int dev0 = fm_dev_nrzs(i, q, li, lq);
-		tap_i32(w, 1, dev0);
-		const double y = biquad_step(s.lp, cfg.lp, (double)dev0);
-		tap_f64(w, y);
-		const int dev = __double2int_rz(y);
-		if (!s.synced) {
-			const double a = biquad_step(s.lp_avg, cfg.lp_avg, __dmul_rn(0.5, (double)dev));
-			tap_f64(w, a);
-			s.avg_of = __double2int_rz(a);
-		}
-		s.timeout_cnt--;
-		const int tdiff = (int)(s.step_lo - s.last_peak);
-		if (dev < s.avg_of && dev > s.last_dev && (double)tdiff > __dmul_rn(cfg.spb, 0.75)) {
-			whb_bit(s, 0);
-			s.bitcnt++;
-			const int bit0 = __double2int_rz(__ddiv_rn(__dadd_rn((double)tdiff, __dmul_rn(cfg.spb, 0.5)), cfg.spb));
-			for (int n = 1; n < bit0; n++) {
-				whb_bit(s, 1);
-				s.bitcnt++;
-			}
-			s.last_peak = s.step_lo;
-		}
-		s.last_dev = dev;
-		if (s.synced) s.rssi_d = __dadd_rn(s.rssi_d, (double)(i * i + q * q));
-		if (!s.timeout_cnt) {
-			if (s.synced) {
-				for (int n = 0; n < 16; n++) whb_bit(s, 0);
-				whb_flush(w);
-			}
-			whb_reset(s);
-			s.rssi_d = 0.0;
-		}
-	}
-	s.step_lo++;
-}
-
-// ------------------------------------------------------------------------------------------------
 // walk_kernel: one thread per (stream, demod), windows in stream order with carried state
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) walk_kernel(const BackParams p)
@@ -482,7 +118,9 @@ __global__ void __launch_bounds__(32) walk_kernel(const BackParams p)
 	w.stream = gid / nd;
 	w.demod = gid % nd;
 	const DemodCfg cfg = p.cfg->d[w.demod];
+	if (cfg.kind != K_WHB) return;   // TFA_1 / TFA_2 family run window-parallel in backend2.cu
 	const StreamJob job = p.jobs[w.stream];
+	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + w.stream;
 	w.s = st->d[w.demod];
 	for (int k = 0; k < 3; k++) w.tap_n[k] = p.tap_cap ? p.tap_cnt[((size_t)w.stream * kMaxDemods + w.demod) * 3 + k] : 0;

@@ -1,0 +1,1030 @@
+// backend2.cu - the parallel back-end.
+//
+// The reference runs every demodulator as one serial state machine over the stream.  What is actually
+// serial is small: a demodulator only runs inside *windows* (a trigger at sample t keeps it active for
+// t .. t+T_d-1, retriggerable: tfa1.cpp:147-148, tfa2.cpp:351-356), window extents are a pure function
+// of the trigger positions, and almost all demodulator state is reset when a window closes.  What does
+// survive a window boundary is
+//     TFA_1            the decoder's 32-bit shift register            (tfa1.cpp:115-117)
+//     TFA_2/3, TX22    the biquad state and last_bit_idx              (tfa2.cpp:325-334)
+// So:  thresh2_kernel  walks the per-block trigger EVENT lists the front-end wrote (cheap), reproduces
+//                      fsk_demod::process' per-block bookkeeping (fm_demod.cpp:51-73) and lists every
+//                      demodulator's windows (start, end) in stream order;
+//      devfm_kernel    computes fm_dev (dsp_stuff.cpp:284-292, FP64 atan2) for every stored sample, in parallel;
+//      win_kernel      ONE THREAD PER WINDOW runs slicer + framer with a *speculated* carry-in: the shift
+//                      register is assumed empty, last_bit_idx is assumed far in the past, and the biquad is
+//                      warmed up over the preceding windows' samples; each run records what is needed to
+//                      check those assumptions;
+//      verify_kernel   one thread per (stream, demod) walks the window records in order with the TRUE carried
+//                      state, proves for each window that its assumed carry-in was equivalent to the true
+//                      one (bitwise for the biquad outputs) and re-runs the window inline when it was not.
+// The result is exact by construction; speculation only decides how often the slow path is taken
+// (Counters::n_reruns).  WeatherHub keeps the serial walker of backend.cu (its 0.0025/spb averaging
+// biquad, whb.cpp:611, remembers ~10^5 samples, so windows are not independent in any useful sense).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "demod_dev.cuh"
+
+namespace tfr {
+
+
+// ------------------------------------------------------------------------------------------------
+// thresh2_kernel: one warp per stream
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
+{
+	const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (stream >= p.n_streams) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const DevConfig &cfg = *p.cfg;
+	const int t_max = cfg.t_max;
+	const int nd = cfg.n_demods;
+	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
+
+	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs;
+	int c = st->any_timeout;              // samples from `cursor` on that are still covered by a trigger
+	const int mode = st->thresh_mode;
+	long long last_trig;                  // position of the latest trigger (negative: in an earlier call)
+	// per-demod window bookkeeping lives in lane d
+	const int T_d = (lane < nd) ? cfg.d[lane].timeout : 0x7fffffff;
+	uint32_t n_win = 0, cum = 0, open = 0;
+	WinEntry *wl = (lane < nd) ? p.wins + job.win_off + (size_t)lane * job.win_cap : nullptr;
+	if (p.tile0 == 0) {
+		last_trig = -(long long)st->trig_age;
+		if (lane < nd && st->d[lane].timeout_cnt > 0) {   // a window was open when the previous call ended
+			WinEntry e = { 0u, 0xffffffffu, 0u, kWinCont };
+			wl[0] = e;
+			n_win = 1;
+			open = 1;
+		}
+	} else {
+		last_trig = st->call_last_trig;
+		if (lane < nd) {
+			n_win = st->win_n[lane];
+			cum = st->win_cum[lane];
+			open = st->win_open[lane];
+		}
+	}
+	unsigned long long act_total = 0;
+	const int t_end = min(p.tile0 + p.n_tiles, (int)job.n_blocks);
+
+	// one trigger at position t (inside the call): coverage for the "any demod active" count and window lists
+	auto on_trigger = [&](uint32_t t, uint32_t &cursor, int &triggered) {
+		const int gap = (int)(t - cursor), use = min(c, gap);
+		triggered += use;
+		c = t_max;
+		cursor = t;
+		if (lane < nd) {
+			if (!open || (long long)t - last_trig >= T_d) {
+				if (open) {   // close the previous window: it flushed T_d-1 samples after its last trigger
+					const uint32_t end = (uint32_t)(last_trig + T_d - 1);
+					wl[n_win - 1].end = end;
+					cum += end - wl[n_win - 1].start + 1;
+				}
+				if (n_win < job.win_cap) {
+					WinEntry e = { t, 0xffffffffu, cum, 0u };
+					wl[n_win] = e;
+					n_win++;
+				} else {
+					p.counters->overflow = 1;
+				}
+				open = 1;
+			}
+		}
+		last_trig = t;
+	};
+
+	// blocks are taken 32 at a time: lane L fetches block L's trigger count and first four events up front, so
+	// that the serial walk below touches memory only for blocks with more than four events
+	for (int tile0 = p.tile0; tile0 < t_end; tile0 += 32) {
+	uint32_t my_n = 0;
+	uint4 my_ev = make_uint4(0, 0, 0, 0);
+	if (tile0 + lane < t_end) {
+		const size_t g = (size_t)job.dec_off + tile0 + lane;
+		my_n = p.tiles[g].n_trig;
+		if (my_n) my_ev = *reinterpret_cast<const uint4 *>(p.events + g * kMaxEvt);
+	}
+	const int tile_hi = min(tile0 + 32, t_end);
+	for (int tile = tile0; tile < tile_hi; tile++) {
+		const size_t gtile = (size_t)job.dec_off + tile;
+		const TileDesc &td = p.tiles[gtile];
+		const int src_lane = tile - tile0;
+		const uint32_t n_trig = __shfl_sync(0xffffffffu, my_n, src_lane);
+		const uint32_t base = (uint32_t)tile * kBlockDec;
+		uint32_t cursor = base;
+		int triggered = 0;
+		if (n_trig <= 4u) {
+			const uint32_t q0 = __shfl_sync(0xffffffffu, my_ev.x, src_lane), q1 = __shfl_sync(0xffffffffu, my_ev.y, src_lane);
+			const uint32_t q2 = __shfl_sync(0xffffffffu, my_ev.z, src_lane), q3 = __shfl_sync(0xffffffffu, my_ev.w, src_lane);
+			for (uint32_t j = 0; j < n_trig; j++) {
+				const uint32_t e = (j == 0) ? q0 : (j == 1) ? q1 : (j == 2) ? q2 : q3;
+				if ((int)(e & 0xffff) > thresh) on_trigger(base + (e >> 16), cursor, triggered);
+			}
+		} else if (n_trig <= (uint32_t)kMaxEvt) {
+			// sparse block: walk the event list; lanes hold 4 events each
+			const uint32_t *ev = p.events + gtile * kMaxEvt;
+			uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+			if ((uint32_t)lane < n_trig) e0 = ev[lane];
+			if ((uint32_t)lane + 32 < n_trig) e1 = ev[lane + 32];
+			if ((uint32_t)lane + 64 < n_trig) e2 = ev[lane + 64];
+			if ((uint32_t)lane + 96 < n_trig) e3 = ev[lane + 96];
+			for (uint32_t j = 0; j < n_trig; j++) {
+				const uint32_t src = (j < 32) ? e0 : (j < 64) ? e1 : (j < 96) ? e2 : e3;
+				const uint32_t e = __shfl_sync(0xffffffffu, src, j & 31);
+				if ((int)(e & 0xffff) > thresh) on_trigger(base + (e >> 16), cursor, triggered);
+			}
+		} else {
+			// dense block (a burst): scan the stored samples 32 at a time.  Every sample of the block that can
+			// be a trigger is stored (it lies in a segment), so scanning the segments is enough.
+			const uint32_t *d = p.dec + gtile * kBlockDec;
+			const int ns = td.n_seg;
+			for (int sgi = 0; sgi < ns; sgi++) {
+				const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+				for (int m0 = a; m0 < b; m0 += 32) {
+					const int m = m0 + lane;
+					const bool t = (m < b) && (pwr_of(d[m]) > thresh);
+					const unsigned mask = __ballot_sync(0xffffffffu, t);
+					if (mask) {
+						const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
+						on_trigger(base + m0 + pf, cursor, triggered);
+						if (pl != pf) {   // later triggers of the chunk are < 32 apart: they only move the tail
+							triggered += pl - pf;
+							cursor = base + m0 + pl;
+							c = t_max;
+							last_trig = base + m0 + pl;
+						}
+					}
+				}
+			}
+		}
+		{
+			const int gap = (int)(base + kBlockDec - cursor), use = min(c, gap);
+			triggered += use;
+			c -= use;
+		}
+		// fm_demod.cpp:58-73
+		runs++;
+		const int used = thresh;
+		avg = (31 * avg + triggered) / 32;
+		if (mode == 1 && (runs & 3) == 0) {
+			if (avg >= kIdxPerBlock / 32) thresh += 2;
+			else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
+		}
+		if (lane == 0) {
+			BlockTrace bt = { used, triggered, avg };
+			p.trace[gtile] = bt;
+		}
+		act_total += (unsigned long long)triggered;
+	}
+	}
+
+	if (p.last_epoch && lane < nd) {
+		if (open) {
+			const long long end = last_trig + T_d - 1;   // >= 0 because an open window means last_trig > -T_d
+			wl[n_win - 1].end = (uint32_t)end;
+			cum += (uint32_t)end - wl[n_win - 1].start + 1;
+		}
+	}
+	if (lane < nd) {
+		st->win_n[lane] = n_win;
+		st->win_cum[lane] = cum;
+		st->win_open[lane] = open;
+	}
+	if (lane == 0) {
+		st->thresh = thresh;
+		st->triggered_avg = avg;
+		st->runs = runs;
+		st->any_timeout = c;
+		st->call_last_trig = (int32_t)max(last_trig, (long long)INT32_MIN / 2);
+		if (p.last_epoch) {
+			const long long age = (long long)call_len - last_trig;
+			st->trig_age = (int32_t)min(age, (long long)INT32_MAX / 2);
+		}
+		if (act_total) atomicAdd(&p.counters->active_samples, act_total);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// devfm_kernel: fm_dev for every stored sample of a block (one CTA per block)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) devfm_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y;
+	const StreamJob job = p.jobs[stream];
+	const int tile = blockIdx.x;
+	if (tile >= (int)job.n_blocks) return;
+	const size_t gtile = (size_t)job.dec_off + tile;
+	const TileDesc &td = p.tiles[gtile];
+	const int carry_in = (tile == 0) ? p.st[stream].carry_in : p.tiles[gtile - 1].carry_out;
+	__shared__ Regions reg;
+	if (threadIdx.x == 0) build_regions(td, carry_in, reg);
+	__syncthreads();
+	const uint32_t *d = p.dec + gtile * kBlockDec;
+	int32_t *o = p.devfm + gtile * kBlockDec;
+	uint32_t prev_last;
+	if (tile == 0) prev_last = ((uint32_t)(uint16_t)p.st[stream].last_i) | ((uint32_t)(uint16_t)p.st[stream].last_q << 16);
+	else prev_last = d[-1];   // the previous block's last sample is always stored
+	for (int r = 0; r < reg.n; r++) {
+		const int a = reg.start[r], b = reg.end[r];
+		for (int m = a + threadIdx.x; m < b; m += blockDim.x) {
+			const uint32_t cw = d[m], lw = (m == 0) ? prev_last : d[m - 1];
+			o[m] = fm_dev((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
+				      (int)(int16_t)(lw >> 16));
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// window context shared by the speculative kernels and the verifier's slow path
+// ------------------------------------------------------------------------------------------------
+struct WinCtx {
+	const BackParams *p;
+	int stream, demod;
+	const uint32_t *dec;     // this stream's sparse decimated samples, indexed by position in the call
+	const int32_t *devfm;
+	uint32_t call_len;
+	uint32_t prev_last;      // sample before position 0
+	int64_t base_pos;        // blocks_done * 8192
+};
+
+static __device__ int put_frame(const WinCtx &c, int reuse, const DemodState &s, uint32_t pos, double rssi_raw, int offset)
+{
+	uint32_t k = (uint32_t)reuse;
+	if (reuse < 0) {
+		k = atomicAdd(&c.p->counters->n_frames, 1u);
+		if (k >= c.p->max_frames) {
+			c.p->counters->overflow = 1;
+			return -1;
+		}
+	}
+	DevFrame &f = c.p->frames[k];
+	f.stream = c.stream;
+	f.demod = c.demod;
+	f.type = c.p->cfg->d[c.demod].type;
+	f.status = -1;
+	f.byte_cnt = s.byte_cnt;
+	f.offset = offset;
+	f.n_records = 0;
+	f.first_record = 0;
+	f.pos = c.base_pos + pos;
+	f.rssi_raw = rssi_raw;
+	for (int n = 0; n < kMaxRdata; n++) f.rdata[n] = s.rdata[n];
+	return (int)k;
+}
+// a re-run that no longer yields a frame retires the slot its first run claimed
+static __device__ void drop_frame(const WinCtx &c, int idx)
+{
+	if (idx >= 0) c.p->frames[idx].status = -2;
+}
+
+// last_bit_idx bookkeeping: the reference keeps it relative to the current block and subtracts len at every
+// block start unless it is 0 (demodulator::start, decoder.cpp:118-122) - so 0 stays 0 forever
+__device__ __forceinline__ int lbi_at_block(int v, int vblock, int block)
+{
+	if (v == 0) return 0;
+	const long long r = (long long)v - (long long)kIdxPerBlock * (block - vblock);
+	return (int)max(r, (long long)INT32_MIN / 2);
+}
+
+// ---- TFA_1 window ------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// The serial walks read the sparse buffers 16 samples per iteration with 128-bit loads (all four in flight
+// together), so one L2 round trip is paid per 16 samples instead of per sample.  Chunks are 16-aligned and
+// never cross the end of the call (a call is a whole number of 8192-sample blocks).
+struct Chunk16 { int v[16]; };
+__device__ __forceinline__ Chunk16 load16(const int32_t *p)
+{
+	Chunk16 c;
+	const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
+	const int4 d = reinterpret_cast<const int4 *>(p)[2], e = reinterpret_cast<const int4 *>(p)[3];
+	c.v[0] = a.x; c.v[1] = a.y; c.v[2] = a.z; c.v[3] = a.w; c.v[4] = b.x; c.v[5] = b.y; c.v[6] = b.z; c.v[7] = b.w;
+	c.v[8] = d.x; c.v[9] = d.y; c.v[10] = d.z; c.v[11] = d.w; c.v[12] = e.x; c.v[13] = e.y; c.v[14] = e.z; c.v[15] = e.w;
+	return c;
+}
+// Order-sensitive hash of the slicer input sequence: sum of ld[i] * (2i+1)*K mod 2^64.  Additive, so the
+// terms do not form a dependency chain (the walks are latency bound); a change of one element by d moves the
+// sum by d*(2i+1)*K != 0, two changes cannot cancel unless i == j.
+constexpr unsigned long long kHashK = 0x9E3779B97F4A7C15ull;
+__device__ __forceinline__ unsigned long long ld_term(int ld, uint32_t i)
+{
+	return (unsigned long long)(long long)ld * ((2ull * i + 1ull) * kHashK);
+}
+// exact int -> double without the (slow, variable latency) I2F.F64: 2^52 + 2^31 + v, minus the offset
+__device__ __forceinline__ double int_to_double(int v)
+{
+	return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v + 0x80000000u)), 4503601774854144.0);
+}
+
+// tfa1_demod::demod, tfa1.cpp:143-190 over the samples [start, min(end, call_len-1)].
+// exact: s holds the true carried state (continuation or first window of the call); otherwise s.sr == 0
+// is a speculation that is checked with head31/nbits.
+static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, DemodState &s, WinRec &rec, bool resume)
+{
+	if (!resume) {
+		s.mark_lvl = 0;
+		s.rssi_i = 0;
+		s.last_bit_idx = 0;
+		s.sr_cnt = -1;
+		s.byte_cnt = 0;
+		s.rdata[10] = 0;
+	}
+	uint32_t head = 0;
+	int nbits = 0;
+	int mark = s.mark_lvl, rssi = s.rssi_i, lbi = s.last_bit_idx;   // hot state in registers
+	auto bit = [&](int b) {
+		if (nbits < 31) head |= (uint32_t)b << nbits;
+		nbits++;
+		tfa1_bit(s, b);
+	};
+	const uint32_t last = min(e.end, c.call_len - 1);
+	const bool taps = c.p->tap_cap != 0;
+	int32_t *tap = taps ? c.p->tap_i32[1] + ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap : nullptr;
+	uint32_t lw = (e.start == 0) ? c.prev_last : c.dec[e.start - 1];
+	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
+	const Chunk16 ck = load16(reinterpret_cast<const int32_t *>(c.dec) + cb);
+#pragma unroll 4
+	for (int kk = 0; kk < 16; kk++) {
+		const uint32_t m = cb + kk;
+		if (m < e.start || m > last) continue;
+		const int index = 2 * (int)(m & (kBlockDec - 1));
+		if (index == 0 && m != e.start && lbi) lbi -= kIdxPerBlock;
+		const uint32_t cw = (uint32_t)ck.v[kk];
+		const int dev = fm_dev_nrzs((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
+					    (int)(int16_t)(lw >> 16));
+		lw = cw;
+		if (taps) {
+			const uint32_t ti = e.cum + (m - e.start);
+			if (ti < c.p->tap_cap) tap[ti] = dev;
+		}
+		if (dev > mark) mark = dev;
+		else mark = __double2int_rz(__dmul_rn((double)mark, 0.95));
+		if (mark > rssi) rssi = mark;
+		if (dev < mark / 2) {
+			if (lbi) {
+				const int gap = index - lbi;
+				if (gap > 4) {
+					for (int n = 22; n <= gap; n += 20) bit(1);
+					bit(0);
+				}
+			}
+			if (index - lbi > 2) lbi = index;
+		}
+	}
+	}
+	s.mark_lvl = mark;
+	s.rssi_i = rssi;
+	s.last_bit_idx = lbi;
+	rec.head31 = head;
+	rec.nbits = nbits;
+	rec.sr_final = s.sr;
+	if (last == e.end) {
+		// tfa1_decoder::flush gate (tfa1.cpp:48); the parser runs in parse_kernel
+		int fi = -1;
+		if (s.byte_cnt >= 10) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, 0);
+		else drop_frame(c, rec.frame_idx);
+		rec.frame_idx = fi;
+		rec.flags = (rec.flags & kRecExact) | kRecRan;
+	} else {
+		s.timeout_cnt = (int)(e.end - last);
+		rec.flags = (rec.flags & kRecExact) | kRecRan | kRecUnfinished;
+	}
+}
+
+// ---- TFA_2 / TFA_3 / TX22 window ---------------------------------------------------------------------
+// tfa2_demod::demod, tfa2.cpp:346-442 over [start, min(end, call_len-1)].  `far`: last_bit_idx is assumed
+// to be so old that the first edge candidate only re-arms it (index > lbi+8 true, tdiff >= 32*spb).
+static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, const WinEntry &e, DemodState &s, WinRec &rec,
+				       bool resume, bool far)
+{
+	if (!resume) {
+		tfa2_reset(s);
+		s.sr_cnt = -1;
+		s.sr = 0;
+		s.byte_cnt = 0;
+	}
+	const uint32_t last = min(e.end, c.call_len - 1);
+	const bool taps = c.p->tap_cap != 0;
+	const size_t tbase = ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap;
+	bool have_edge = false;
+	rec.flags &= ~kRecEdge;
+	// hot state in registers
+	Biquad lp = s.lp;
+	const BiquadCoef k = cfg.lp;
+	int bitcnt = s.bitcnt, dmin = s.dmin, dmax = s.dmax, offset = s.offset, last_bit = s.last_bit, rssi = s.rssi_i,
+	    lbi = s.last_bit_idx;
+	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
+	unsigned long long hash = 0;
+	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
+	const Chunk16 ck = load16(c.devfm + cb);
+#pragma unroll 4
+	for (int kk = 0; kk < 16; kk++) {
+		const uint32_t m = cb + kk;
+		if (m < e.start || m > last) continue;
+		const int index = 2 * (int)(m & (kBlockDec - 1));
+		if (index == 0 && m != e.start && lbi) lbi -= kIdxPerBlock;
+		const int dev0 = ck.v[kk];
+		const double y = biquad_step(lp, k, int_to_double(dev0));
+		if (taps) {
+			const uint32_t ti = e.cum + (m - e.start);
+			if (ti < c.p->tap_cap) {
+				c.p->tap_i32[0][tbase + ti] = dev0;
+				c.p->tap_f64[tbase + ti] = y;
+			}
+		}
+		const int ld = __double2int_rz(y);
+		hash += ld_term(ld, m - e.start);
+		if (bitcnt < 10) {
+			if (ld > dmax) dmax = (7 * dmax + ld) / 8;
+			if (ld < dmin) dmin = (7 * dmin + ld) / 8;
+			offset = (dmax + dmin) / 2;
+			if (bitcnt > 4) {
+				const uint32_t cw = c.dec[m];
+				const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
+				const uint32_t sum = (uint32_t)rssi + (uint32_t)(i * i) + (uint32_t)(q * q);
+				rssi = (int)((uint32_t)rssi + (uint32_t)((int)sum / 100));
+			}
+		}
+		const int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+		const int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
+		const int bit = ld > hi ? 1 : 0;
+		if ((ld > hi || ld < lo) && bit != last_bit) {
+			if (far && !have_edge) {
+				// speculated: index > last_bit_idx+8, tdiff >= 32*spb  ->  bitcnt++, no bits, re-arm
+				rec.first_edge = index;
+				rec.first_edge_block = (int)(m >> 13);
+				rec.flags |= kRecEdge;
+				bitcnt++;
+				lbi = index;
+			} else {
+				if (index > lbi + 8) {
+					bitcnt++;
+					const int tdiff = index - lbi;
+					if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
+						const int bit_diff = tdiff / 2;
+						const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
+						if (numbits < 32)
+							for (int n = 1; n < numbits; n++) tfa2_bit(s, last_bit);
+						tfa2_bit(s, bit);
+						last_bit = bit;
+					}
+				}
+				if (index - lbi > 2) lbi = index;
+			}
+			have_edge = true;
+		}
+	}
+	}
+	s.lp = lp;
+	s.bitcnt = bitcnt; s.dmin = dmin; s.dmax = dmax; s.offset = offset; s.last_bit = last_bit; s.rssi_i = rssi;
+	s.last_bit_idx = lbi;
+	rec.e_y0 = lp.y0;
+	rec.e_y1 = lp.y1;
+	rec.ld_hash = hash;
+	rec.lbi_end = lbi;
+	rec.lbi_end_block = (int)(last >> 13);
+	if (!far && have_edge) rec.flags |= kRecEdge;
+	if (last == e.end) {
+		for (int n = 0; n < 16; n++) tfa2_bit(s, last_bit);
+		const bool gate = (cfg.kind == K_TX22) ? (s.byte_cnt >= 7 && s.byte_cnt < 64) : (s.byte_cnt >= 7);
+		int fi = -1;
+		if (gate) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, s.offset);
+		else drop_frame(c, rec.frame_idx);
+		rec.frame_idx = fi;
+		s.sr_cnt = -1;
+		s.sr = 0;
+		s.byte_cnt = 0;
+		tfa2_reset(s);
+		s.timeout_cnt = 0;
+		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan;
+	} else {
+		s.timeout_cnt = (int)(e.end - last);
+		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan | kRecUnfinished;
+	}
+}
+
+__device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int demod, const StreamJob &job, const StreamState *st)
+{
+	WinCtx c;
+	c.p = &p;
+	c.stream = stream;
+	c.demod = demod;
+	c.dec = p.dec + (size_t)job.dec_off * kBlockDec;
+	c.devfm = p.devfm ? p.devfm + (size_t)job.dec_off * kBlockDec : nullptr;
+	c.call_len = job.n_blocks * (uint32_t)kBlockDec;
+	c.prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
+	c.base_pos = st->blocks_done * (int64_t)kBlockDec;
+	return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// win_kernel: one thread per window; blockIdx.y = stream, blockIdx.z = registered demod
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) win_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y;
+	const int demod = blockIdx.z;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = st->win_n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
+		const WinEntry e = wl[w];
+		if (e.start >= c.call_len) continue;
+		WinRec rec;
+		rec.frame_idx = -1;
+		rec.flags = 0;
+		rec.first_edge = rec.first_edge_block = 0;
+		rec.pad = 0;
+		DemodState s;
+		const bool cont = (e.flags & kWinCont) != 0;
+		if (w == 0) {
+			// the first window of a call starts from the true carried state: nothing to speculate
+			s = st->d[demod];
+			if (!cont && cfg.kind != K_TFA1) s.last_bit_idx = lbi_at_block(s.last_bit_idx, -1, (int)(e.start >> 13));
+			if (cont && s.last_bit_idx) s.last_bit_idx -= kIdxPerBlock;   // demodulator::start for block 0
+			rec.flags = kRecExact;
+		} else {
+			memset(&s, 0, sizeof(s));
+		}
+		if (cfg.kind == K_TFA1) {
+			run_tfa1_window(c, e, s, rec, cont);
+		} else {
+			bool far = true;
+			if (w == 0) {
+				far = false;
+			} else {
+				// biquad warm-up over the samples of the preceding windows of this demod (they are the
+				// filter's actual history); reaching window 0 means the true carried state can be used
+				const uint32_t want = 3u * (uint32_t)cfg.timeout;
+				uint32_t have = 0;
+				int v = (int)w;
+				uint32_t from = e.start;
+				while (v > 0 && have < want) {
+					v--;
+					const uint32_t len = wl[v].end - wl[v].start + 1;
+					if (have + len >= want && v > 0) {
+						from = wl[v].end + 1 - (want - have);
+						have = want;
+					} else {
+						from = wl[v].start;
+						have += len;
+					}
+				}
+				Biquad lp;
+				lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
+				if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
+				const BiquadCoef k = cfg.lp;
+				for (int u = v; u < (int)w; u++) {
+					const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
+					for (uint32_t cb = a & ~15u; cb <= b; cb += 16) {
+						const Chunk16 ck = load16(c.devfm + cb);
+#pragma unroll
+						for (int kk = 0; kk < 16; kk++) {
+							const uint32_t m = cb + kk;
+							if (m >= a && m <= b) biquad_step(lp, k, int_to_double(ck.v[kk]));
+						}
+					}
+				}
+				s.lp = lp;
+			}
+			rec.u_y0 = s.lp.y0;
+			rec.u_y1 = s.lp.y1;
+			run_tfa2_window(c, cfg, e, s, rec, cont, far);
+		}
+		if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+		rl[w] = rec;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// carried-state reconstruction from window records (valid when every earlier window has been proven)
+// ------------------------------------------------------------------------------------------------
+struct Lbi { int v, block; };
+// last_bit_idx after window v: the newest window at or before v that either saw an edge candidate or is
+// window 0 (which ran from the true state, so its recorded value is true even without an edge)
+__device__ __forceinline__ Lbi lbi_after(const WinRec *rl, int v, const DemodState &carry0)
+{
+	for (; v >= 0; v--)
+		if (v == 0 || (rl[v].flags & kRecEdge)) return Lbi{ rl[v].lbi_end, rl[v].lbi_end_block };
+	return Lbi{ carry0.last_bit_idx, -1 };
+}
+// biquad state after window v (d1/d2 are the window's last discriminator values)
+__device__ __forceinline__ Biquad biquad_after(const WinCtx &c, const WinEntry *wl, const WinRec *rl, int v, const DemodState &carry0)
+{
+	if (v < 0) return carry0.lp;
+	Biquad lp;
+	const WinEntry e = wl[v];
+	const uint32_t last = min(e.end, c.call_len - 1);
+	lp.y0 = rl[v].e_y0;
+	lp.y1 = rl[v].e_y1;
+	lp.d1 = (double)c.devfm[last];
+	if (last >= e.start + 1) {
+		lp.d2 = (double)c.devfm[last - 1];
+	} else if (v > 0) {   // one-sample window: d2 is the previous window's last discriminator value
+		lp.d2 = (double)c.devfm[min(wl[v - 1].end, c.call_len - 1)];
+	} else {
+		lp.d2 = carry0.lp.d1;
+	}
+	return lp;
+}
+// decoder shift register before TFA_1 window w: the newest 32 bits pushed by earlier windows
+__device__ __forceinline__ uint32_t sr_before(const WinRec *rl, int w, const DemodState &carry0)
+{
+	uint32_t sr = 0;
+	int nb = 0;   // bits of sr (from the top) already determined by newer windows
+	for (int v = w - 1; v >= 0 && nb < 32; v--) {
+		const WinRec &r = rl[v];
+		sr |= (nb == 0) ? r.sr_final : (r.sr_final >> nb);
+		nb += (v == 0) ? 32 : min(r.nbits, 32);   // window 0 ran from the true register: it is complete
+	}
+	if (nb < 32) sr |= (nb == 0) ? carry0.sr : (carry0.sr >> nb);
+	return sr;
+}
+__device__ __forceinline__ bool tfa1_sync_same(const WinRec &rec, uint32_t sr_true)
+{
+	// would any sync decision among the first 31 shifts differ with the true shift register?
+	uint32_t a = 0, b = sr_true;
+	bool same = true;
+	const int n = min(rec.nbits, 31);
+	for (int k = 0; k < n; k++) {
+		const uint32_t bitv = (rec.head31 >> k) & 1u;
+		a = (a >> 1) | (bitv << 31);
+		b = (b >> 1) | (bitv << 31);
+		same &= ((a & 0xffff) == 0xd42d) == ((b & 0xffff) == 0xd42d);
+	}
+	return same;
+}
+__device__ __forceinline__ bool tfa2_edge_same(const WinRec &rec, const DemodCfg &cfg, Lbi l, uint32_t start)
+{
+	// a run that was handed an explicit last_bit_idx is right iff that value is the true one
+	if (rec.flags & kRecLbiIn) return rec.lbi_in == lbi_at_block(l.v, l.block, (int)(start >> 13));
+	if (!(rec.flags & kRecEdge)) return true;
+	// the first edge candidate must behave the same with the true last_bit_idx
+	const int v = lbi_at_block(l.v, l.block, rec.first_edge_block);
+	const int tdiff = rec.first_edge - v;
+	const bool c1 = rec.first_edge > v + 8;
+	const bool c2 = (double)tdiff > __dmul_rn(cfg.spb, 0.25) && (double)tdiff < __dmul_rn(32.0, cfg.spb);
+	return c1 && !c2 && (tdiff > 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// flag_kernel: rec.pad = 1 iff the window's assumed carry-in equals what its predecessor's record says it
+// left behind (parallel over windows; lets the verifier skip consistent runs 32 windows at a time).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) flag_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y, demod = blockIdx.z;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = st->win_n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
+		int pad = kPadOk;
+		if (w > 0) {
+			const WinRec rec = rl[w];
+			if (cfg.kind == K_TFA1) {
+				if (!tfa1_sync_same(rec, sr_before(rl, (int)w, st->d[demod]))) pad = 0;
+			} else {
+				const WinRec &pr = rl[w - 1];
+				const Lbi l = lbi_after(rl, (int)w - 1, st->d[demod]);
+				const bool bq = (__double_as_longlong(rec.u_y0) == __double_as_longlong(pr.e_y0)) &&
+						(__double_as_longlong(rec.u_y1) == __double_as_longlong(pr.e_y1));
+				const bool edge = tfa2_edge_same(rec, cfg, l, wl[w].start);
+				if (!bq || !edge) pad = 0;
+				if (!edge) {
+					pad |= kPadEdgeRepair;
+					rl[w].lbi_in = lbi_at_block(l.v, l.block, (int)(wl[w].start >> 13));
+				}
+			}
+		}
+		rl[w].pad = pad;
+	}
+}
+
+// edge_repair_kernel: windows whose "last edge is far in the past" assumption fails against the predecessor
+// chain's record are re-run, in parallel, with that record's last_bit_idx.  A window's last_bit_idx after its
+// first edge candidate does not depend on the speculation, so the value handed over is the true one except in
+// corner cases, which verify_kernel still catches.  The re-run keeps the window's own assumed biquad outputs
+// (d1/d2 are data), so the biquad check in verify_kernel applies unchanged.  Only the window's own record is
+// written; the values read from other records were snapshotted into lbi_in by flag_kernel.
+__global__ void __launch_bounds__(64) edge_repair_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y, demod = blockIdx.z;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB || cfg.kind == K_TFA1) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = st->win_n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	for (uint32_t w = 1 + blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
+		if (!(rl[w].pad & kPadEdgeRepair)) continue;
+		const WinEntry e = wl[w];
+		WinRec rec = rl[w];
+		DemodState s;
+		memset(&s, 0, sizeof(s));
+		s.lp.y0 = rec.u_y0;
+		s.lp.y1 = rec.u_y1;
+		const uint32_t pe = min(wl[w - 1].end, c.call_len - 1);   // the predecessor's last two samples feed d1/d2
+		s.lp.d1 = (double)c.devfm[pe];
+		s.lp.d2 = (pe >= wl[w - 1].start + 1) ? (double)c.devfm[pe - 1] : 0.0;
+		s.last_bit_idx = rec.lbi_in;
+		rec.flags &= ~kRecEdge;
+		rec.flags |= kRecLbiIn;
+		run_tfa2_window(c, cfg, e, s, rec, false, false);
+		if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+		rec.pad = 0;
+		rl[w] = rec;
+		atomicAdd(&p.counters->rerun_edge, 1u);
+	}
+}
+
+// the biquad alone over a window from a given (true) start state: returns the hash of (int)y and leaves the
+// end state in lp.  This is what the verifier runs when a window's assumed biquad state was not bitwise the
+// true one: if the slicer inputs hash the same, everything the window produced stands.
+static __device__ unsigned long long biquad_only(const WinCtx &c, const DemodCfg &cfg, const WinEntry &e, Biquad &lp)
+{
+	const uint32_t last = min(e.end, c.call_len - 1);
+	const BiquadCoef k = cfg.lp;
+	const bool taps = c.p->tap_cap != 0;
+	const size_t tbase = ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap;
+	unsigned long long hash = 0;
+	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
+		const Chunk16 ck = load16(c.devfm + cb);
+#pragma unroll
+		for (int kk = 0; kk < 16; kk++) {
+			const uint32_t m = cb + kk;
+			if (m < e.start || m > last) continue;
+			const double y = biquad_step(lp, k, int_to_double(ck.v[kk]));
+			if (taps) {
+				const uint32_t ti = e.cum + (m - e.start);
+				if (ti < c.p->tap_cap) c.p->tap_f64[tbase + ti] = y;
+			}
+			hash += ld_term(__double2int_rz(y), m - e.start);
+		}
+	}
+	return hash;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cheap_repair_kernel: one parallel round of the verifier's cheap fix.  A window whose assumed biquad outputs
+// differ from what its predecessor's record left behind re-runs the biquad alone from the predecessor's end
+// state; if the slicer inputs hash the same it adopts that state.  The predecessor's record is not
+// necessarily the truth yet, so this only REDUCES the serial work: verify_kernel re-derives everything from
+// the true state and re-checks the successor of every window it changes.  Reads of neighbouring records are
+// limited to fields this kernel never writes for a window with a good flag (only flagged-bad windows whose
+// predecessor is flagged good are touched).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) cheap_repair_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y, demod = blockIdx.z;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB || cfg.kind == K_TFA1) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = st->win_n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	for (uint32_t w = 1 + blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
+		if ((rl[w].pad & kPadOk) || !(rl[w - 1].pad & kPadOk) || (rl[w].pad & kPadEdgeRepair)) continue;
+		const WinEntry e = wl[w];
+		WinRec rec = rl[w];
+		if (rec.flags & kRecUnfinished) continue;   // the carried state of an open window is the verifier's business
+		Biquad lp = biquad_after(c, wl, rl, (int)w - 1, st->d[demod]);
+		const double y0 = lp.y0, y1 = lp.y1;
+		if (__double_as_longlong(rec.u_y0) == __double_as_longlong(y0) && __double_as_longlong(rec.u_y1) == __double_as_longlong(y1))
+			continue;
+		if (biquad_only(c, cfg, e, lp) != rec.ld_hash) continue;
+		rl[w].u_y0 = y0;
+		rl[w].u_y1 = y1;
+		rl[w].e_y0 = lp.y0;
+		rl[w].e_y1 = lp.y1;
+		atomicAdd(&p.counters->rerun_biquad, 1u);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// verify_kernel: one warp per (stream, demod): the exactness backstop.  Windows whose flag is good and whose
+// predecessor's record did not change are proven by induction from window 0 (which ran from the true
+// state).  Lane 0 repairs the others in stream order with the true carried state:
+//   biquad state differs  -> biquad-only run from the true state; same slicer-input hash => adopt the true
+//                            end state, otherwise full re-run
+//   edge / shift-register assumption wrong -> full re-run
+// and finally writes the state carried into the next call.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
+{
+	const int gid = blockIdx.x;
+	const int lane = threadIdx.x;
+	const int nd = p.cfg->n_demods;
+	if (gid >= p.n_streams * nd) return;
+	const int stream = gid / nd, demod = gid % nd;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = st->win_n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	const int last_block = (int)job.n_blocks - 1;
+	const DemodState &carry0 = st->d[demod];   // read in place; overwritten only by the final store below
+	uint32_t reruns = 0, cheap = 0;
+	int force = 0;   // the previous window's record changed: re-check this one whatever its flag says
+
+	for (uint32_t base = 0; base < n_win; base += 32) {
+		const uint32_t wq = base + lane;
+		const bool bad = (wq < n_win) && !(rl[wq].pad & kPadOk);
+		const unsigned mask = __ballot_sync(0xffffffffu, bad);
+		if (lane == 0 && (mask || force)) {
+			for (uint32_t k = 0; k < 32 && base + k < n_win; k++) {
+				if (!(((mask >> k) & 1u) || force)) continue;
+				const uint32_t w = base + k;
+				force = 0;
+				if (w == 0) continue;   // window 0 ran from the true state
+				const WinEntry e = wl[w];
+				WinRec rec = rl[w];
+				if (cfg.kind == K_TFA1) {
+					const uint32_t sr = sr_before(rl, (int)w, carry0);
+					if (!(rec.flags & kRecExact) && !tfa1_sync_same(rec, sr)) {
+						DemodState s;
+						memset(&s, 0, sizeof(s));
+						s.sr = sr;
+						run_tfa1_window(c, e, s, rec, false);
+						rec.flags |= kRecExact;
+						if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+						reruns++;
+						atomicAdd(&p.counters->rerun_sr, 1u);
+						rec.pad = kPadOk;
+						rl[w] = rec;
+						force = 1;
+					}
+					continue;
+				}
+				const Biquad lp0 = biquad_after(c, wl, rl, (int)w - 1, carry0);
+				const Lbi l = lbi_after(rl, (int)w - 1, carry0);
+				const bool bq_ok = (__double_as_longlong(rec.u_y0) == __double_as_longlong(lp0.y0)) &&
+						   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp0.y1));
+				const bool edge_ok = tfa2_edge_same(rec, cfg, l, e.start);
+				if (bq_ok && edge_ok) continue;   // consistent with the true predecessor state after all
+				bool full = !edge_ok;
+				if (!full) {
+					Biquad lp = lp0;
+					const unsigned long long h = biquad_only(c, cfg, e, lp);
+					if (h == rec.ld_hash) {
+						rec.u_y0 = lp0.y0;
+						rec.u_y1 = lp0.y1;
+						rec.e_y0 = lp.y0;
+						rec.e_y1 = lp.y1;
+						if (rec.flags & kRecUnfinished) st->fin[demod].lp = lp;
+						cheap++;
+						atomicAdd(&p.counters->rerun_biquad, 1u);
+					} else {
+						full = true;
+					}
+				}
+				if (full) {
+					DemodState s;
+					memset(&s, 0, sizeof(s));
+					s.lp = lp0;
+					s.last_bit_idx = lbi_at_block(l.v, l.block, (int)(e.start >> 13));
+					rec.lbi_in = s.last_bit_idx;
+					rec.u_y0 = lp0.y0;
+					rec.u_y1 = lp0.y1;
+					rec.flags &= ~kRecEdge;
+					rec.flags |= kRecLbiIn;
+					run_tfa2_window(c, cfg, e, s, rec, false, false);
+					if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+					reruns++;
+				}
+				rec.pad = kPadOk;
+				rl[w] = rec;
+				force = 1;
+			}
+		}
+		force = __shfl_sync(0xffffffffu, force, 0);
+	}
+	if (lane != 0) return;
+
+	bool unfinished = false;
+	if (n_win) unfinished = (rl[n_win - 1].flags & kRecUnfinished) != 0;
+	if (cfg.kind == K_TFA1) {
+		const uint32_t sr_end = sr_before(rl, (int)n_win, carry0);
+		DemodState &out = st->d[demod];
+		if (unfinished) {
+			out = st->fin[demod];
+		} else {
+			// tfa1.cpp:179-184 + :115-117: everything but the shift register is reset by the flush
+			out.mark_lvl = out.rssi_i = out.last_bit_idx = out.timeout_cnt = 0;
+			out.sr_cnt = -1;
+			out.byte_cnt = 0;
+			out.rdata[10] = 0;
+		}
+		out.sr = sr_end;
+	} else {
+		const Lbi l = lbi_after(rl, (int)n_win - 1, carry0);
+		const Biquad lp_end = biquad_after(c, wl, rl, (int)n_win - 1, carry0);
+		const int lbi_end = lbi_at_block(l.v, l.block, last_block);
+		DemodState &out = st->d[demod];
+		if (unfinished) {
+			out = st->fin[demod];
+			out.lp = lp_end;
+		} else {
+			tfa2_reset(out);
+			out.timeout_cnt = 0;
+			out.sr_cnt = -1;
+			out.sr = 0;
+			out.byte_cnt = 0;
+			out.lp = lp_end;
+		}
+		out.last_bit_idx = lbi_end;
+	}
+	if (reruns) atomicAdd(&p.counters->n_reruns, reruns);
+	(void)cheap;
+	if (n_win) atomicAdd(&p.counters->n_windows, (unsigned long long)n_win);
+	if (p.tap_cap) {
+		uint32_t *tc = p.tap_cnt + ((size_t)stream * kMaxDemods + demod) * 3;
+		const uint32_t n = st->win_cum[demod];
+		// taps are written at (cum + offset): the number valid is the demod's active-sample count clipped to the call
+		uint32_t valid = n;
+		if (n_win) {
+			const WinEntry e = wl[n_win - 1];
+			if (e.end >= c.call_len) valid = n - (e.end - (c.call_len - 1));
+		}
+		if (cfg.kind == K_TFA1) {
+			tc[1] = valid;
+		} else {
+			tc[0] = valid;
+			tc[2] = valid;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
+{
+	thresh2_kernel<<<(p.n_streams + 3) / 4, 128, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)
+{
+	if (p.max_blocks <= 0) return cudaSuccess;
+	devfm_kernel<<<dim3(p.max_blocks, p.n_streams), 128, 0, s>>>(p);
+	return cudaGetLastError();
+}
+static dim3 win_grid(const BackParams &p, int n_demods, int threads)
+{
+	// windows per (stream, demod) are at most a few per block
+	int gx = (p.max_blocks * 2 + threads - 1) / threads;
+	gx = gx < 1 ? 1 : (gx > 512 ? 512 : gx);
+	return dim3(gx, p.n_streams, n_demods);
+}
+cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_flag(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	flag_kernel<<<win_grid(p, n_demods, 128), 128, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_edge_repair(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	edge_repair_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_cheap_repair(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	cheap_repair_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	verify_kernel<<<p.n_streams * n_demods, 32, 0, s>>>(p);
+	return cudaGetLastError();
+}
+
+}  // namespace tfr

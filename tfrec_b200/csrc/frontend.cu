@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	__shared__ int s_last[kThreads];
 	__shared__ int s_seg_start[kMaxSeg + 4], s_seg_end[kMaxSeg + 4];
 	__shared__ int s_nseg, s_ntrig;
+	__shared__ int s_warp_cnt[kThreads / 32];
 
 	const int tid = threadIdx.x;
 	const int stream = blockIdx.y;
@@ -192,10 +193,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 
 	const uint32_t bar = smem_u32(smem);
 	const uint8_t *src = job.iq + (size_t)tile * kBlockBytes;
-	if (tid == 0) {
-		mbar_init(bar, 1);
-		s_ntrig = 0;
-	}
+	if (tid == 0) mbar_init(bar, 1);
 	__syncthreads();
 	if (tid == 0) {
 		mbar_expect_tx(bar, kBlockBytes + kHistBytes);
@@ -234,12 +232,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 		for (int k = 0; k < 6; k++) xh[k] = hx[42 + k];
 	}
 
-	uint32_t trig[2] = { 0u, 0u };
+	unsigned long long trig64 = 0ull;   // bit m = pwr(output m) > thresh_lo
 	const uint4 *rowv = reinterpret_cast<const uint4 *>(row);
 	uint32_t *outw = reinterpret_cast<uint32_t *>(row);   // outputs overwrite the front of the own row
 
 #pragma unroll 1
 	for (int it = 0; it < 4; it++) {
+		uint32_t t16 = 0u;   // trigger bits of this iteration's 16 outputs (static bit positions)
 #pragma unroll
 		for (int s = 0; s < 8; s++) {
 			const uint4 v = rowv[it * 8 + s];
@@ -272,13 +271,14 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 				const int yi = (int)(ai + bi - y2_bias(WIDE));
 				const int yq = (int)(aq + bq - y2_bias(WIDE));
 				const int pwr = abs(yi) + abs(yq);
-				const int idx = it * 16 + m;
-				if (pwr > thresh_lo) trig[idx >> 5] |= 1u << (idx & 31);
+				if (pwr > thresh_lo) t16 |= 1u << m;
 				o[mm] = __byte_perm((uint32_t)yi, (uint32_t)yq, 0x5410);
 			}
 			*reinterpret_cast<uint2 *>(outw + it * 16 + 2 * s) = make_uint2(o[0], o[1]);
 		}
+		trig64 |= (unsigned long long)t16 << (16 * it);
 	}
+	const uint32_t trig[2] = { (uint32_t)trig64, (uint32_t)(trig64 >> 32) };
 
 	// ------------------------------------------------------------------ block-level trigger bookkeeping
 	{
@@ -290,7 +290,30 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 		s_first[tid] = (f < 0) ? -1 : tid * kOutPerThread + f;
 		s_last[tid] = (l < 0) ? -1 : tid * kOutPerThread + l;
 		const int nt = __popc(trig[0]) + __popc(trig[1]);
-		if (nt) atomicAdd(&s_ntrig, nt);
+		// ordered event list: exclusive scan of the per-thread trigger counts over the CTA
+		int incl = nt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int o = __shfl_up_sync(0xffffffffu, incl, d);
+			if ((tid & 31) >= d) incl += o;
+		}
+		if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = incl;
+		__syncthreads();
+		int base = incl - nt;
+		for (int w = 0; w < (tid >> 5); w++) base += s_warp_cnt[w];
+		if (tid == kThreads - 1) s_ntrig = base + nt;
+		if (nt && base < kMaxEvt) {
+			uint32_t *ev = p.events + ((size_t)job.dec_off + tile) * kMaxEvt;
+			unsigned long long msk = trig64;
+			int k = base;
+			while (msk && k < kMaxEvt) {
+				const int b = __ffsll((long long)msk) - 1;
+				msk &= msk - 1;
+				const uint32_t w = outw[b];   // this thread's own output b (I lo16, Q hi16)
+				const int pi = (int)(int16_t)(w & 0xffff), pq = (int)(int16_t)(w >> 16);
+				ev[k++] = ((uint32_t)(tid * kOutPerThread + b) << 16) | (uint32_t)(abs(pi) + abs(pq));
+			}
+		}
 	}
 	__syncthreads();
 

@@ -17,7 +17,13 @@
 namespace tfr {
 cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaStream_t stream);
 cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream);
-cudaError_t launch_thresh(const BackParams &p, cudaStream_t s);
+cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
+cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
+cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_flag(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_edge_repair(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_cheap_repair(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
 cudaError_t launch_parse(const BackParams &p, cudaStream_t s);
@@ -25,7 +31,7 @@ cudaError_t launch_parse(const BackParams &p, cudaStream_t s);
 
 using namespace tfr;
 
-static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 72,
+static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 112,
 	      "public struct layout changed: bump TFR_ABI_VERSION");
 
 static thread_local std::string g_err;
@@ -82,6 +88,12 @@ struct tfr_handle {
 	TileDesc *d_tiles = nullptr;
 	uint32_t *d_dec = nullptr;
 	BlockTrace *d_trace = nullptr;
+	uint32_t *d_events = nullptr;
+	int32_t *d_devfm = nullptr;
+	size_t cap_wins = 0;
+	WinEntry *d_wins = nullptr;
+	WinRec *d_recs = nullptr;
+	bool has_fm = false, has_whb = false;
 	// input arena for host submits: normally one chunk; more are added when a later submit does not
 	// fit while earlier ones are still pending, and merged into one the next time the arena is idle
 	struct Chunk { uint8_t *ptr; size_t cap, used; };
@@ -95,7 +107,7 @@ struct tfr_handle {
 	std::vector<PendingSubmit> pend;
 	std::vector<StreamJob> jobs;       // jobs of the last tfr_process
 	std::vector<cudaEvent_t> ev;       // front-end start/stop pairs then back-end pairs, per epoch
-	int n_epochs_last = 0;
+	int n_epochs_last = 0, n_epochs_total = 0;
 	cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
 	bool h2d_timed = false;
 	tfr_stats stats;
@@ -168,7 +180,8 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_jobs); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records); cudaFree(h->d_tiles); cudaFree(h->d_dec);
-	cudaFree(h->d_trace); for (auto &c : h->arena) cudaFree(c.ptr); cudaFree(h->d_tap_i32[0]); cudaFree(h->d_tap_i32[1]);
+	cudaFree(h->d_trace); cudaFree(h->d_events); cudaFree(h->d_devfm); cudaFree(h->d_wins); cudaFree(h->d_recs);
+	for (auto &c : h->arena) cudaFree(c.ptr); cudaFree(h->d_tap_i32[0]); cudaFree(h->d_tap_i32[1]);
 	cudaFree(h->d_tap_f64); cudaFree(h->d_tap_cnt);
 	for (auto e : h->ev) cudaEventDestroy(e);
 	if (h->ev_h2d0) cudaEventDestroy(h->ev_h2d0);
@@ -193,12 +206,21 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		return fail(TFR_E_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
 						    ", kernels are built for sm_100a only");
 	CU(cudaSetDevice(cfg->device));
+	{   // the serial slow paths (window re-runs) keep a whole demodulator state on the stack
+		size_t lim = 0;
+		CU(cudaDeviceGetLimit(&lim, cudaLimitStackSize));
+		if (lim < 4096) CU(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+	}
 
 	tfr_handle *h = new tfr_handle();
 	h->cfg = *cfg;
 	h->device = cfg->device;
 	memset(&h->stats, 0, sizeof(h->stats));
 	build_config(*cfg, h->dcfg);
+	for (int k = 0; k < h->dcfg.n_demods; k++) {
+		h->has_fm |= (h->dcfg.d[k].kind == K_TFA2 || h->dcfg.d[k].kind == K_TFA3 || h->dcfg.d[k].kind == K_TX22);
+		h->has_whb |= (h->dcfg.d[k].kind == K_WHB);
+	}
 	h->pend.resize(cfg->n_streams);
 	h->max_frames = cfg->max_frames ? cfg->max_frames : 65536u;
 	h->max_records = h->max_frames * 5u;
@@ -240,19 +262,31 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	return TFR_OK;
 }
 
-static int ensure_blocks(tfr_handle *h, size_t blocks)
+static int ensure_blocks(tfr_handle *h, size_t blocks, size_t wins)
 {
-	if (blocks <= h->cap_blocks) return TFR_OK;
-	CU(cudaStreamSynchronize(h->stream));
-	cudaFree(h->d_tiles); cudaFree(h->d_dec); cudaFree(h->d_trace);
-	h->d_tiles = nullptr; h->d_dec = nullptr; h->d_trace = nullptr;
-	h->cap_blocks = 0;
-	cudaError_t e = cudaMalloc(&h->d_tiles, blocks * sizeof(TileDesc));
-	if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
-	if (e == cudaSuccess) e = cudaMalloc(&h->d_trace, blocks * sizeof(BlockTrace));
-	if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA,
-					  std::string("work buffers: ") + cudaGetErrorString(e));
-	h->cap_blocks = blocks;
+	if (blocks > h->cap_blocks) {
+		CU(cudaStreamSynchronize(h->stream));
+		cudaFree(h->d_tiles); cudaFree(h->d_dec); cudaFree(h->d_trace); cudaFree(h->d_events); cudaFree(h->d_devfm);
+		h->d_tiles = nullptr; h->d_dec = nullptr; h->d_trace = nullptr; h->d_events = nullptr; h->d_devfm = nullptr;
+		h->cap_blocks = 0;
+		cudaError_t e = cudaMalloc(&h->d_tiles, blocks * sizeof(TileDesc));
+		if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
+		if (e == cudaSuccess) e = cudaMalloc(&h->d_trace, blocks * sizeof(BlockTrace));
+		if (e == cudaSuccess) e = cudaMalloc(&h->d_events, blocks * (size_t)kMaxEvt * sizeof(uint32_t));
+		if (e == cudaSuccess && h->has_fm) e = cudaMalloc(&h->d_devfm, blocks * (size_t)kBlockDec * sizeof(int32_t));
+		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("work buffers: ") + cudaGetErrorString(e)); }
+		h->cap_blocks = blocks;
+	}
+	if (wins > h->cap_wins) {
+		CU(cudaStreamSynchronize(h->stream));
+		cudaFree(h->d_wins); cudaFree(h->d_recs);
+		h->d_wins = nullptr; h->d_recs = nullptr;
+		h->cap_wins = 0;
+		cudaError_t e = cudaMalloc(&h->d_wins, wins * sizeof(WinEntry));
+		if (e == cudaSuccess) e = cudaMalloc(&h->d_recs, wins * sizeof(WinRec));
+		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("window lists: ") + cudaGetErrorString(e)); }
+		h->cap_wins = wins;
+	}
 	return TFR_OK;
 }
 
@@ -261,7 +295,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_submit(tfr_handle *h, 
 	if (!h || !iq) return fail(TFR_E_INVAL, "tfr_submit: null argument");
 	if (stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_submit: stream out of range");
 	if (nbytes == 0 || nbytes % TFR_BLOCK_BYTES) return fail(TFR_E_INVAL, "tfr_submit: nbytes must be a positive multiple of 65536");
-	if (nbytes / TFR_BLOCK_BYTES > 0x7fffffffull) return fail(TFR_E_INVAL, "tfr_submit: too many blocks");
+	if (nbytes / TFR_BLOCK_BYTES > 262143ull) return fail(TFR_E_INVAL, "tfr_submit: at most 262143 blocks (16 GiB) per stream per call");
 	PendingSubmit &ps = h->pend[stream];
 	if (ps.pending) return fail(TFR_E_BUSY, "tfr_submit: stream already has a pending submit");
 	CU(cudaSetDevice(h->device));
@@ -331,8 +365,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	CU(cudaSetDevice(h->device));
 	cudaGetLastError();   // do not inherit a stale error from another user of the runtime
 	const int ns = h->cfg.n_streams;
-	h->jobs.assign(ns, StreamJob{ nullptr, 0, 0 });
-	size_t total = 0;
+	h->jobs.assign(ns, StreamJob{ nullptr, 0, 0, 0, 0 });
+	size_t total = 0, total_wins = 0;
+	const int ndm = std::max(h->dcfg.n_demods, 1);
 	uint32_t max_blocks = 0;
 	for (int s = 0; s < ns; s++) {
 		PendingSubmit &ps = h->pend[s];
@@ -341,6 +376,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		j.iq = ps.dev_ptr;
 		j.n_blocks = (uint32_t)(ps.nbytes / TFR_BLOCK_BYTES);
 		j.dec_off = (uint32_t)total;
+		j.win_cap = j.n_blocks * (uint32_t)kWinPerBlock + 4u;
+		j.win_off = (uint32_t)total_wins;
+		total_wins += (size_t)j.win_cap * ndm;
 		total += j.n_blocks;
 		max_blocks = std::max(max_blocks, j.n_blocks);
 		ps.pending = false;
@@ -348,8 +386,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	for (auto &c : h->arena) c.used = 0;   // contents stay valid until the next submit overwrites them (stream ordered)
 	h->n_epochs_last = 0;
 	if (total == 0) return TFR_OK;
-	if (total > 0xffffffffull) return fail(TFR_E_INVAL, "tfr_process: too many blocks in one call");
-	int rc = ensure_blocks(h, total);
+	if (total > 0x7ffffffull || total_wins > 0xffffffffull) return fail(TFR_E_INVAL, "tfr_process: too many blocks in one call");
+	int rc = ensure_blocks(h, total, total_wins);
 	if (rc) return rc;
 	CU(cudaMemcpyAsync(h->d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, h->stream));
 
@@ -370,6 +408,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	fp.t_max = h->dcfg.t_max;
 	fp.keep_all = (h->cfg.flags & TFR_FLAG_KEEP_DECIM) ? 1 : 0;
 	fp.epoch_blocks = (int)epoch;
+	fp.events = h->d_events;
 	BackParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.cfg = h->d_cfg;
@@ -389,6 +428,12 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.max_frames = h->max_frames;
 	bp.max_records = h->max_records;
 	bp.n_streams = ns;
+	bp.events = h->d_events;
+	bp.wins = h->d_wins;
+	bp.recs = h->d_recs;
+	bp.devfm = h->d_devfm;
+	bp.max_blocks = (int)max_blocks;
+	if (h->d_tap_cnt) CU(cudaMemsetAsync(h->d_tap_cnt, 0, (size_t)ns * kMaxDemods * 3 * sizeof(uint32_t), h->stream));   // taps cover one tfr_process
 
 	for (int e = 0; e < n_epochs; e++) {
 		const int tile0 = (int)(e * epoch);
@@ -402,13 +447,32 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
 		CU(cudaEventRecord(h->ev[4 * e + 1], h->stream));
 		CU(cudaEventRecord(h->ev[4 * e + 2], h->stream));
-		CU(launch_thresh(bp, h->stream));
+		CU(launch_thresh2(bp, h->stream));
 		h->stats.kernel_launches += 2;
-		if (h->dcfg.n_demods) {
-			CU(launch_walk(bp, h->dcfg.n_demods, h->stream));
-			h->stats.kernel_launches += 1;
-		}
 		if (e == n_epochs - 1) {
+			// everything below runs once per call, over all blocks
+			bp.tile0 = 0;
+			bp.n_tiles = (int)max_blocks;
+			if (h->dcfg.n_demods) {
+				if (h->has_fm) { CU(launch_devfm(bp, h->stream)); h->stats.kernel_launches += 1; }
+				const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
+				if (has_win) {
+					CU(launch_win(bp, h->dcfg.n_demods, h->stream));
+					h->stats.kernel_launches += 1;
+					CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
+					h->stats.kernel_launches += 1;
+					if (h->has_fm) {
+						CU(launch_edge_repair(bp, h->dcfg.n_demods, h->stream));
+						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
+						CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
+						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
+						h->stats.kernel_launches += 4;
+					}
+				}
+				if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
+				CU(launch_verify(bp, h->dcfg.n_demods, h->stream));
+				h->stats.kernel_launches += 1;
+			}
 			CU(launch_submit_epilogue(bp, h->stream));
 			CU(launch_save_history(h->d_jobs, h->d_state, ns, h->stream));
 			CU(launch_parse(bp, h->stream));
@@ -417,6 +481,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		CU(cudaEventRecord(h->ev[4 * e + 3], h->stream));
 	}
 	h->n_epochs_last = n_epochs;
+	h->n_epochs_total = n_epochs;
 	h->stats.blocks += total;
 	h->stats.raw_samples += total * (uint64_t)kBlockRaw;
 	h->results_valid = false;
@@ -441,11 +506,19 @@ extern "C" __attribute__((visibility("default"))) int tfr_sync(tfr_handle *h)
 		h->stats.last_backend_ms = be;
 		h->n_epochs_last = 0;
 	}
+	if (h->n_epochs_total) {
+		float a = 0;
+		CU(cudaEventElapsedTime(&a, h->h2d_timed ? h->ev_h2d0 : h->ev[0], h->ev[4 * (h->n_epochs_total - 1) + 3]));
+		h->stats.last_total_ms = a;
+		h->n_epochs_total = 0;
+	}
 	if (h->h2d_timed) {
 		float a = 0;
 		CU(cudaEventElapsedTime(&a, h->ev_h2d0, h->ev_h2d1));
 		h->stats.last_h2d_ms = a;
 		h->h2d_timed = false;
+	} else {
+		h->stats.last_h2d_ms = 0;
 	}
 	return TFR_OK;
 }
@@ -526,6 +599,11 @@ static int fetch_results(tfr_handle *h)
 	h->stats.frames = h->frames.size();
 	h->stats.records = h->records.size();
 	h->stats.active_samples = c.active_samples;
+	h->stats.windows = c.n_windows;
+	h->stats.reruns = c.n_reruns;
+	h->stats.reruns_sr = c.rerun_sr;
+	h->stats.reruns_biquad = c.rerun_biquad;
+	h->stats.reruns_edge = c.rerun_edge;
 	h->results_valid = true;
 	if (c.overflow) return fail(TFR_E_OVERFLOW, "frame/record buffer overflowed; raise tfr_config.max_frames");
 	return TFR_OK;
@@ -562,6 +640,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_clear_results(tfr_hand
 	Counters c;
 	CU(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
 	c.n_frames = c.n_records = c.overflow = 0;
+	c.n_reruns = c.rerun_sr = c.rerun_biquad = c.rerun_edge = 0;
+	c.n_windows = 0;
 	CU(cudaMemcpy(h->d_counters, &c, sizeof(c), cudaMemcpyHostToDevice));
 	if (h->d_tap_cnt) CU(cudaMemset(h->d_tap_cnt, 0, (size_t)h->cfg.n_streams * kMaxDemods * 3 * sizeof(uint32_t)));
 	h->frames.clear();

@@ -18,6 +18,8 @@ constexpr int kHistBytes = 96;          // raw bytes of FIR history carried betw
 constexpr int kMaxSeg = 28;             // trigger segments per block (>= 8192/357 + 2)
 constexpr int kMaxDemods = 5;
 constexpr int kMaxRdata = 64;
+constexpr int kMaxEvt = 128;            // trigger events kept per block; a block with more is 'dense'
+constexpr int kWinPerBlock = 24;        // worst-case demod windows that can start in one block (8192/357 + 1)
 constexpr int kRdataBytes = 256;        // decoder::rdata (decoder.h:52)
 
 // demod kinds, in the reference's registration order (main.cpp:173-218)
@@ -89,8 +91,15 @@ struct alignas(128) StreamState {
 	int32_t carry_in;             // decimated samples at the head of the next block covered by earlier triggers
 	int16_t last_i, last_q;       // previous decimated sample (every demod's last_i/last_q)
 	int32_t hist_parity;
-	int32_t pad;
+	int32_t trig_age;             // samples since the last trigger as of the end of the previous call (>= 1; huge = none)
+	// scratch of the current process call (threshold kernel -> window kernels)
+	int32_t call_last_trig;       // position of the last trigger seen so far in this call (negative: before the call)
+	uint32_t call_cursor;         // coverage cursor
+	uint32_t win_n[kMaxDemods];   // windows listed so far per demod
+	uint32_t win_cum[kMaxDemods]; // active samples in closed windows
+	uint32_t win_open[kMaxDemods];// 1 if the last listed window is still open
 	DemodState d[kMaxDemods];
+	DemodState fin[kMaxDemods];   // state left by an unfinished (ran out of data) last window, pending verification
 };
 
 // one entry per (stream, block) of a process() call, written by the front-end
@@ -108,7 +117,43 @@ struct StreamJob {
 	const uint8_t *iq;            // device pointer to this stream's submitted bytes
 	uint32_t n_blocks;            // blocks in this submit
 	uint32_t dec_off;             // offset (in blocks) of this stream inside the sparse decimated buffer
+	uint32_t win_off;             // first window-list entry of this stream (demod d starts at win_off + d*win_cap)
+	uint32_t win_cap;             // window-list capacity per demod = n_blocks*kWinPerBlock + 4
 };
+
+// one demodulator window = one retriggerable timeout interval, derived from the trigger positions alone
+// (a trigger at t keeps demod d active for samples t .. t+T_d-1; tfa1.cpp:147-148, tfa2.cpp:351-356)
+struct WinEntry {
+	uint32_t start;               // first sample (the trigger), position inside this process call
+	uint32_t end;                 // sample at which timeout_cnt reaches 0 and flush() runs (may lie beyond the call)
+	uint32_t cum;                 // active samples of this demod in earlier windows of this call (tap index base)
+	uint32_t flags;               // kWinCont: the window was already open when the call began
+};
+constexpr uint32_t kWinCont = 1u;
+
+// what a speculative window run leaves behind so that the verifier can prove (or repair) its carry-in
+struct WinRec {
+	int32_t frame_idx;            // frame emitted by this window, -1 if none
+	uint32_t flags;               // kRec*
+	// TFA_1: decoder shift register carry (tfa1.cpp:115-117 keeps sr across flush)
+	uint32_t head31;              // first min(31,nbits) bits the window pushed into the framer
+	uint32_t sr_final;            // shift register at window end (under the assumed carry-in)
+	int32_t nbits;
+	// TFA_2 family: biquad and last_bit_idx carry (tfa2.cpp:325-334 resets neither)
+	int32_t first_edge;           // in-block index of the first edge candidate, valid if kRecEdge
+	int32_t first_edge_block;
+	int32_t lbi_end;              // last_bit_idx at window end, relative to lbi_end_block
+	int32_t lbi_end_block;
+	int32_t pad;
+	double u_y0, u_y1;            // biquad outputs assumed at window start (after warm-up)
+	double e_y0, e_y1;            // biquad outputs at window end
+	unsigned long long ld_hash;   // hash of the slicer input sequence (int)y over the window
+	int32_t lbi_in;               // edge repair: the predecessor chain's last_bit_idx, relative to the window's first block
+	int32_t pad3;
+};
+constexpr uint32_t kRecRan = 1u, kRecExact = 2u, kRecEdge = 4u, kRecUnfinished = 8u;
+constexpr uint32_t kRecLbiIn = 16u;   // the run used the explicit last_bit_idx in lbi_in instead of the 'far' assumption
+constexpr int32_t kPadOk = 1, kPadEdgeRepair = 2;   // WinRec::pad bits written by flag_kernel
 
 // device-side frame / record (converted to tfr_frame / tfr_record on the host)
 struct DevFrame {
@@ -133,8 +178,10 @@ struct Counters {
 	uint32_t n_frames;
 	uint32_t n_records;
 	uint32_t overflow;
-	uint32_t pad;
+	uint32_t n_reruns;            // windows the verifier had to re-run because a speculated carry-in was wrong
 	unsigned long long active_samples;
+	unsigned long long n_windows;
+	uint32_t rerun_sr, rerun_biquad, rerun_edge, pad2;   // why the verifier re-ran windows
 };
 
 struct FrontParams {
@@ -147,6 +194,7 @@ struct FrontParams {
 	int t_max;
 	int keep_all;          // TFR_FLAG_KEEP_DECIM: write every sample
 	int epoch_blocks;      // bound on threshold drift: thresh_lo = thresh - 2*ceil(epoch_blocks/4) in auto mode
+	uint32_t *events;      // [gtile][kMaxEvt]
 };
 
 struct BackParams {
@@ -167,6 +215,12 @@ struct BackParams {
 	int tile0, n_tiles;      // epoch range inside the submit
 	int n_streams;
 	int last_epoch;          // 1: this epoch ends the submit -> roll stream state forward
+	const uint32_t *events;  // [gtile][kMaxEvt] (pos<<16 | pwr) of samples with pwr > thresh_lo, in order
+	WinEntry *wins;
+	WinRec *recs;
+	int32_t *devfm;          // fm_dev per stored sample, direct mapped like dec
+	int demod;               // kernels that run per registered demod: which one
+	int max_blocks;
 };
 
 }  // namespace tfr

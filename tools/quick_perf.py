@@ -27,8 +27,8 @@ def main():
         samples = n_streams * nbytes / 2
         print("iter %d wall %.3f ms  frontend %.3f ms (%.1f GS/s, %.1f GB/s)  backend %.3f ms  active %.2f%% frames %d thresh %d" % (
             it, dt * 1e3, st["last_frontend_ms"], samples / st["last_frontend_ms"] / 1e6, 2 * samples / st["last_frontend_ms"] / 1e6,
-            st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)))
-        rx.clear()
+            st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)), "windows", rx.stats()["windows"], "reruns", rx.stats()["reruns"], "sr/bq/edge", rx.stats()["reruns_sr"], rx.stats()["reruns_biquad"], rx.stats()["reruns_edge"])
+        rx.records(); rx.clear()
 
 if __name__ == "__main__":
     main()
