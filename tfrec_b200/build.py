@@ -51,5 +51,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+CLI = os.path.join(HERE, "tfrec_b200_cli")
+HOST_SOURCES = ["main.cpp", "engine.cpp", "fm_demod.cpp", "decoder.cpp"]
+
+
+def build_cli(force=False):
+    """the tfrec-compatible command line: C++ host mirror of the reference's engine/decoder surface over the C ABI"""
+    hdir = os.path.join(HERE, "host")
+    srcs = [os.path.join(hdir, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(hdir, h) for h in os.listdir(hdir) if h.endswith(".h")] + [LIB]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    cmd = ["g++", "-O2", "-std=c++11", "-Wall", "-o", CLI, *srcs, "-L" + HERE, "-ltfrb200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building tfrec_b200_cli")
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli(force="--force" in sys.argv))
