@@ -48,7 +48,16 @@ def test_cli_hex_replay_matches_reference(cli, golden, tmp_path):
         p.write_text("".join(" ".join(re.findall("..", k["hex"])) + "\n" for k in ks))
         mask = "%x" % (1 << sensor)
         want_lines = [ln for k in ks for ln in k["lines"]]
-        want_exec = [ln for k in ks for ln in k["exec"]]
+        want_exec = []
+        seen = {}   # decoder::store_data (decoder.cpp:46-65): a WeatherHub repeat with the same sequence is not exec'd again
+        for k in ks:
+            for ln in k["exec"]:
+                f = ln.split()
+                if sensor == 5:
+                    if f[0] in seen and seen[f[0]] == f[3]:
+                        continue
+                    seen[f[0]] = f[3]
+                want_exec.append(ln)
         assert make_golden.decode_lines(run([cli, "-T", mask, "-X", str(p)])) == want_lines
         assert make_golden.exec_lines(run([cli, "-T", mask, "-q", "-e", "/bin/echo", "-X", str(p)])) == want_exec
 

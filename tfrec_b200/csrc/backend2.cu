@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 	long long last_trig;                  // position of the latest trigger (negative: in an earlier call)
 	// per-demod window bookkeeping lives in lane d
 	const int T_d = (lane < nd) ? cfg.d[lane].timeout : 0x7fffffff;
-	uint32_t n_win = 0, cum = 0, open = 0;
+	uint32_t n_win = 0, cum = 0, open = 0, open_start = 0;
 	WinEntry *wl = (lane < nd) ? p.wins + job.win_off + (size_t)lane * job.win_cap : nullptr;
 	if (p.tile0 == 0) {
 		last_trig = -(long long)st->trig_age;
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 			n_win = st->win_n[lane];
 			cum = st->win_cum[lane];
 			open = st->win_open[lane];
+			if (open && n_win) open_start = wl[n_win - 1].start;
 		}
 	}
 	unsigned long long act_total = 0;
@@ -84,12 +85,13 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 				if (open) {   // close the previous window: it flushed T_d-1 samples after its last trigger
 					const uint32_t end = (uint32_t)(last_trig + T_d - 1);
 					wl[n_win - 1].end = end;
-					cum += end - wl[n_win - 1].start + 1;
+					cum += end - open_start + 1;
 				}
 				if (n_win < job.win_cap) {
 					WinEntry e = { t, 0xffffffffu, cum, 0u };
 					wl[n_win] = e;
 					n_win++;
+					open_start = t;
 				} else {
 					p.counters->overflow = 1;
 				}
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		if (open) {
 			const long long end = last_trig + T_d - 1;   // >= 0 because an open window means last_trig > -T_d
 			wl[n_win - 1].end = (uint32_t)end;
-			cum += (uint32_t)end - wl[n_win - 1].start + 1;
+			cum += (uint32_t)end - open_start + 1;
 		}
 	}
 	if (lane < nd) {
@@ -306,13 +308,29 @@ __device__ __forceinline__ Chunk16 load16(const int32_t *p)
 	c.v[8] = d.x; c.v[9] = d.y; c.v[10] = d.z; c.v[11] = d.w; c.v[12] = e.x; c.v[13] = e.y; c.v[14] = e.z; c.v[15] = e.w;
 	return c;
 }
-// Order-sensitive hash of the slicer input sequence: sum of ld[i] * (2i+1)*K mod 2^64.  Additive, so the
-// terms do not form a dependency chain (the walks are latency bound); a change of one element by d moves the
-// sum by d*(2i+1)*K != 0, two changes cannot cancel unless i == j.
-constexpr unsigned long long kHashK = 0x9E3779B97F4A7C15ull;
-__device__ __forceinline__ unsigned long long ld_term(int ld, uint32_t i)
+// Order-sensitive hash of the slicer input sequence: two 32-bit weighted sums, sum ld[i]*(2i+1) and
+// sum ld[i]*(i*i+i+1), packed into 64 bits.  Additive (no dependency chain; the walks are instruction
+// bound) and cheap (one 32-bit IMAD each).  The sequences compared differ, if at all, by +-1 in isolated
+// places: one change moves the first sum by an odd number, two changes cannot cancel in both sums.
+struct LdHash {
+	uint32_t a, b, w1, w2, dw2;   // running sums and the current position weights
+	__device__ __forceinline__ void init() { a = b = 0; w1 = 1; w2 = 1; dw2 = 2; }
+	__device__ __forceinline__ void add(int ld)
+	{
+		a += (uint32_t)ld * w1;
+		b += (uint32_t)ld * w2;
+		w1 += 2;
+		w2 += dw2;   // i*i+i+1 -> (i+1)^2+(i+1)+1 adds 2i+2
+		dw2 += 2;
+	}
+	__device__ __forceinline__ unsigned long long value() const { return ((unsigned long long)b << 32) | a; }
+};
+// (int)y, truncation toward zero, for |y| < 2^31 without the variable-latency F2I.F64: |y| + 2^52 rounded toward
+// zero leaves floor(|y|) in the low mantissa word; the sign comes back from y's high word
+__device__ __forceinline__ int trunc_to_int(double y)
 {
-	return (unsigned long long)(long long)ld * ((2ull * i + 1ull) * kHashK);
+	const int lo = __double2loint(__dadd_rz(fabs(y), 4503599627370496.0));
+	return (__double2hiint(y) < 0) ? -lo : lo;
 }
 // exact int -> double without the (slow, variable latency) I2F.F64: 2^52 + 2^31 + v, minus the offset
 __device__ __forceinline__ double int_to_double(int v)
@@ -418,7 +436,11 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	int bitcnt = s.bitcnt, dmin = s.dmin, dmax = s.dmax, offset = s.offset, last_bit = s.last_bit, rssi = s.rssi_i,
 	    lbi = s.last_bit_idx;
 	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
-	unsigned long long hash = 0;
+	LdHash hash;
+	hash.init();
+	// the slicer levels only move while bitcnt < 10: keep them out of the per-sample chain
+	int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+	int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
 	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
 	const Chunk16 ck = load16(c.devfm + cb);
 #pragma unroll 4
@@ -436,8 +458,8 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 				c.p->tap_f64[tbase + ti] = y;
 			}
 		}
-		const int ld = __double2int_rz(y);
-		hash += ld_term(ld, m - e.start);
+		const int ld = trunc_to_int(y);
+		hash.add(ld);
 		if (bitcnt < 10) {
 			if (ld > dmax) dmax = (7 * dmax + ld) / 8;
 			if (ld < dmin) dmin = (7 * dmin + ld) / 8;
@@ -448,9 +470,10 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 				const uint32_t sum = (uint32_t)rssi + (uint32_t)(i * i) + (uint32_t)(q * q);
 				rssi = (int)((uint32_t)rssi + (uint32_t)((int)sum / 100));
 			}
+			noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+			hi = noffset + dmax / 32;
+			lo = noffset + dmin / 32;
 		}
-		const int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
-		const int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
 		const int bit = ld > hi ? 1 : 0;
 		if ((ld > hi || ld < lo) && bit != last_bit) {
 			if (far && !have_edge) {
@@ -484,7 +507,7 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	s.last_bit_idx = lbi;
 	rec.e_y0 = lp.y0;
 	rec.e_y1 = lp.y1;
-	rec.ld_hash = hash;
+	rec.ld_hash = hash.value();
 	rec.lbi_end = lbi;
 	rec.lbi_end_block = (int)(last >> 13);
 	if (!far && have_edge) rec.flags |= kRecEdge;
@@ -587,14 +610,14 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 				const BiquadCoef k = cfg.lp;
 				for (int u = v; u < (int)w; u++) {
 					const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
-					for (uint32_t cb = a & ~15u; cb <= b; cb += 16) {
-						const Chunk16 ck = load16(c.devfm + cb);
+					uint32_t m = a;
+					for (; (m & 15u) && m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
+					for (; m + 15 <= b; m += 16) {
+						const Chunk16 ck = load16(c.devfm + m);
 #pragma unroll
-						for (int kk = 0; kk < 16; kk++) {
-							const uint32_t m = cb + kk;
-							if (m >= a && m <= b) biquad_step(lp, k, int_to_double(ck.v[kk]));
-						}
+						for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
 					}
+					for (; m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
 				}
 				s.lp = lp;
 			}
@@ -759,28 +782,33 @@ __global__ void __launch_bounds__(64) edge_repair_kernel(const BackParams p)
 // the biquad alone over a window from a given (true) start state: returns the hash of (int)y and leaves the
 // end state in lp.  This is what the verifier runs when a window's assumed biquad state was not bitwise the
 // true one: if the slicer inputs hash the same, everything the window produced stands.
-static __device__ unsigned long long biquad_only(const WinCtx &c, const DemodCfg &cfg, const WinEntry &e, Biquad &lp)
+static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c, const DemodCfg &cfg, const WinEntry &e, Biquad &lp_io)
 {
+	Biquad lp = lp_io;   // keep the recurrence in registers (a by-reference state would live in local memory)
 	const uint32_t last = min(e.end, c.call_len - 1);
 	const BiquadCoef k = cfg.lp;
 	const bool taps = c.p->tap_cap != 0;
 	const size_t tbase = ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap;
-	unsigned long long hash = 0;
-	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
-		const Chunk16 ck = load16(c.devfm + cb);
-#pragma unroll
-		for (int kk = 0; kk < 16; kk++) {
-			const uint32_t m = cb + kk;
-			if (m < e.start || m > last) continue;
-			const double y = biquad_step(lp, k, int_to_double(ck.v[kk]));
-			if (taps) {
-				const uint32_t ti = e.cum + (m - e.start);
-				if (ti < c.p->tap_cap) c.p->tap_f64[tbase + ti] = y;
-			}
-			hash += ld_term(__double2int_rz(y), m - e.start);
+	LdHash hash;
+	hash.init();
+	auto step = [&](uint32_t m, int dv) {
+		const double y = biquad_step(lp, k, int_to_double(dv));
+		if (taps) {
+			const uint32_t ti = e.cum + (m - e.start);
+			if (ti < c.p->tap_cap) c.p->tap_f64[tbase + ti] = y;
 		}
+		hash.add(trunc_to_int(y));
+	};
+	uint32_t m = e.start;
+	for (; (m & 15u) && m <= last; m++) step(m, c.devfm[m]);            // head up to the first 16-aligned sample
+	for (; m + 15 <= last; m += 16) {                                     // whole chunks: no per-sample predicate
+		const Chunk16 ck = load16(c.devfm + m);
+#pragma unroll
+		for (int kk = 0; kk < 16; kk++) step(m + kk, ck.v[kk]);
 	}
-	return hash;
+	for (; m <= last; m++) step(m, c.devfm[m]);                          // tail
+	lp_io = lp;
+	return hash.value();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,7 +846,7 @@ __global__ void __launch_bounds__(64) cheap_repair_kernel(const BackParams p)
 		rl[w].u_y1 = y1;
 		rl[w].e_y0 = lp.y0;
 		rl[w].e_y1 = lp.y1;
-		atomicAdd(&p.counters->rerun_biquad, 1u);
+		atomicAdd(&p.counters->par_cheap, 1u);
 	}
 }
 
@@ -886,6 +914,7 @@ __global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
 				const bool bq_ok = (__double_as_longlong(rec.u_y0) == __double_as_longlong(lp0.y0)) &&
 						   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp0.y1));
 				const bool edge_ok = tfa2_edge_same(rec, cfg, l, e.start);
+				atomicAdd(&p.counters->ver_checked, 1u);
 				if (bq_ok && edge_ok) continue;   // consistent with the true predecessor state after all
 				bool full = !edge_ok;
 				if (!full) {
@@ -898,7 +927,7 @@ __global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
 						rec.e_y1 = lp.y1;
 						if (rec.flags & kRecUnfinished) st->fin[demod].lp = lp;
 						cheap++;
-						atomicAdd(&p.counters->rerun_biquad, 1u);
+						atomicAdd(&p.counters->ver_cheap, 1u);
 					} else {
 						full = true;
 					}
@@ -916,6 +945,7 @@ __global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
 					run_tfa2_window(c, cfg, e, s, rec, false, false);
 					if (rec.flags & kRecUnfinished) st->fin[demod] = s;
 					reruns++;
+					atomicAdd(&p.counters->ver_full, 1u);
 				}
 				rec.pad = kPadOk;
 				rl[w] = rec;

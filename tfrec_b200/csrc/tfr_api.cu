@@ -464,9 +464,14 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 					if (h->has_fm) {
 						CU(launch_edge_repair(bp, h->dcfg.n_demods, h->stream));
 						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-						CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
-						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-						h->stats.kernel_launches += 4;
+						h->stats.kernel_launches += 2;
+						// a repaired window makes its successor eligible in the next round; stuck trajectories come in
+						// short runs, so three rounds leave the serial verifier almost nothing to do
+						for (int round = 0; round < 3; round++) {
+							CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
+							CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
+							h->stats.kernel_launches += 2;
+						}
 					}
 				}
 				if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
@@ -602,7 +607,9 @@ static int fetch_results(tfr_handle *h)
 	h->stats.windows = c.n_windows;
 	h->stats.reruns = c.n_reruns;
 	h->stats.reruns_sr = c.rerun_sr;
-	h->stats.reruns_biquad = c.rerun_biquad;
+	h->stats.reruns_biquad = c.par_cheap;
+	h->stats.reserved = c.ver_checked;
+	if (getenv("TFR_DEBUG")) fprintf(stderr, "[tfr] windows %llu par_cheap %u edge_par %u | verify: checked %u cheap %u full %u sr %u\n", c.n_windows, c.par_cheap, c.rerun_edge, c.ver_checked, c.ver_cheap, c.ver_full, c.rerun_sr);
 	h->stats.reruns_edge = c.rerun_edge;
 	h->results_valid = true;
 	if (c.overflow) return fail(TFR_E_OVERFLOW, "frame/record buffer overflowed; raise tfr_config.max_frames");
@@ -641,6 +648,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_clear_results(tfr_hand
 	CU(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
 	c.n_frames = c.n_records = c.overflow = 0;
 	c.n_reruns = c.rerun_sr = c.rerun_biquad = c.rerun_edge = 0;
+	c.par_cheap = c.ver_checked = c.ver_cheap = c.ver_full = 0;
 	c.n_windows = 0;
 	CU(cudaMemcpy(h->d_counters, &c, sizeof(c), cudaMemcpyHostToDevice));
 	if (h->d_tap_cnt) CU(cudaMemset(h->d_tap_cnt, 0, (size_t)h->cfg.n_streams * kMaxDemods * 3 * sizeof(uint32_t)));

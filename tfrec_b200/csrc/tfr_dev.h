@@ -182,6 +182,7 @@ struct Counters {
 	unsigned long long active_samples;
 	unsigned long long n_windows;
 	uint32_t rerun_sr, rerun_biquad, rerun_edge, pad2;   // why the verifier re-ran windows
+	uint32_t par_cheap, ver_checked, ver_cheap, ver_full;  // parallel cheap repairs; verifier: flagged windows looked at, cheap fixes, full re-runs
 };
 
 struct FrontParams {
