@@ -113,7 +113,8 @@ typedef struct {
 	uint64_t kernel_launches;   /* kernels launched by this handle */
 	uint64_t windows;           /* demodulator windows decoded (one GPU thread each) */
 	uint64_t reruns;            /* windows the verifier re-ran because a speculated carry-in state was wrong */
-	uint32_t reruns_sr, reruns_biquad, reruns_edge, reserved;   /* ... by cause */
+	uint32_t reruns_sr, reruns_biquad, reruns_edge;   /* ... by cause */
+	uint32_t fallback_epochs;   /* auto threshold: 64-block epochs re-run because the speculative threshold bound failed */
 	double last_frontend_ms;    /* CUDA-event time of the decimate+trigger kernel(s) of the last tfr_process */
 	double last_backend_ms;     /* ... of the demod/framer/parser kernels */
 	double last_h2d_ms;

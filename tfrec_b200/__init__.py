@@ -54,7 +54,7 @@ class Stats(C.Structure):
     _fields_ = [("blocks", C.c_uint64), ("raw_samples", C.c_uint64), ("active_samples", C.c_uint64),
                 ("frames", C.c_uint64), ("records", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("windows", C.c_uint64), ("reruns", C.c_uint64), ("reruns_sr", C.c_uint32), ("reruns_biquad", C.c_uint32),
-                ("reruns_edge", C.c_uint32), ("reserved", C.c_uint32),
+                ("reruns_edge", C.c_uint32), ("fallback_epochs", C.c_uint32),
                 ("last_frontend_ms", C.c_double), ("last_backend_ms", C.c_double), ("last_h2d_ms", C.c_double),
                 ("last_total_ms", C.c_double)]
 

@@ -184,6 +184,7 @@ __global__ void submit_epilogue_kernel(const BackParams p)
 	st->last_q = (int16_t)(lw >> 16);
 	st->carry_in = p.tiles[glast].carry_out;
 	st->blocks_done += job.n_blocks;
+	st->t2_done = 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -31,16 +31,25 @@ namespace tfr {
 
 
 // ------------------------------------------------------------------------------------------------
-// thresh2_kernel: one warp per stream
+// thresh2_kernel: one warp per stream.  Walks the blocks [t2_done, t2_done + n_tiles) of the call in order.
+// The walk is a serial chain (block b's threshold depends on the triggered counts of the blocks before it),
+// so everything that can be taken off the chain is: the event lists of 32 blocks at a time are staged in
+// shared memory with coalesced loads, and the events of a block are tested against the threshold by all
+// lanes at once (ballot) - only true triggers (about one per block in steady state) are handled serially.
 // ------------------------------------------------------------------------------------------------
+constexpr int kT2Stage = 32;   // events per block staged in shared memory (blocks with more fall back to global reads)
 __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 {
-	const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	__shared__ uint32_t s_ev[4][32][kT2Stage];
+	const int wib = threadIdx.x >> 5;
+	const int stream = blockIdx.x * (blockDim.x >> 5) + wib;
 	const int lane = threadIdx.x & 31;
 	if (stream >= p.n_streams) return;
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + stream;
+	const int b0 = (int)st->t2_done;
+	if (b0 >= (int)job.n_blocks) return;   // this stream finished in an earlier launch of the call
 	const DevConfig &cfg = *p.cfg;
 	const int t_max = cfg.t_max;
 	const int nd = cfg.n_demods;
@@ -49,12 +58,14 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs;
 	int c = st->any_timeout;              // samples from `cursor` on that are still covered by a trigger
 	const int mode = st->thresh_mode;
+	// the bound the front-end launch before this one kept samples and events for (it read the same st->thresh)
+	const int thresh_lo = (mode == 1) ? thresh - (p.margin ? p.margin : spec_margin(thresh)) : thresh;
 	long long last_trig;                  // position of the latest trigger (negative: in an earlier call)
 	// per-demod window bookkeeping lives in lane d
 	const int T_d = (lane < nd) ? cfg.d[lane].timeout : 0x7fffffff;
 	uint32_t n_win = 0, cum = 0, open = 0, open_start = 0;
 	WinEntry *wl = (lane < nd) ? p.wins + job.win_off + (size_t)lane * job.win_cap : nullptr;
-	if (p.tile0 == 0) {
+	if (b0 == 0) {
 		last_trig = -(long long)st->trig_age;
 		if (lane < nd && st->d[lane].timeout_cnt > 0) {   // a window was open when the previous call ended
 			WinEntry e = { 0u, 0xffffffffu, 0u, kWinCont };
@@ -72,7 +83,8 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		}
 	}
 	unsigned long long act_total = 0;
-	const int t_end = min(p.tile0 + p.n_tiles, (int)job.n_blocks);
+	const int t_end = min(b0 + p.n_tiles, (int)job.n_blocks);
+	int t_stop = t_end;                   // first block NOT walked (a violated bound stops the walk early)
 
 	// one trigger at position t (inside the call): coverage for the "any demod active" count and window lists
 	auto on_trigger = [&](uint32_t t, uint32_t &cursor, int &triggered) {
@@ -101,91 +113,94 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		last_trig = t;
 	};
 
-	// blocks are taken 32 at a time: lane L fetches block L's trigger count and first four events up front, so
-	// that the serial walk below touches memory only for blocks with more than four events
-	for (int tile0 = p.tile0; tile0 < t_end; tile0 += 32) {
-	uint32_t my_n = 0;
-	uint4 my_ev = make_uint4(0, 0, 0, 0);
-	if (tile0 + lane < t_end) {
-		const size_t g = (size_t)job.dec_off + tile0 + lane;
-		my_n = p.tiles[g].n_trig;
-		if (my_n) my_ev = *reinterpret_cast<const uint4 *>(p.events + g * kMaxEvt);
-	}
-	const int tile_hi = min(tile0 + 32, t_end);
-	for (int tile = tile0; tile < tile_hi; tile++) {
-		const size_t gtile = (size_t)job.dec_off + tile;
-		const TileDesc &td = p.tiles[gtile];
-		const int src_lane = tile - tile0;
-		const uint32_t n_trig = __shfl_sync(0xffffffffu, my_n, src_lane);
-		const uint32_t base = (uint32_t)tile * kBlockDec;
-		uint32_t cursor = base;
-		int triggered = 0;
-		if (n_trig <= 4u) {
-			const uint32_t q0 = __shfl_sync(0xffffffffu, my_ev.x, src_lane), q1 = __shfl_sync(0xffffffffu, my_ev.y, src_lane);
-			const uint32_t q2 = __shfl_sync(0xffffffffu, my_ev.z, src_lane), q3 = __shfl_sync(0xffffffffu, my_ev.w, src_lane);
-			for (uint32_t j = 0; j < n_trig; j++) {
-				const uint32_t e = (j == 0) ? q0 : (j == 1) ? q1 : (j == 2) ? q2 : q3;
-				if ((int)(e & 0xffff) > thresh) on_trigger(base + (e >> 16), cursor, triggered);
+	bool stop = false;
+	for (int tile0 = b0; tile0 < t_end && !stop; tile0 += 32) {
+		uint32_t my_n = 0;
+		if (tile0 + lane < t_end) my_n = p.tiles[(size_t)job.dec_off + tile0 + lane].n_trig;
+		const int tile_hi = min(tile0 + 32, t_end);
+		__syncwarp();
+#pragma unroll 8
+		for (int j = 0; j < 32; j++) {
+			const uint32_t nj = __shfl_sync(0xffffffffu, my_n, j);
+			if (nj <= (uint32_t)kMaxEvt && (uint32_t)lane < min(nj, (uint32_t)kT2Stage))
+				s_ev[wib][j][lane] = p.events[((size_t)job.dec_off + tile0 + j) * kMaxEvt + lane];
+		}
+		__syncwarp();
+		for (int tile = tile0; tile < tile_hi; tile++) {
+			if (mode == 1 && thresh < thresh_lo) {   // the front-end's bound does not cover this block: hand back
+				stop = true;
+				t_stop = tile;
+				break;
 			}
-		} else if (n_trig <= (uint32_t)kMaxEvt) {
-			// sparse block: walk the event list; lanes hold 4 events each
-			const uint32_t *ev = p.events + gtile * kMaxEvt;
-			uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-			if ((uint32_t)lane < n_trig) e0 = ev[lane];
-			if ((uint32_t)lane + 32 < n_trig) e1 = ev[lane + 32];
-			if ((uint32_t)lane + 64 < n_trig) e2 = ev[lane + 64];
-			if ((uint32_t)lane + 96 < n_trig) e3 = ev[lane + 96];
-			for (uint32_t j = 0; j < n_trig; j++) {
-				const uint32_t src = (j < 32) ? e0 : (j < 64) ? e1 : (j < 96) ? e2 : e3;
-				const uint32_t e = __shfl_sync(0xffffffffu, src, j & 31);
-				if ((int)(e & 0xffff) > thresh) on_trigger(base + (e >> 16), cursor, triggered);
-			}
-		} else {
-			// dense block (a burst): scan the stored samples 32 at a time.  Every sample of the block that can
-			// be a trigger is stored (it lies in a segment), so scanning the segments is enough.
-			const uint32_t *d = p.dec + gtile * kBlockDec;
-			const int ns = td.n_seg;
-			for (int sgi = 0; sgi < ns; sgi++) {
-				const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
-				for (int m0 = a; m0 < b; m0 += 32) {
-					const int m = m0 + lane;
-					const bool t = (m < b) && (pwr_of(d[m]) > thresh);
-					const unsigned mask = __ballot_sync(0xffffffffu, t);
-					if (mask) {
-						const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
-						on_trigger(base + m0 + pf, cursor, triggered);
-						if (pl != pf) {   // later triggers of the chunk are < 32 apart: they only move the tail
-							triggered += pl - pf;
-							cursor = base + m0 + pl;
-							c = t_max;
-							last_trig = base + m0 + pl;
+			const size_t gtile = (size_t)job.dec_off + tile;
+			const int src_lane = tile - tile0;
+			const uint32_t n_trig = __shfl_sync(0xffffffffu, my_n, src_lane);
+			const uint32_t base = (uint32_t)tile * kBlockDec;
+			uint32_t cursor = base;
+			int triggered = 0;
+			if (n_trig <= (uint32_t)kMaxEvt) {
+				// sparse block: lanes test 32 events at a time, true triggers are taken in order
+				const uint32_t *ev = p.events + gtile * kMaxEvt;
+				for (uint32_t eb = 0; eb < n_trig; eb += 32) {
+					uint32_t e = 0;
+					const bool have = eb + (uint32_t)lane < n_trig;
+					if (have) e = (eb == 0) ? s_ev[wib][src_lane][lane] : ev[eb + lane];
+					unsigned mask = __ballot_sync(0xffffffffu, have && (int)(e & 0xffff) > thresh);
+					while (mask) {
+						const int k = __ffs(mask) - 1;
+						mask &= mask - 1;
+						const uint32_t ek = __shfl_sync(0xffffffffu, e, k);
+						on_trigger(base + (ek >> 16), cursor, triggered);
+					}
+				}
+			} else {
+				// dense block (a burst): scan the stored samples 32 at a time.  Every sample of the block that can
+				// be a trigger is stored (it lies in a segment), so scanning the segments is enough.
+				const TileDesc &td = p.tiles[gtile];
+				const uint32_t *d = p.dec + gtile * kBlockDec;
+				const int ns = td.n_seg;
+				for (int sgi = 0; sgi < ns; sgi++) {
+					const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+					for (int m0 = a; m0 < b; m0 += 32) {
+						const int m = m0 + lane;
+						const bool t = (m < b) && (pwr_of(d[m]) > thresh);
+						const unsigned mask = __ballot_sync(0xffffffffu, t);
+						if (mask) {
+							const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
+							on_trigger(base + m0 + pf, cursor, triggered);
+							if (pl != pf) {   // later triggers of the chunk are < 32 apart: they only move the tail
+								triggered += pl - pf;
+								cursor = base + m0 + pl;
+								c = t_max;
+								last_trig = base + m0 + pl;
+							}
 						}
 					}
 				}
 			}
+			{
+				const int gap = (int)(base + kBlockDec - cursor), use = min(c, gap);
+				triggered += use;
+				c -= use;
+			}
+			// fm_demod.cpp:58-73
+			runs++;
+			const int used = thresh;
+			avg = (31 * avg + triggered) / 32;
+			if (mode == 1 && (runs & 3) == 0) {
+				if (avg >= kIdxPerBlock / 32) thresh += 2;
+				else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
+			}
+			if (lane == 0) {
+				BlockTrace bt = { used, triggered, avg };
+				p.trace[gtile] = bt;
+			}
+			act_total += (unsigned long long)triggered;
 		}
-		{
-			const int gap = (int)(base + kBlockDec - cursor), use = min(c, gap);
-			triggered += use;
-			c -= use;
-		}
-		// fm_demod.cpp:58-73
-		runs++;
-		const int used = thresh;
-		avg = (31 * avg + triggered) / 32;
-		if (mode == 1 && (runs & 3) == 0) {
-			if (avg >= kIdxPerBlock / 32) thresh += 2;
-			else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
-		}
-		if (lane == 0) {
-			BlockTrace bt = { used, triggered, avg };
-			p.trace[gtile] = bt;
-		}
-		act_total += (unsigned long long)triggered;
-	}
 	}
 
-	if (p.last_epoch && lane < nd) {
+	const bool finished = (t_stop == (int)job.n_blocks);
+	if (finished && lane < nd) {
 		if (open) {
 			const long long end = last_trig + T_d - 1;   // >= 0 because an open window means last_trig > -T_d
 			wl[n_win - 1].end = (uint32_t)end;
@@ -203,10 +218,12 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		st->runs = runs;
 		st->any_timeout = c;
 		st->call_last_trig = (int32_t)max(last_trig, (long long)INT32_MIN / 2);
-		if (p.last_epoch) {
+		if (finished) {
 			const long long age = (long long)call_len - last_trig;
 			st->trig_age = (int32_t)min(age, (long long)INT32_MAX / 2);
 		}
+		st->t2_done = (uint32_t)t_stop;   // == n_blocks when finished; submit_epilogue_kernel clears it for the next call
+		if (p.progress) p.progress[stream] = (uint32_t)t_stop;
 		if (act_total) atomicAdd(&p.counters->active_samples, act_total);
 	}
 }

@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	const int tid = threadIdx.x;
 	const int stream = blockIdx.y;
 	const StreamJob job = p.jobs[stream];
-	const int tile = p.tile0 + blockIdx.x;            // block index inside the submit
-	if (tile >= (int)job.n_blocks) return;
 	StreamState *st = p.st + stream;
+	const int tile = (p.use_progress ? (int)st->t2_done : p.tile0) + blockIdx.x;   // block index inside the submit
+	if (tile >= (int)job.n_blocks) return;
 
 	const uint32_t bar = smem_u32(smem);
 	const uint8_t *src = job.iq + (size_t)tile * kBlockBytes;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	tma_bulk_g2s(smem_u32(smem + kRow0 + tid * kRowStride), src + tid * kRowBytes, kRowBytes, bar);
 
 	int thresh_lo = st->thresh;
-	if (st->thresh_mode) thresh_lo -= 2 * ((p.epoch_blocks + 3) / 4);
+	if (st->thresh_mode) thresh_lo -= p.margin ? p.margin : spec_margin(thresh_lo);
 
 	mbar_wait(bar, 0);
 

@@ -106,8 +106,10 @@ struct tfr_handle {
 	// bookkeeping
 	std::vector<PendingSubmit> pend;
 	std::vector<StreamJob> jobs;       // jobs of the last tfr_process
-	std::vector<cudaEvent_t> ev;       // front-end start/stop pairs then back-end pairs, per epoch
-	int n_epochs_last = 0, n_epochs_total = 0;
+	std::vector<cudaEvent_t> ev;       // front-end start/stop pairs (one per front-end launch), then the end of the call
+	int n_fe_last = 0;                 // front-end launches of the last tfr_process (0: nothing to time)
+	uint32_t *d_progress = nullptr;    // [stream] blocks walked by the threshold kernel
+	uint32_t *h_progress = nullptr;    // pinned host copy
 	cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
 	bool h2d_timed = false;
 	tfr_stats stats;
@@ -182,7 +184,8 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	cudaFree(h->d_frames); cudaFree(h->d_records); cudaFree(h->d_tiles); cudaFree(h->d_dec);
 	cudaFree(h->d_trace); cudaFree(h->d_events); cudaFree(h->d_devfm); cudaFree(h->d_wins); cudaFree(h->d_recs);
 	for (auto &c : h->arena) cudaFree(c.ptr); cudaFree(h->d_tap_i32[0]); cudaFree(h->d_tap_i32[1]);
-	cudaFree(h->d_tap_f64); cudaFree(h->d_tap_cnt);
+	cudaFree(h->d_tap_f64); cudaFree(h->d_tap_cnt); cudaFree(h->d_progress);
+	if (h->h_progress) cudaFreeHost(h->h_progress);
 	for (auto e : h->ev) cudaEventDestroy(e);
 	if (h->ev_h2d0) cudaEventDestroy(h->ev_h2d0);
 	if (h->ev_h2d1) cudaEventDestroy(h->ev_h2d1);
@@ -244,6 +247,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaMemcpy(h->d_state, init.data(), sizeof(StreamState) * cfg->n_streams, cudaMemcpyHostToDevice));
 	}
 	CUH(cudaMalloc(&h->d_jobs, sizeof(StreamJob) * cfg->n_streams));
+	CUH(cudaMalloc(&h->d_progress, sizeof(uint32_t) * cfg->n_streams));
+	CUH(cudaMemset(h->d_progress, 0, sizeof(uint32_t) * cfg->n_streams));
+	CUH(cudaMallocHost(&h->h_progress, sizeof(uint32_t) * cfg->n_streams));
 	CUH(cudaMalloc(&h->d_counters, sizeof(Counters)));
 	CUH(cudaMemset(h->d_counters, 0, sizeof(Counters)));
 	CUH(cudaMalloc(&h->d_frames, sizeof(DevFrame) * h->max_frames));
@@ -384,20 +390,18 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		ps.pending = false;
 	}
 	for (auto &c : h->arena) c.used = 0;   // contents stay valid until the next submit overwrites them (stream ordered)
-	h->n_epochs_last = 0;
+	h->n_fe_last = 0;
 	if (total == 0) return TFR_OK;
 	if (total > 0x7ffffffull || total_wins > 0xffffffffull) return fail(TFR_E_INVAL, "tfr_process: too many blocks in one call");
 	int rc = ensure_blocks(h, total, total_wins);
 	if (rc) return rc;
 	CU(cudaMemcpyAsync(h->d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, h->stream));
 
-	// In auto-threshold mode the threshold may drift by 2 every 4th block (fm_demod.cpp:63-72); the
-	// front-end keeps windows for a lower bound that holds for one epoch, then the threshold kernel
-	// publishes the exact per-block values before the next epoch's front-end launch reads them.
+	// Auto threshold: the whole call is first run against a speculative lower bound of the threshold (see
+	// spec_margin in tfr_dev.h).  The threshold kernel stops a stream where the bound fails; the rest of such a
+	// stream is redone in epochs of kEpochBlocks blocks, each with a bound that provably holds for the epoch.
 	const bool auto_mode = (h->dcfg.thresh_cfg == 0);
-	const uint32_t epoch = auto_mode ? 64u : max_blocks;
-	const int n_epochs = (int)((max_blocks + epoch - 1) / epoch);
-	rc = ensure_events(h, (size_t)n_epochs * 4);
+	rc = ensure_events(h, 3);
 	if (rc) return rc;
 
 	FrontParams fp;
@@ -407,8 +411,11 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	fp.dec = h->d_dec;
 	fp.t_max = h->dcfg.t_max;
 	fp.keep_all = (h->cfg.flags & TFR_FLAG_KEEP_DECIM) ? 1 : 0;
-	fp.epoch_blocks = (int)epoch;
 	fp.events = h->d_events;
+	fp.tile0 = 0;
+	fp.n_tiles = (int)max_blocks;
+	fp.margin = 0;
+	fp.use_progress = 0;
 	BackParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.cfg = h->d_cfg;
@@ -433,60 +440,79 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.recs = h->d_recs;
 	bp.devfm = h->d_devfm;
 	bp.max_blocks = (int)max_blocks;
+	bp.tile0 = 0;
+	bp.n_tiles = (int)max_blocks;
+	bp.margin = 0;
+	bp.progress = h->d_progress;
 	if (h->d_tap_cnt) CU(cudaMemsetAsync(h->d_tap_cnt, 0, (size_t)ns * kMaxDemods * 3 * sizeof(uint32_t), h->stream));   // taps cover one tfr_process
 
-	for (int e = 0; e < n_epochs; e++) {
-		const int tile0 = (int)(e * epoch);
-		const int nt = (int)std::min<uint32_t>(epoch, max_blocks - tile0);
-		fp.tile0 = tile0;
-		fp.n_tiles = nt;
-		bp.tile0 = tile0;
-		bp.n_tiles = nt;
-		bp.last_epoch = (e == n_epochs - 1);
-		CU(cudaEventRecord(h->ev[4 * e + 0], h->stream));
-		CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
-		CU(cudaEventRecord(h->ev[4 * e + 1], h->stream));
-		CU(cudaEventRecord(h->ev[4 * e + 2], h->stream));
-		CU(launch_thresh2(bp, h->stream));
-		h->stats.kernel_launches += 2;
-		if (e == n_epochs - 1) {
-			// everything below runs once per call, over all blocks
-			bp.tile0 = 0;
-			bp.n_tiles = (int)max_blocks;
-			if (h->dcfg.n_demods) {
-				if (h->has_fm) { CU(launch_devfm(bp, h->stream)); h->stats.kernel_launches += 1; }
-				const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
-				if (has_win) {
-					CU(launch_win(bp, h->dcfg.n_demods, h->stream));
-					h->stats.kernel_launches += 1;
+	int n_fe = 0;
+	CU(cudaEventRecord(h->ev[0], h->stream));
+	CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
+	CU(cudaEventRecord(h->ev[1], h->stream));
+	n_fe = 1;
+	CU(launch_thresh2(bp, h->stream));
+	h->stats.kernel_launches += 2;
+	if (auto_mode) {
+		CU(cudaMemcpyAsync(h->h_progress, h->d_progress, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+		uint32_t remaining = 0;
+		for (int s = 0; s < ns; s++)
+			if (h->jobs[s].n_blocks) remaining = std::max(remaining, h->jobs[s].n_blocks - std::min(h->h_progress[s], h->jobs[s].n_blocks));
+		const int n_fallback = (int)((remaining + kEpochBlocks - 1) / kEpochBlocks);
+		rc = ensure_events(h, (size_t)3 + 2 * n_fallback);
+		if (rc) return rc;
+		fp.use_progress = 1;
+		fp.n_tiles = kEpochBlocks;
+		fp.margin = kEpochMargin;
+		bp.n_tiles = kEpochBlocks;
+		bp.margin = kEpochMargin;
+		for (int e = 0; e < n_fallback; e++) {
+			CU(cudaEventRecord(h->ev[2 * n_fe], h->stream));
+			CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
+			CU(cudaEventRecord(h->ev[2 * n_fe + 1], h->stream));
+			n_fe++;
+			CU(launch_thresh2(bp, h->stream));
+			h->stats.kernel_launches += 2;
+		}
+		h->stats.fallback_epochs += (uint32_t)n_fallback;
+	}
+	{
+		// everything below runs once per call, over all blocks
+		bp.tile0 = 0;
+		bp.n_tiles = (int)max_blocks;
+		if (h->dcfg.n_demods) {
+			if (h->has_fm) { CU(launch_devfm(bp, h->stream)); h->stats.kernel_launches += 1; }
+			const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
+			if (has_win) {
+				CU(launch_win(bp, h->dcfg.n_demods, h->stream));
+				h->stats.kernel_launches += 1;
+				CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
+				h->stats.kernel_launches += 1;
+				if (h->has_fm) {
+					CU(launch_edge_repair(bp, h->dcfg.n_demods, h->stream));
 					CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-					h->stats.kernel_launches += 1;
-					if (h->has_fm) {
-						CU(launch_edge_repair(bp, h->dcfg.n_demods, h->stream));
+					h->stats.kernel_launches += 2;
+					// a repaired window makes its successor eligible in the next round; stuck trajectories come in
+					// short runs, so three rounds leave the serial verifier almost nothing to do
+					for (int round = 0; round < 3; round++) {
+						CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
 						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
 						h->stats.kernel_launches += 2;
-						// a repaired window makes its successor eligible in the next round; stuck trajectories come in
-						// short runs, so three rounds leave the serial verifier almost nothing to do
-						for (int round = 0; round < 3; round++) {
-							CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
-							CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-							h->stats.kernel_launches += 2;
-						}
 					}
 				}
-				if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
-				CU(launch_verify(bp, h->dcfg.n_demods, h->stream));
-				h->stats.kernel_launches += 1;
 			}
-			CU(launch_submit_epilogue(bp, h->stream));
-			CU(launch_save_history(h->d_jobs, h->d_state, ns, h->stream));
-			CU(launch_parse(bp, h->stream));
-			h->stats.kernel_launches += 3;
+			if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
+			CU(launch_verify(bp, h->dcfg.n_demods, h->stream));
+			h->stats.kernel_launches += 1;
 		}
-		CU(cudaEventRecord(h->ev[4 * e + 3], h->stream));
+		CU(launch_submit_epilogue(bp, h->stream));
+		CU(launch_save_history(h->d_jobs, h->d_state, ns, h->stream));
+		CU(launch_parse(bp, h->stream));
+		h->stats.kernel_launches += 3;
 	}
-	h->n_epochs_last = n_epochs;
-	h->n_epochs_total = n_epochs;
+	CU(cudaEventRecord(h->ev[2 * n_fe], h->stream));
+	h->n_fe_last = n_fe;
 	h->stats.blocks += total;
 	h->stats.raw_samples += total * (uint64_t)kBlockRaw;
 	h->results_valid = false;
@@ -498,24 +524,21 @@ extern "C" __attribute__((visibility("default"))) int tfr_sync(tfr_handle *h)
 	if (!h) return fail(TFR_E_INVAL, "tfr_sync: null handle");
 	CU(cudaSetDevice(h->device));
 	CU(cudaStreamSynchronize(h->stream));
-	if (h->n_epochs_last) {
-		double fe = 0, be = 0;
-		for (int e = 0; e < h->n_epochs_last; e++) {
-			float a = 0, b = 0;
-			CU(cudaEventElapsedTime(&a, h->ev[4 * e + 0], h->ev[4 * e + 1]));
-			CU(cudaEventElapsedTime(&b, h->ev[4 * e + 2], h->ev[4 * e + 3]));
+	if (h->n_fe_last) {
+		const int n = h->n_fe_last;
+		double fe = 0;
+		for (int e = 0; e < n; e++) {
+			float a = 0;
+			CU(cudaEventElapsedTime(&a, h->ev[2 * e], h->ev[2 * e + 1]));
 			fe += a;
-			be += b;
 		}
+		float all = 0, tot = 0;
+		CU(cudaEventElapsedTime(&all, h->ev[0], h->ev[2 * n]));
+		CU(cudaEventElapsedTime(&tot, h->h2d_timed ? h->ev_h2d0 : h->ev[0], h->ev[2 * n]));
 		h->stats.last_frontend_ms = fe;
-		h->stats.last_backend_ms = be;
-		h->n_epochs_last = 0;
-	}
-	if (h->n_epochs_total) {
-		float a = 0;
-		CU(cudaEventElapsedTime(&a, h->h2d_timed ? h->ev_h2d0 : h->ev[0], h->ev[4 * (h->n_epochs_total - 1) + 3]));
-		h->stats.last_total_ms = a;
-		h->n_epochs_total = 0;
+		h->stats.last_backend_ms = all - fe;
+		h->stats.last_total_ms = tot;
+		h->n_fe_last = 0;
 	}
 	if (h->h2d_timed) {
 		float a = 0;
@@ -608,7 +631,6 @@ static int fetch_results(tfr_handle *h)
 	h->stats.reruns = c.n_reruns;
 	h->stats.reruns_sr = c.rerun_sr;
 	h->stats.reruns_biquad = c.par_cheap;
-	h->stats.reserved = c.ver_checked;
 	if (getenv("TFR_DEBUG")) fprintf(stderr, "[tfr] windows %llu par_cheap %u edge_par %u | verify: checked %u cheap %u full %u sr %u\n", c.n_windows, c.par_cheap, c.rerun_edge, c.ver_checked, c.ver_cheap, c.ver_full, c.rerun_sr);
 	h->stats.reruns_edge = c.rerun_edge;
 	h->results_valid = true;

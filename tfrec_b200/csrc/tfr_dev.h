@@ -95,6 +95,8 @@ struct alignas(128) StreamState {
 	// scratch of the current process call (threshold kernel -> window kernels)
 	int32_t call_last_trig;       // position of the last trigger seen so far in this call (negative: before the call)
 	uint32_t call_cursor;         // coverage cursor
+	uint32_t t2_done;             // blocks of this call the threshold kernel has walked (0 between calls)
+	uint32_t t2_pad;
 	uint32_t win_n[kMaxDemods];   // windows listed so far per demod
 	uint32_t win_cum[kMaxDemods]; // active samples in closed windows
 	uint32_t win_open[kMaxDemods];// 1 if the last listed window is still open
@@ -174,6 +176,20 @@ struct DevRecord {
 
 struct BlockTrace { int32_t thresh, triggered, triggered_avg; };
 
+// Auto threshold (fm_demod.cpp:58-73) moves by 2 every 4th block as a function of the blocks before it, so the
+// front-end cannot know a block's threshold.  It keeps everything above a lower bound instead.  The whole call
+// is first run against thresh_at_call_start - spec_margin(): in steady state the threshold wanders by a few
+// steps only, so this speculation normally holds for every block; the threshold kernel stops a stream at the
+// first block whose true threshold fell below the bound and the host re-runs the rest of that stream in epochs
+// of kEpochBlocks blocks with the provable bound 2*ceil(kEpochBlocks/4).
+constexpr int kEpochBlocks = 64;
+constexpr int kEpochMargin = 2 * ((kEpochBlocks + 3) / 4);
+__host__ __device__ inline int spec_margin(int thresh)
+{
+	const int m = ((thresh >> 4) + 1) & ~1;
+	return m < 16 ? 16 : m;
+}
+
 struct Counters {
 	uint32_t n_frames;
 	uint32_t n_records;
@@ -194,7 +210,9 @@ struct FrontParams {
 	int n_tiles;           // blocks in this epoch (grid.x)
 	int t_max;
 	int keep_all;          // TFR_FLAG_KEEP_DECIM: write every sample
-	int epoch_blocks;      // bound on threshold drift: thresh_lo = thresh - 2*ceil(epoch_blocks/4) in auto mode
+	int margin;            // auto threshold: the launch keeps every sample with pwr > thresh - margin (thresh as of
+	                       // the launch); 0 = the speculative whole-call margin spec_margin(thresh)
+	int use_progress;      // 1: a stream's first block of this launch is its StreamState::t2_done (epoch fallback)
 	uint32_t *events;      // [gtile][kMaxEvt]
 };
 
@@ -215,7 +233,8 @@ struct BackParams {
 	uint32_t max_frames, max_records;
 	int tile0, n_tiles;      // epoch range inside the submit
 	int n_streams;
-	int last_epoch;          // 1: this epoch ends the submit -> roll stream state forward
+	int margin;              // same meaning and value as FrontParams::margin of the front-end launch before it
+	uint32_t *progress;      // [stream] blocks walked so far by the threshold kernel (host reads it back)
 	const uint32_t *events;  // [gtile][kMaxEvt] (pos<<16 | pwr) of samples with pwr > thresh_lo, in order
 	WinEntry *wins;
 	WinRec *recs;
