@@ -562,12 +562,34 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// win_kernel: one thread per window; blockIdx.y = stream, blockIdx.z = registered demod
+// win_kernel: one thread per window CHAIN; blockIdx.y = stream, blockIdx.z = registered demod (longest
+// timeout first, so that the slowest windows start first).
+//
+// TFA_2 family: a window that begins within T_d+1 samples of its predecessor's end is `near`: the
+// predecessor's last edge candidate can be less than 32 bit periods old (tfa2.cpp:395-397), so the "last
+// edge is far in the past" speculation is unsafe for it.  Near windows are not speculated at all: the thread
+// that ran the predecessor carries on into them with the biquad state and last_bit_idx it holds, exactly as
+// the reference does.  A chain starts at a window that is not near (the speculation is then provably right
+// unless last_bit_idx is the 0 sentinel, which verify_kernel catches) and is cut every kChainMax windows to
+// bound the tail latency.  TFA_1 windows carry only the decoder shift register and stay one per thread.
 // ------------------------------------------------------------------------------------------------
+constexpr int kChainMax = 8;
+__device__ __forceinline__ bool win_near(const WinEntry *wl, uint32_t w, int timeout)
+{
+	return wl[w].start - wl[w - 1].end <= (uint32_t)timeout + 1u;
+}
+// pure function of the window list, so that every thread agrees on where chains begin
+__device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int timeout)
+{
+	uint32_t k = 0;
+	while (w - k > 0 && k < 8u * kChainMax && win_near(wl, w - k, timeout)) k++;
+	return (k % kChainMax) == 0;
+}
+
 __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 {
 	const int stream = blockIdx.y;
-	const int demod = blockIdx.z;
+	const int demod = (int)gridDim.z - 1 - (int)blockIdx.z;
 	const DemodCfg &cfg = p.cfg->d[demod];
 	if (cfg.kind == K_WHB) return;
 	const StreamJob job = p.jobs[stream];
@@ -577,73 +599,94 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
 	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	const bool chains = (cfg.kind != K_TFA1);
 
-	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
-		const WinEntry e = wl[w];
-		if (e.start >= c.call_len) continue;
-		WinRec rec;
-		rec.frame_idx = -1;
-		rec.flags = 0;
-		rec.first_edge = rec.first_edge_block = 0;
-		rec.pad = 0;
+	for (uint32_t w0 = blockIdx.x * blockDim.x + threadIdx.x; w0 < n_win; w0 += gridDim.x * blockDim.x) {
+		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
 		DemodState s;
-		const bool cont = (e.flags & kWinCont) != 0;
-		if (w == 0) {
-			// the first window of a call starts from the true carried state: nothing to speculate
-			s = st->d[demod];
-			if (!cont && cfg.kind != K_TFA1) s.last_bit_idx = lbi_at_block(s.last_bit_idx, -1, (int)(e.start >> 13));
-			if (cont && s.last_bit_idx) s.last_bit_idx -= kIdxPerBlock;   // demodulator::start for block 0
-			rec.flags = kRecExact;
-		} else {
-			memset(&s, 0, sizeof(s));
-		}
-		if (cfg.kind == K_TFA1) {
-			run_tfa1_window(c, e, s, rec, cont);
-		} else {
-			bool far = true;
+		bool have_lbi = false;   // s.last_bit_idx is the value the reference would hold (given the chain head's start state)
+		for (uint32_t w = w0; w < n_win; w++) {
+			if (w != w0 && (!chains || chain_head(wl, w, cfg.timeout))) break;
+			const WinEntry e = wl[w];
+			if (e.start >= c.call_len) break;
+			WinRec rec;
+			rec.frame_idx = -1;
+			rec.flags = 0;
+			rec.first_edge = rec.first_edge_block = 0;
+			rec.pad = 0;
+			rec.lbi_in = 0;
+			const bool cont = (e.flags & kWinCont) != 0;
 			if (w == 0) {
-				far = false;
-			} else {
-				// biquad warm-up over the samples of the preceding windows of this demod (they are the
-				// filter's actual history); reaching window 0 means the true carried state can be used
-				const uint32_t want = 3u * (uint32_t)cfg.timeout;
-				uint32_t have = 0;
-				int v = (int)w;
-				uint32_t from = e.start;
-				while (v > 0 && have < want) {
-					v--;
-					const uint32_t len = wl[v].end - wl[v].start + 1;
-					if (have + len >= want && v > 0) {
-						from = wl[v].end + 1 - (want - have);
-						have = want;
-					} else {
-						from = wl[v].start;
-						have += len;
-					}
-				}
-				Biquad lp;
-				lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
-				if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
-				const BiquadCoef k = cfg.lp;
-				for (int u = v; u < (int)w; u++) {
-					const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
-					uint32_t m = a;
-					for (; (m & 15u) && m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
-					for (; m + 15 <= b; m += 16) {
-						const Chunk16 ck = load16(c.devfm + m);
-#pragma unroll
-						for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
-					}
-					for (; m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
-				}
-				s.lp = lp;
+				// the first window of a call starts from the true carried state: nothing to speculate
+				s = st->d[demod];
+				if (!cont && cfg.kind != K_TFA1) s.last_bit_idx = lbi_at_block(s.last_bit_idx, -1, (int)(e.start >> 13));
+				if (cont && s.last_bit_idx) s.last_bit_idx -= kIdxPerBlock;   // demodulator::start for block 0
+				rec.flags = kRecExact;
+				have_lbi = true;
+			} else if (w == w0) {
+				memset(&s, 0, sizeof(s));
 			}
-			rec.u_y0 = s.lp.y0;
-			rec.u_y1 = s.lp.y1;
-			run_tfa2_window(c, cfg, e, s, rec, cont, far);
+			if (cfg.kind == K_TFA1) {
+				run_tfa1_window(c, e, s, rec, cont);
+			} else {
+				bool far = true;
+				if (w == 0) {
+					far = false;
+				} else if (w == w0) {
+					// biquad warm-up over the samples of the preceding windows of this demod (they are the
+					// filter's actual history); reaching window 0 means the true carried state can be used
+					const uint32_t want = 3u * (uint32_t)cfg.timeout;
+					uint32_t have = 0;
+					int v = (int)w;
+					uint32_t from = e.start;
+					while (v > 0 && have < want) {
+						v--;
+						const uint32_t len = wl[v].end - wl[v].start + 1;
+						if (have + len >= want && v > 0) {
+							from = wl[v].end + 1 - (want - have);
+							have = want;
+						} else {
+							from = wl[v].start;
+							have += len;
+						}
+					}
+					Biquad lp;
+					lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
+					if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
+					const BiquadCoef k = cfg.lp;
+					for (int u = v; u < (int)w; u++) {
+						const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
+						uint32_t m = a;
+						for (; (m & 15u) && m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
+						for (; m + 15 <= b; m += 16) {
+							const Chunk16 ck = load16(c.devfm + m);
+#pragma unroll
+							for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
+						}
+						for (; m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
+					}
+					s.lp = lp;
+				} else {
+					// chain member: s is what the predecessor left (run_tfa2_window already did the end-of-window
+					// reset); last_bit_idx moves to this window's first block (demodulator::start, decoder.cpp:118-122)
+					far = !have_lbi;
+					memset(s.rdata, 0, sizeof(s.rdata));   // every window starts from an empty frame buffer
+					if (have_lbi) {
+						const uint32_t plast = min(wl[w - 1].end, c.call_len - 1);
+						s.last_bit_idx = lbi_at_block(s.last_bit_idx, (int)(plast >> 13), (int)(e.start >> 13));
+						rec.flags |= kRecLbiIn;
+						rec.lbi_in = s.last_bit_idx;
+					}
+				}
+				rec.u_y0 = s.lp.y0;
+				rec.u_y1 = s.lp.y1;
+				run_tfa2_window(c, cfg, e, s, rec, cont, far);
+				if (rec.flags & kRecEdge) have_lbi = true;
+			}
+			if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+			rl[w] = rec;
+			if (rec.flags & kRecUnfinished) break;
 		}
-		if (rec.flags & kRecUnfinished) st->fin[demod] = s;
-		rl[w] = rec;
 	}
 }
 
@@ -718,84 +761,6 @@ __device__ __forceinline__ bool tfa2_edge_same(const WinRec &rec, const DemodCfg
 	return c1 && !c2 && (tdiff > 2);
 }
 
-// ------------------------------------------------------------------------------------------------
-// flag_kernel: rec.pad = 1 iff the window's assumed carry-in equals what its predecessor's record says it
-// left behind (parallel over windows; lets the verifier skip consistent runs 32 windows at a time).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) flag_kernel(const BackParams p)
-{
-	const int stream = blockIdx.y, demod = blockIdx.z;
-	const DemodCfg &cfg = p.cfg->d[demod];
-	if (cfg.kind == K_WHB) return;
-	const StreamJob job = p.jobs[stream];
-	if (job.n_blocks == 0) return;
-	StreamState *st = p.st + stream;
-	const uint32_t n_win = st->win_n[demod];
-	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
-	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
-	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
-		int pad = kPadOk;
-		if (w > 0) {
-			const WinRec rec = rl[w];
-			if (cfg.kind == K_TFA1) {
-				if (!tfa1_sync_same(rec, sr_before(rl, (int)w, st->d[demod]))) pad = 0;
-			} else {
-				const WinRec &pr = rl[w - 1];
-				const Lbi l = lbi_after(rl, (int)w - 1, st->d[demod]);
-				const bool bq = (__double_as_longlong(rec.u_y0) == __double_as_longlong(pr.e_y0)) &&
-						(__double_as_longlong(rec.u_y1) == __double_as_longlong(pr.e_y1));
-				const bool edge = tfa2_edge_same(rec, cfg, l, wl[w].start);
-				if (!bq || !edge) pad = 0;
-				if (!edge) {
-					pad |= kPadEdgeRepair;
-					rl[w].lbi_in = lbi_at_block(l.v, l.block, (int)(wl[w].start >> 13));
-				}
-			}
-		}
-		rl[w].pad = pad;
-	}
-}
-
-// edge_repair_kernel: windows whose "last edge is far in the past" assumption fails against the predecessor
-// chain's record are re-run, in parallel, with that record's last_bit_idx.  A window's last_bit_idx after its
-// first edge candidate does not depend on the speculation, so the value handed over is the true one except in
-// corner cases, which verify_kernel still catches.  The re-run keeps the window's own assumed biquad outputs
-// (d1/d2 are data), so the biquad check in verify_kernel applies unchanged.  Only the window's own record is
-// written; the values read from other records were snapshotted into lbi_in by flag_kernel.
-__global__ void __launch_bounds__(64) edge_repair_kernel(const BackParams p)
-{
-	const int stream = blockIdx.y, demod = blockIdx.z;
-	const DemodCfg &cfg = p.cfg->d[demod];
-	if (cfg.kind == K_WHB || cfg.kind == K_TFA1) return;
-	const StreamJob job = p.jobs[stream];
-	if (job.n_blocks == 0) return;
-	StreamState *st = p.st + stream;
-	const uint32_t n_win = st->win_n[demod];
-	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
-	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
-	const WinCtx c = make_ctx(p, stream, demod, job, st);
-	for (uint32_t w = 1 + blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
-		if (!(rl[w].pad & kPadEdgeRepair)) continue;
-		const WinEntry e = wl[w];
-		WinRec rec = rl[w];
-		DemodState s;
-		memset(&s, 0, sizeof(s));
-		s.lp.y0 = rec.u_y0;
-		s.lp.y1 = rec.u_y1;
-		const uint32_t pe = min(wl[w - 1].end, c.call_len - 1);   // the predecessor's last two samples feed d1/d2
-		s.lp.d1 = (double)c.devfm[pe];
-		s.lp.d2 = (pe >= wl[w - 1].start + 1) ? (double)c.devfm[pe - 1] : 0.0;
-		s.last_bit_idx = rec.lbi_in;
-		rec.flags &= ~kRecEdge;
-		rec.flags |= kRecLbiIn;
-		run_tfa2_window(c, cfg, e, s, rec, false, false);
-		if (rec.flags & kRecUnfinished) st->fin[demod] = s;
-		rec.pad = 0;
-		rl[w] = rec;
-		atomicAdd(&p.counters->rerun_edge, 1u);
-	}
-}
-
 // the biquad alone over a window from a given (true) start state: returns the hash of (int)y and leaves the
 // end state in lp.  This is what the verifier runs when a window's assumed biquad state was not bitwise the
 // true one: if the slicer inputs hash the same, everything the window produced stands.
@@ -829,57 +794,33 @@ static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c
 }
 
 // ------------------------------------------------------------------------------------------------
-// cheap_repair_kernel: one parallel round of the verifier's cheap fix.  A window whose assumed biquad outputs
-// differ from what its predecessor's record left behind re-runs the biquad alone from the predecessor's end
-// state; if the slicer inputs hash the same it adopts that state.  The predecessor's record is not
-// necessarily the truth yet, so this only REDUCES the serial work: verify_kernel re-derives everything from
-// the true state and re-checks the successor of every window it changes.  Reads of neighbouring records are
-// limited to fields this kernel never writes for a window with a good flag (only flagged-bad windows whose
-// predecessor is flagged good are touched).
+// verify_kernel: one CTA per (stream, demod) - the exactness backstop, run in parallel rounds.
+//
+// A window's record is TRUE when it was produced from the start state the reference would have had.  Window
+// 0 ran from the true carried state.  A later window is `good` when the carry-in its run assumed is
+// equivalent to what its predecessor's record left behind:
+//     TFA_1         the sync decisions of its first 31 shifts are the same with the predecessor chain's shift
+//                   register as with the empty one it assumed (or it was re-run with exactly that register)
+//     TFA_2 family  its assumed biquad outputs are bitwise the predecessor's end state, and its first edge
+//                   candidate behaves the same with the predecessor chain's last_bit_idx
+// If every window is good, every record is true by induction from window 0.  Each round recomputes the flags
+// (all threads), collects the RUN STARTS (a bad window after a good one) and repairs every run in parallel,
+// one thread per run, following the repaired state into the successors for as long as they disagree with it:
+//     biquad state differs  -> re-run the biquad alone; if the slicer inputs (int)y hash the same, everything
+//                              the window produced stands and it adopts the new start/end state; else full re-run
+//     edge / shift register -> full re-run of the window from the predecessor chain's state
+// Only the first run of a round is certain to start from a true state; a later run may be repaired from a
+// stale predecessor and is then simply flagged again in the next round.  At least one window becomes true per
+// round, so the loop ends, and it ends only when every link has been proven.  Finally thread 0 writes the
+// state carried into the next call.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) cheap_repair_kernel(const BackParams p)
-{
-	const int stream = blockIdx.y, demod = blockIdx.z;
-	const DemodCfg &cfg = p.cfg->d[demod];
-	if (cfg.kind == K_WHB || cfg.kind == K_TFA1) return;
-	const StreamJob job = p.jobs[stream];
-	if (job.n_blocks == 0) return;
-	StreamState *st = p.st + stream;
-	const uint32_t n_win = st->win_n[demod];
-	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
-	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
-	const WinCtx c = make_ctx(p, stream, demod, job, st);
-	for (uint32_t w = 1 + blockIdx.x * blockDim.x + threadIdx.x; w < n_win; w += gridDim.x * blockDim.x) {
-		if ((rl[w].pad & kPadOk) || !(rl[w - 1].pad & kPadOk) || (rl[w].pad & kPadEdgeRepair)) continue;
-		const WinEntry e = wl[w];
-		WinRec rec = rl[w];
-		if (rec.flags & kRecUnfinished) continue;   // the carried state of an open window is the verifier's business
-		Biquad lp = biquad_after(c, wl, rl, (int)w - 1, st->d[demod]);
-		const double y0 = lp.y0, y1 = lp.y1;
-		if (__double_as_longlong(rec.u_y0) == __double_as_longlong(y0) && __double_as_longlong(rec.u_y1) == __double_as_longlong(y1))
-			continue;
-		if (biquad_only(c, cfg, e, lp) != rec.ld_hash) continue;
-		rl[w].u_y0 = y0;
-		rl[w].u_y1 = y1;
-		rl[w].e_y0 = lp.y0;
-		rl[w].e_y1 = lp.y1;
-		atomicAdd(&p.counters->par_cheap, 1u);
-	}
-}
+constexpr int kVerifyThreads = 128;
+struct VerifyCounts { uint32_t cheap, full, sr, rounds; };
 
-// ------------------------------------------------------------------------------------------------
-// verify_kernel: one warp per (stream, demod): the exactness backstop.  Windows whose flag is good and whose
-// predecessor's record did not change are proven by induction from window 0 (which ran from the true
-// state).  Lane 0 repairs the others in stream order with the true carried state:
-//   biquad state differs  -> biquad-only run from the true state; same slicer-input hash => adopt the true
-//                            end state, otherwise full re-run
-//   edge / shift-register assumption wrong -> full re-run
-// and finally writes the state carried into the next call.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
+__global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams p)
 {
 	const int gid = blockIdx.x;
-	const int lane = threadIdx.x;
+	const int tid = threadIdx.x;
 	const int nd = p.cfg->n_demods;
 	if (gid >= p.n_streams * nd) return;
 	const int stream = gid / nd, demod = gid % nd;
@@ -894,84 +835,132 @@ __global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
 	const int last_block = (int)job.n_blocks - 1;
 	const DemodState &carry0 = st->d[demod];   // read in place; overwritten only by the final store below
-	uint32_t reruns = 0, cheap = 0;
-	int force = 0;   // the previous window's record changed: re-check this one whatever its flag says
+	__shared__ uint32_t s_runs[kVerifyThreads];
+	__shared__ uint32_t s_nruns, s_first;
+	uint32_t n_cheap = 0, n_full = 0, n_sr = 0, rounds = 0;
 
-	for (uint32_t base = 0; base < n_win; base += 32) {
-		const uint32_t wq = base + lane;
-		const bool bad = (wq < n_win) && !(rl[wq].pad & kPadOk);
-		const unsigned mask = __ballot_sync(0xffffffffu, bad);
-		if (lane == 0 && (mask || force)) {
-			for (uint32_t k = 0; k < 32 && base + k < n_win; k++) {
-				if (!(((mask >> k) & 1u) || force)) continue;
-				const uint32_t w = base + k;
-				force = 0;
-				if (w == 0) continue;   // window 0 ran from the true state
-				const WinEntry e = wl[w];
-				WinRec rec = rl[w];
-				if (cfg.kind == K_TFA1) {
-					const uint32_t sr = sr_before(rl, (int)w, carry0);
-					if (!(rec.flags & kRecExact) && !tfa1_sync_same(rec, sr)) {
-						DemodState s;
-						memset(&s, 0, sizeof(s));
-						s.sr = sr;
-						run_tfa1_window(c, e, s, rec, false);
-						rec.flags |= kRecExact;
-						if (rec.flags & kRecUnfinished) st->fin[demod] = s;
-						reruns++;
-						atomicAdd(&p.counters->rerun_sr, 1u);
-						rec.pad = kPadOk;
-						rl[w] = rec;
-						force = 1;
-					}
-					continue;
-				}
-				const Biquad lp0 = biquad_after(c, wl, rl, (int)w - 1, carry0);
-				const Lbi l = lbi_after(rl, (int)w - 1, carry0);
-				const bool bq_ok = (__double_as_longlong(rec.u_y0) == __double_as_longlong(lp0.y0)) &&
-						   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp0.y1));
-				const bool edge_ok = tfa2_edge_same(rec, cfg, l, e.start);
-				atomicAdd(&p.counters->ver_checked, 1u);
-				if (bq_ok && edge_ok) continue;   // consistent with the true predecessor state after all
-				bool full = !edge_ok;
-				if (!full) {
-					Biquad lp = lp0;
-					const unsigned long long h = biquad_only(c, cfg, e, lp);
-					if (h == rec.ld_hash) {
-						rec.u_y0 = lp0.y0;
-						rec.u_y1 = lp0.y1;
-						rec.e_y0 = lp.y0;
-						rec.e_y1 = lp.y1;
-						if (rec.flags & kRecUnfinished) st->fin[demod].lp = lp;
-						cheap++;
-						atomicAdd(&p.counters->ver_cheap, 1u);
-					} else {
-						full = true;
-					}
-				}
-				if (full) {
-					DemodState s;
-					memset(&s, 0, sizeof(s));
-					s.lp = lp0;
-					s.last_bit_idx = lbi_at_block(l.v, l.block, (int)(e.start >> 13));
-					rec.lbi_in = s.last_bit_idx;
-					rec.u_y0 = lp0.y0;
-					rec.u_y1 = lp0.y1;
-					rec.flags &= ~kRecEdge;
-					rec.flags |= kRecLbiIn;
-					run_tfa2_window(c, cfg, e, s, rec, false, false);
-					if (rec.flags & kRecUnfinished) st->fin[demod] = s;
-					reruns++;
-					atomicAdd(&p.counters->ver_full, 1u);
-				}
-				rec.pad = kPadOk;
-				rl[w] = rec;
-				force = 1;
+	// is window w (> 0) consistent with the records before it?  edge_bad reports a wrong last_bit_idx assumption
+	auto good = [&](uint32_t w, const WinRec &rec, bool &edge_bad) -> bool {
+		edge_bad = false;
+		if (cfg.kind == K_TFA1) {
+			if (rec.flags & kRecExact) return true;
+			const uint32_t sr = sr_before(rl, (int)w, carry0);
+			if (rec.flags & kRecLbiIn) return (uint32_t)rec.lbi_in == sr;
+			return tfa1_sync_same(rec, sr);
+		}
+		const WinRec &pr = rl[w - 1];
+		const bool bq = (__double_as_longlong(rec.u_y0) == __double_as_longlong(pr.e_y0)) &&
+				(__double_as_longlong(rec.u_y1) == __double_as_longlong(pr.e_y1));
+		edge_bad = !tfa2_edge_same(rec, cfg, lbi_after(rl, (int)w - 1, carry0), wl[w].start);
+		return bq && !edge_bad;
+	};
+
+	for (;;) {
+		if (tid == 0) {
+			s_nruns = 0;
+			s_first = 0xffffffffu;
+		}
+		// ---- flags
+		for (uint32_t w = tid; w < n_win; w += kVerifyThreads) {
+			int pad = kPadOk;
+			if (w > 0) {
+				bool eb;
+				if (!good(w, rl[w], eb)) pad = 0;
+			}
+			rl[w].pad = pad;
+		}
+		__syncthreads();
+		// ---- run starts
+		for (uint32_t w = 1 + tid; w < n_win; w += kVerifyThreads) {
+			if (!(rl[w].pad & kPadOk) && (rl[w - 1].pad & kPadOk)) {
+				const uint32_t k = atomicAdd(&s_nruns, 1u);
+				if (k < (uint32_t)kVerifyThreads) s_runs[k] = w;   // the rest waits for the next round
+				atomicMin(&s_first, w);
 			}
 		}
-		force = __shfl_sync(0xffffffffu, force, 0);
+		__syncthreads();
+		const uint32_t n_runs = min(s_nruns, (uint32_t)kVerifyThreads);
+		if (n_runs == 0) break;
+		// the first run is the one whose repair is certainly final: it must be in every round (a duplicate entry
+		// only repeats the same deterministic work)
+		if (tid == 0 && s_nruns > (uint32_t)kVerifyThreads) s_runs[0] = s_first;
+		__syncthreads();
+		rounds++;
+		// ---- repair, one thread per run
+		if ((uint32_t)tid < n_runs) {
+			const uint32_t w = s_runs[tid];
+			if (cfg.kind == K_TFA1) {
+				for (uint32_t v = w; v < n_win; v++) {
+					WinRec rec = rl[v];
+					if (v != w && !(rec.pad & kPadOk) && (rl[v - 1].pad & kPadOk)) break;   // another thread's run
+					bool eb;
+					if (good(v, rec, eb)) break;
+					const uint32_t sr = sr_before(rl, (int)v, carry0);
+					DemodState s;
+					memset(&s, 0, sizeof(s));
+					s.sr = sr;
+					run_tfa1_window(c, wl[v], s, rec, false);
+					rec.flags |= kRecLbiIn;
+					rec.lbi_in = (int32_t)sr;
+					if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+					rl[v] = rec;
+					n_sr++;
+				}
+			} else {
+				Biquad lp = biquad_after(c, wl, rl, (int)w - 1, carry0);
+				for (uint32_t v = w; v < n_win; v++) {
+					WinRec rec = rl[v];
+					if (v != w && !(rec.pad & kPadOk) && (rl[v - 1].pad & kPadOk)) break;   // another thread's run
+					const WinEntry e = wl[v];
+					const Lbi l = lbi_after(rl, (int)v - 1, carry0);
+					const bool bq_ok = (__double_as_longlong(rec.u_y0) == __double_as_longlong(lp.y0)) &&
+							   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp.y1));
+					const bool edge_ok = tfa2_edge_same(rec, cfg, l, e.start);
+					if (bq_ok && edge_ok) break;   // consistent from here on
+					bool full = !edge_ok;
+					if (!full) {
+						Biquad t = lp;
+						if (biquad_only(c, cfg, e, t) == rec.ld_hash) {
+							rec.u_y0 = lp.y0;
+							rec.u_y1 = lp.y1;
+							rec.e_y0 = t.y0;
+							rec.e_y1 = t.y1;
+							if (rec.flags & kRecUnfinished) st->fin[demod].lp = t;
+							lp = t;
+							n_cheap++;
+						} else {
+							full = true;
+						}
+					}
+					if (full) {
+						DemodState s;
+						memset(&s, 0, sizeof(s));
+						s.lp = lp;
+						s.last_bit_idx = lbi_at_block(l.v, l.block, (int)(e.start >> 13));
+						rec.lbi_in = s.last_bit_idx;
+						rec.u_y0 = lp.y0;
+						rec.u_y1 = lp.y1;
+						rec.flags &= ~kRecEdge;
+						rec.flags |= kRecLbiIn;
+						run_tfa2_window(c, cfg, e, s, rec, false, false);
+						if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+						lp = s.lp;
+						n_full++;
+					}
+					rl[v] = rec;
+					if (rec.flags & kRecUnfinished) break;
+				}
+			}
+		}
+		__syncthreads();
 	}
-	if (lane != 0) return;
+
+	if (n_cheap) atomicAdd(&p.counters->par_cheap, n_cheap);
+	if (n_full) atomicAdd(&p.counters->ver_full, n_full);
+	if (n_sr) atomicAdd(&p.counters->rerun_sr, n_sr);
+	if (n_full + n_sr) atomicAdd(&p.counters->n_reruns, n_full + n_sr);
+	if (tid != 0) return;
+	if (rounds) atomicAdd(&p.counters->ver_checked, rounds);
 
 	bool unfinished = false;
 	if (n_win) unfinished = (rl[n_win - 1].flags & kRecUnfinished) != 0;
@@ -1006,8 +995,6 @@ __global__ void __launch_bounds__(32) verify_kernel(const BackParams p)
 		}
 		out.last_bit_idx = lbi_end;
 	}
-	if (reruns) atomicAdd(&p.counters->n_reruns, reruns);
-	(void)cheap;
 	if (n_win) atomicAdd(&p.counters->n_windows, (unsigned long long)n_win);
 	if (p.tap_cap) {
 		uint32_t *tc = p.tap_cnt + ((size_t)stream * kMaxDemods + demod) * 3;
@@ -1053,24 +1040,9 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 	win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
 	return cudaGetLastError();
 }
-cudaError_t launch_flag(const BackParams &p, int n_demods, cudaStream_t s)
-{
-	flag_kernel<<<win_grid(p, n_demods, 128), 128, 0, s>>>(p);
-	return cudaGetLastError();
-}
-cudaError_t launch_edge_repair(const BackParams &p, int n_demods, cudaStream_t s)
-{
-	edge_repair_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
-	return cudaGetLastError();
-}
-cudaError_t launch_cheap_repair(const BackParams &p, int n_demods, cudaStream_t s)
-{
-	cheap_repair_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
-	return cudaGetLastError();
-}
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s)
 {
-	verify_kernel<<<p.n_streams * n_demods, 32, 0, s>>>(p);
+	verify_kernel<<<p.n_streams * n_demods, kVerifyThreads, 0, s>>>(p);
 	return cudaGetLastError();
 }
 

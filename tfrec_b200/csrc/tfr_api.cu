@@ -20,9 +20,6 @@ cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_st
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
-cudaError_t launch_flag(const BackParams &p, int n_demods, cudaStream_t s);
-cudaError_t launch_edge_repair(const BackParams &p, int n_demods, cudaStream_t s);
-cudaError_t launch_cheap_repair(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
@@ -487,20 +484,6 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			if (has_win) {
 				CU(launch_win(bp, h->dcfg.n_demods, h->stream));
 				h->stats.kernel_launches += 1;
-				CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-				h->stats.kernel_launches += 1;
-				if (h->has_fm) {
-					CU(launch_edge_repair(bp, h->dcfg.n_demods, h->stream));
-					CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-					h->stats.kernel_launches += 2;
-					// a repaired window makes its successor eligible in the next round; stuck trajectories come in
-					// short runs, so three rounds leave the serial verifier almost nothing to do
-					for (int round = 0; round < 3; round++) {
-						CU(launch_cheap_repair(bp, h->dcfg.n_demods, h->stream));
-						CU(launch_flag(bp, h->dcfg.n_demods, h->stream));
-						h->stats.kernel_launches += 2;
-					}
-				}
 			}
 			if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
 			CU(launch_verify(bp, h->dcfg.n_demods, h->stream));
