@@ -31,19 +31,28 @@ namespace tfr {
 
 
 // ------------------------------------------------------------------------------------------------
-// thresh2_kernel: one warp per stream.  Walks the blocks [t2_done, t2_done + n_tiles) of the call in order.
-// The walk is a serial chain (block b's threshold depends on the triggered counts of the blocks before it),
-// so everything that can be taken off the chain is: the event lists of 32 blocks at a time are staged in
-// shared memory with coalesced loads, and the events of a block are tested against the threshold by all
-// lanes at once (ballot) - only true triggers (about one per block in steady state) are handled serially.
+// thresh2_kernel: one warp per stream; reproduces fsk_demod::process' per-block bookkeeping
+// (fm_demod.cpp:51-73) from the front-end's event lists and lists every demodulator's windows.
+//
+// Block b's threshold depends on the triggered counts of the blocks before it, so the walk over blocks is a
+// serial chain.  What is on the chain is kept minimal.  Blocks are taken in aligned chunks of 32, lane L owning
+// block chunk+L:
+//   1. every lane walks ITS block's events against the current threshold (assumed constant over the chunk):
+//      first/last trigger, samples covered by its own triggers, count, and the first four trigger positions
+//   2. the coverage carried in from the previous block is one shuffle away (a trigger covers t_max < 8192
+//      samples, so it never reaches past the next block)
+//   3. the chain itself: triggered_avg = (31*avg + triggered)/32 and the +-2 threshold step every 4th block,
+//      evaluated by all lanes from shuffled counts - a handful of integer instructions per block.  The blocks
+//      up to and including the first threshold change are accepted; the rest of the chunk is redone with the new
+//      threshold (in steady state the threshold sits in its dead band and whole chunks are accepted)
+//   4. the accepted blocks' true triggers (about one per block) are fed, in order, to the per-demod window
+//      bookkeeping (lane d = demod d).
+// Blocks with more than kMaxEvt events (a burst) have no complete list: the warp scans their stored samples.
 // ------------------------------------------------------------------------------------------------
-constexpr int kT2Stage = 32;   // events per block staged in shared memory (blocks with more fall back to global reads)
-__global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
+__global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 {
-	__shared__ uint32_t s_ev[4][32][kT2Stage];
-	const int wib = threadIdx.x >> 5;
-	const int stream = blockIdx.x * (blockDim.x >> 5) + wib;
-	const int lane = threadIdx.x & 31;
+	const int stream = blockIdx.x;
+	const int lane = threadIdx.x;
 	if (stream >= p.n_streams) return;
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
@@ -56,7 +65,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
 
 	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs;
-	int c = st->any_timeout;              // samples from `cursor` on that are still covered by a trigger
+	int c = st->any_timeout;              // samples at the head of the next block still covered by a trigger
 	const int mode = st->thresh_mode;
 	// the bound the front-end launch before this one kept samples and events for (it read the same st->thresh)
 	const int thresh_lo = (mode == 1) ? thresh - (p.margin ? p.margin : spec_margin(thresh)) : thresh;
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 	WinEntry *wl = (lane < nd) ? p.wins + job.win_off + (size_t)lane * job.win_cap : nullptr;
 	if (b0 == 0) {
 		last_trig = -(long long)st->trig_age;
-		if (lane < nd && st->d[lane].timeout_cnt > 0) {   // a window was open when the previous call ended
+		if (lane < nd && st->win_cont[lane]) {   // a window was open when the previous call ended
 			WinEntry e = { 0u, 0xffffffffu, 0u, kWinCont };
 			wl[0] = e;
 			n_win = 1;
@@ -82,16 +91,12 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 			if (open && n_win) open_start = wl[n_win - 1].start;
 		}
 	}
-	unsigned long long act_total = 0;
+	unsigned long long act_lane = 0;
 	const int t_end = min(b0 + p.n_tiles, (int)job.n_blocks);
 	int t_stop = t_end;                   // first block NOT walked (a violated bound stops the walk early)
 
-	// one trigger at position t (inside the call): coverage for the "any demod active" count and window lists
-	auto on_trigger = [&](uint32_t t, uint32_t &cursor, int &triggered) {
-		const int gap = (int)(t - cursor), use = min(c, gap);
-		triggered += use;
-		c = t_max;
-		cursor = t;
+	// one trigger at position t (inside the call), in order: the window lists
+	auto win_trigger = [&](uint32_t t) {
 		if (lane < nd) {
 			if (!open || (long long)t - last_trig >= T_d) {
 				if (open) {   // close the previous window: it flushed T_d-1 samples after its last trigger
@@ -113,105 +118,196 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		last_trig = t;
 	};
 
-	bool stop = false;
-	for (int tile0 = b0; tile0 < t_end && !stop; tile0 += 32) {
-		uint32_t my_n = 0;
-		if (tile0 + lane < t_end) my_n = p.tiles[(size_t)job.dec_off + tile0 + lane].n_trig;
-		const int tile_hi = min(tile0 + 32, t_end);
-		__syncwarp();
-#pragma unroll 8
-		for (int j = 0; j < 32; j++) {
-			const uint32_t nj = __shfl_sync(0xffffffffu, my_n, j);
-			if (nj <= (uint32_t)kMaxEvt && (uint32_t)lane < min(nj, (uint32_t)kT2Stage))
-				s_ev[wib][j][lane] = p.events[((size_t)job.dec_off + tile0 + j) * kMaxEvt + lane];
+	// lane L's block of a chunk: event count and the first eight events
+	auto fetch = [&](int chunk, uint32_t &n, uint4 &ea, uint4 &eb) {
+		n = 0;
+		ea = eb = make_uint4(0, 0, 0, 0);
+		const int b = chunk + lane;
+		if (b >= b0 && b < t_end) {
+			const size_t g = (size_t)job.dec_off + b;
+			n = p.tiles[g].n_trig;
+			const uint4 *ev = reinterpret_cast<const uint4 *>(p.events + g * kMaxEvt);
+			ea = ev[0];
+			eb = ev[1];
 		}
-		__syncwarp();
-		for (int tile = tile0; tile < tile_hi; tile++) {
-			if (mode == 1 && thresh < thresh_lo) {   // the front-end's bound does not cover this block: hand back
-				stop = true;
-				t_stop = tile;
-				break;
-			}
-			const size_t gtile = (size_t)job.dec_off + tile;
-			const int src_lane = tile - tile0;
-			const uint32_t n_trig = __shfl_sync(0xffffffffu, my_n, src_lane);
-			const uint32_t base = (uint32_t)tile * kBlockDec;
-			uint32_t cursor = base;
-			int triggered = 0;
-			if (n_trig <= (uint32_t)kMaxEvt) {
-				// sparse block: lanes test 32 events at a time, true triggers are taken in order
-				const uint32_t *ev = p.events + gtile * kMaxEvt;
-				for (uint32_t eb = 0; eb < n_trig; eb += 32) {
-					uint32_t e = 0;
-					const bool have = eb + (uint32_t)lane < n_trig;
-					if (have) e = (eb == 0) ? s_ev[wib][src_lane][lane] : ev[eb + lane];
-					unsigned mask = __ballot_sync(0xffffffffu, have && (int)(e & 0xffff) > thresh);
-					while (mask) {
-						const int k = __ffs(mask) - 1;
-						mask &= mask - 1;
-						const uint32_t ek = __shfl_sync(0xffffffffu, e, k);
-						on_trigger(base + (ek >> 16), cursor, triggered);
-					}
+	};
+
+	bool stop = false;
+	int chunk = b0 & ~31;
+	uint32_t n, n_nx;
+	uint4 ea, eb, ea_nx, eb_nx;
+	fetch(chunk, n, ea, eb);
+	int pos = b0;
+	while (pos < t_end && !stop) {
+		fetch(chunk + 32, n_nx, ea_nx, eb_nx);   // in flight while this chunk is walked
+		const int jend = min(32, t_end - chunk);
+		const size_t g = (size_t)job.dec_off + chunk + lane;
+		while (pos < chunk + jend && !stop) {
+			const int theta = thresh;
+			const int j0 = pos - chunk;
+			const bool active = lane >= j0 && lane < jend;
+			// ---- 1. own block against theta
+			int f = -1, l = -1, cov = 0, cnt = 0, cend = 0;
+			uint32_t tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
+			auto own = [&](uint32_t e) {
+				if ((int)(e & 0xffff) > theta) {
+					const int t = (int)(e >> 16);
+					if (f < 0) f = t;
+					const int hi = min(t + t_max, kBlockDec);
+					cov += max(hi - max(t, cend), 0);
+					cend = hi;
+					l = t;
+					if (cnt == 0) tp0 = t; else if (cnt == 1) tp1 = t; else if (cnt == 2) tp2 = t; else if (cnt == 3) tp3 = t;
+					cnt++;
 				}
-			} else {
-				// dense block (a burst): scan the stored samples 32 at a time.  Every sample of the block that can
-				// be a trigger is stored (it lies in a segment), so scanning the segments is enough.
-				const TileDesc &td = p.tiles[gtile];
-				const uint32_t *d = p.dec + gtile * kBlockDec;
+			};
+			if (active && n <= (uint32_t)kMaxEvt) {
+				if (n > 0) own(ea.x);
+				if (n > 1) own(ea.y);
+				if (n > 2) own(ea.z);
+				if (n > 3) own(ea.w);
+				if (n > 4) own(eb.x);
+				if (n > 5) own(eb.y);
+				if (n > 6) own(eb.z);
+				if (n > 7) own(eb.w);
+				const uint32_t *ev = p.events + g * kMaxEvt;
+				for (uint32_t j = 8; j < n; j++) own(ev[j]);
+			}
+			unsigned dense = __ballot_sync(0xffffffffu, active && n > (uint32_t)kMaxEvt);
+			while (dense) {
+				// a burst block: every sample that can be a trigger is stored (it lies in a segment); scan the segments
+				const int j = __ffs(dense) - 1;
+				dense &= dense - 1;
+				const size_t gj = (size_t)job.dec_off + chunk + j;
+				const TileDesc &td = p.tiles[gj];
+				const uint32_t *d = p.dec + gj * kBlockDec;
 				const int ns = td.n_seg;
+				int df = -1, dl = -1, dcov = 0, dcnt = 0, dend = 0;
 				for (int sgi = 0; sgi < ns; sgi++) {
 					const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
 					for (int m0 = a; m0 < b; m0 += 32) {
 						const int m = m0 + lane;
-						const bool t = (m < b) && (pwr_of(d[m]) > thresh);
-						const unsigned mask = __ballot_sync(0xffffffffu, t);
+						const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(d[m]) > theta));
 						if (mask) {
-							const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
-							on_trigger(base + m0 + pf, cursor, triggered);
-							if (pl != pf) {   // later triggers of the chunk are < 32 apart: they only move the tail
-								triggered += pl - pf;
-								cursor = base + m0 + pl;
-								c = t_max;
-								last_trig = base + m0 + pl;
+							const int pf = m0 + __ffs(mask) - 1, pl = m0 + 31 - __clz(mask);
+							if (df < 0) df = pf;
+							const int hi = min(pl + t_max, kBlockDec);   // triggers of one chunk are < 32 < t_max apart
+							dcov += max(hi - max(pf, dend), 0);
+							dend = hi;
+							dl = pl;
+							dcnt += __popc(mask);
+						}
+					}
+				}
+				if (lane == j) { f = df; l = dl; cov = dcov; cnt = dcnt ? dcnt + 1000 : 0; }   // +1000: positions not in tp0..3
+			}
+			// ---- 2. coverage carried in
+			const bool has = cnt > 0;
+			const int out = has ? max(l + t_max - kBlockDec, 0) : 0;
+			int c_in = __shfl_up_sync(0xffffffffu, out, 1);
+			if (lane == j0) c_in = c;
+			const int trig = cov + (has ? min(c_in, f) : c_in);
+			// ---- 3. the chain
+			int acc_end = jend, my_used = 0, my_avg = 0;
+			for (int j = j0; j < jend; j++) {
+				if (mode == 1 && thresh < thresh_lo) {   // the front-end's bound does not cover this block: hand back
+					stop = true;
+					acc_end = j;
+					break;
+				}
+				const int tj = __shfl_sync(0xffffffffu, trig, j);
+				runs++;
+				const int used = thresh;
+				avg = (31 * avg + tj) / 32;
+				if (lane == j) { my_used = used; my_avg = avg; }
+				if (mode == 1 && (runs & 3) == 0) {
+					if (avg >= kIdxPerBlock / 32) thresh += 2;
+					else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
+					if (thresh != used) { acc_end = j + 1; break; }
+				}
+			}
+			const bool accepted = lane >= j0 && lane < acc_end;
+			if (accepted) {
+				BlockTrace bt = { my_used, trig, my_avg };
+				p.trace[g] = bt;
+				act_lane += (unsigned long long)trig;
+			}
+			if (acc_end > j0) c = __shfl_sync(0xffffffffu, out, acc_end - 1);
+			// ---- 4. window lists: the accepted blocks' triggers in order
+			unsigned wm = __ballot_sync(0xffffffffu, accepted && has);
+			while (wm) {
+				const int j = __ffs(wm) - 1;
+				wm &= wm - 1;
+				const int cj = __shfl_sync(0xffffffffu, cnt, j);
+				const uint32_t q0 = __shfl_sync(0xffffffffu, tp0, j), q1 = __shfl_sync(0xffffffffu, tp1, j);
+				const uint32_t q2 = __shfl_sync(0xffffffffu, tp2, j), q3 = __shfl_sync(0xffffffffu, tp3, j);
+				const uint32_t base = (uint32_t)(chunk + j) * kBlockDec;
+				const size_t gj = (size_t)job.dec_off + chunk + j;
+				if (cj <= 4) {
+					win_trigger(base + q0);
+					if (cj > 1) win_trigger(base + q1);
+					if (cj > 2) win_trigger(base + q2);
+					if (cj > 3) win_trigger(base + q3);
+				} else if (cj < 1000) {
+					const uint32_t nj = __shfl_sync(0xffffffffu, n, j);
+					const uint32_t *ev = p.events + gj * kMaxEvt;
+					for (uint32_t e0 = 0; e0 < nj; e0 += 32) {
+						const bool have = e0 + (uint32_t)lane < nj;
+						const uint32_t e = have ? ev[e0 + lane] : 0u;
+						unsigned mask = __ballot_sync(0xffffffffu, have && (int)(e & 0xffff) > theta);
+						while (mask) {
+							const int k = __ffs(mask) - 1;
+							mask &= mask - 1;
+							win_trigger(base + (__shfl_sync(0xffffffffu, e, k) >> 16));
+						}
+					}
+				} else {
+					const TileDesc &td = p.tiles[gj];
+					const uint32_t *d = p.dec + gj * kBlockDec;
+					const int ns = td.n_seg;
+					for (int sgi = 0; sgi < ns; sgi++) {
+						const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+						for (int m0 = a; m0 < b; m0 += 32) {
+							const int m = m0 + lane;
+							const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(d[m]) > theta));
+							if (mask) {
+								const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
+								win_trigger(base + m0 + pf);
+								if (pl != pf) last_trig = base + m0 + pl;   // < 32 apart: they only move the tail
 							}
 						}
 					}
 				}
 			}
-			{
-				const int gap = (int)(base + kBlockDec - cursor), use = min(c, gap);
-				triggered += use;
-				c -= use;
-			}
-			// fm_demod.cpp:58-73
-			runs++;
-			const int used = thresh;
-			avg = (31 * avg + triggered) / 32;
-			if (mode == 1 && (runs & 3) == 0) {
-				if (avg >= kIdxPerBlock / 32) thresh += 2;
-				else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
-			}
-			if (lane == 0) {
-				BlockTrace bt = { used, triggered, avg };
-				p.trace[gtile] = bt;
-			}
-			act_total += (unsigned long long)triggered;
+			pos = chunk + acc_end;
 		}
+		if (stop) {
+			t_stop = pos;
+			break;
+		}
+		chunk += 32;
+		n = n_nx;
+		ea = ea_nx;
+		eb = eb_nx;
 	}
 
 	const bool finished = (t_stop == (int)job.n_blocks);
 	if (finished && lane < nd) {
+		uint32_t cont = 0;
 		if (open) {
 			const long long end = last_trig + T_d - 1;   // >= 0 because an open window means last_trig > -T_d
 			wl[n_win - 1].end = (uint32_t)end;
 			cum += (uint32_t)end - open_start + 1;
+			cont = (end >= (long long)call_len) ? 1u : 0u;   // still running when the data ends: the next call resumes it
 		}
+		st->win_cont[lane] = cont;
 	}
 	if (lane < nd) {
 		st->win_n[lane] = n_win;
 		st->win_cum[lane] = cum;
 		st->win_open[lane] = open;
 	}
+	for (int o = 16; o; o >>= 1) act_lane += __shfl_xor_sync(0xffffffffu, act_lane, o);
 	if (lane == 0) {
 		st->thresh = thresh;
 		st->triggered_avg = avg;
@@ -224,7 +320,7 @@ __global__ void __launch_bounds__(128) thresh2_kernel(const BackParams p)
 		}
 		st->t2_done = (uint32_t)t_stop;   // == n_blocks when finished; submit_epilogue_kernel clears it for the next call
 		if (p.progress) p.progress[stream] = (uint32_t)t_stop;
-		if (act_total) atomicAdd(&p.counters->active_samples, act_total);
+		if (act_lane) atomicAdd(&p.counters->active_samples, act_lane);
 	}
 }
 
@@ -380,15 +476,21 @@ static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, Demod
 	const bool taps = c.p->tap_cap != 0;
 	int32_t *tap = taps ? c.p->tap_i32[1] + ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap : nullptr;
 	uint32_t lw = (e.start == 0) ? c.prev_last : c.dec[e.start - 1];
-	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
-	const Chunk16 ck = load16(reinterpret_cast<const int32_t *>(c.dec) + cb);
-#pragma unroll 4
-	for (int kk = 0; kk < 16; kk++) {
+	// four samples per 128-bit load, the next load issued before the current four are walked; the walk itself is
+	// ONE copy of the per-sample code (rotating the vector) - unrolled copies thrash the instruction cache
+	const int4 *src4 = reinterpret_cast<const int4 *>(c.dec);
+	int4 nxt = src4[(e.start & ~3u) >> 2];
+	for (uint32_t cb = e.start & ~3u; cb <= last; cb += 4) {
+	int4 v4 = nxt;
+	if (cb + 4 <= last) nxt = src4[(cb + 4) >> 2];
+#pragma unroll 1
+	for (int kk = 0; kk < 4; kk++) {
 		const uint32_t m = cb + kk;
+		const uint32_t cw = (uint32_t)v4.x;
+		v4.x = v4.y; v4.y = v4.z; v4.z = v4.w;
 		if (m < e.start || m > last) continue;
 		const int index = 2 * (int)(m & (kBlockDec - 1));
 		if (index == 0 && m != e.start && lbi) lbi -= kIdxPerBlock;
-		const uint32_t cw = (uint32_t)ck.v[kk];
 		const int dev = fm_dev_nrzs((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
 					    (int)(int16_t)(lw >> 16));
 		lw = cw;
@@ -458,15 +560,19 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	// the slicer levels only move while bitcnt < 10: keep them out of the per-sample chain
 	int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
 	int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
-	for (uint32_t cb = e.start & ~15u; cb <= last; cb += 16) {
-	const Chunk16 ck = load16(c.devfm + cb);
-#pragma unroll 4
-	for (int kk = 0; kk < 16; kk++) {
+	const int4 *src4 = reinterpret_cast<const int4 *>(c.devfm);
+	int4 nxt = src4[(e.start & ~3u) >> 2];
+	for (uint32_t cb = e.start & ~3u; cb <= last; cb += 4) {
+	int4 v4 = nxt;
+	if (cb + 4 <= last) nxt = src4[(cb + 4) >> 2];
+#pragma unroll 1
+	for (int kk = 0; kk < 4; kk++) {
 		const uint32_t m = cb + kk;
+		const int dev0 = v4.x;
+		v4.x = v4.y; v4.y = v4.z; v4.z = v4.w;
 		if (m < e.start || m > last) continue;
 		const int index = 2 * (int)(m & (kBlockDec - 1));
 		if (index == 0 && m != e.start && lbi) lbi -= kIdxPerBlock;
-		const int dev0 = ck.v[kk];
 		const double y = biquad_step(lp, k, int_to_double(dev0));
 		if (taps) {
 			const uint32_t ti = e.cum + (m - e.start);
@@ -1019,7 +1125,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 {
-	thresh2_kernel<<<(p.n_streams + 3) / 4, 128, 0, s>>>(p);
+	thresh2_kernel<<<p.n_streams, 32, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)

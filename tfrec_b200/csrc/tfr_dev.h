@@ -100,6 +100,7 @@ struct alignas(128) StreamState {
 	uint32_t win_n[kMaxDemods];   // windows listed so far per demod
 	uint32_t win_cum[kMaxDemods]; // active samples in closed windows
 	uint32_t win_open[kMaxDemods];// 1 if the last listed window is still open
+	uint32_t win_cont[kMaxDemods];// 1 if demod d's last window of the previous call runs on into the next call
 	DemodState d[kMaxDemods];
 	DemodState fin[kMaxDemods];   // state left by an unfinished (ran out of data) last window, pending verification
 };
