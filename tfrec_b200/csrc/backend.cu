@@ -1,7 +1,5 @@
 // backend.cu - everything downstream of the decimator, on the device:
 //
-//   thresh_kernel  fsk_demod::process bookkeeping (fm_demod.cpp:34-74): per block the number of samples
-//                  with any demodulator active, the IIR average and the auto-threshold step
 //   walk_kernel    the per-sample demodulator state machines and bit framers
 //                    TFA_1            tfa1_demod::demod      tfa1.cpp:143-190, store_bit :120-134
 //                    TFA_2/TFA_3/TX22 tfa2_demod::demod      tfa2.cpp:346-442, store_bit :281-314
@@ -22,88 +20,6 @@
 #include "demod_dev.cuh"
 
 namespace tfr {
-
-// ------------------------------------------------------------------------------------------------
-// thresh_kernel: one warp per stream
-// ------------------------------------------------------------------------------------------------
-__global__ void thresh_kernel(const BackParams p)
-{
-	const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	const int lane = threadIdx.x & 31;
-	if (stream >= p.n_streams) return;
-	const StreamJob job = p.jobs[stream];
-	StreamState *st = p.st + stream;
-	const int t_max = p.cfg->t_max;
-
-	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs, c = st->any_timeout;
-	const int mode = st->thresh_mode;
-	int carry_in = entry_carry(p, job, st);
-	const int t_end = min(p.tile0 + p.n_tiles, (int)job.n_blocks);
-	__shared__ Regions s_reg[4];
-	Regions &reg = s_reg[threadIdx.x >> 5];
-	unsigned long long act_total = 0;
-
-	for (int tile = p.tile0; tile < t_end; tile++) {
-		const size_t gtile = (size_t)job.dec_off + tile;
-		const TileDesc &td = p.tiles[gtile];
-		const uint32_t *d = p.dec + gtile * kBlockDec;
-		if (lane == 0) build_regions(td, carry_in, reg);
-		__syncwarp();
-		int triggered = 0, pos = 0;
-		for (int r = 0; r < reg.n; r++) {
-			const int a = reg.start[r], b = reg.end[r];
-			{   // gap before the region
-				const int gap = a - pos, use = min(c, gap);
-				triggered += use;
-				c -= use;
-			}
-			for (int m0 = a; m0 < b; m0 += 32) {
-				const int m = m0 + lane;
-				const bool t = (m < b) && (pwr_of(d[m]) > thresh);
-				const unsigned mask = __ballot_sync(0xffffffffu, t);
-				const int n = min(32, b - m0);
-				if (mask == 0) {
-					const int use = min(c, n);
-					triggered += use;
-					c -= use;
-				} else {
-					const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
-					// [0,c) U [pf, n) is active; after the chunk t_max-(n-pl) samples remain
-					triggered += (c >= pf) ? n : c + (n - pf);
-					c = t_max - (n - pl);
-				}
-			}
-			pos = b;
-		}
-		{
-			const int gap = kBlockDec - pos, use = min(c, gap);
-			triggered += use;
-			c -= use;
-		}
-		// fm_demod.cpp:58-73
-		runs++;
-		const int used = thresh;
-		avg = (31 * avg + triggered) / 32;
-		if (mode == 1 && (runs & 3) == 0) {
-			if (avg >= kIdxPerBlock / 32) thresh += 2;
-			else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
-		}
-		if (lane == 0) {
-			BlockTrace bt = { used, triggered, avg };
-			p.trace[gtile] = bt;
-		}
-		act_total += (unsigned long long)triggered;
-		carry_in = td.carry_out;
-		__syncwarp();
-	}
-	if (lane == 0) {
-		st->thresh = thresh;
-		st->triggered_avg = avg;
-		st->runs = runs;
-		st->any_timeout = c;
-		if (act_total) atomicAdd(&p.counters->active_samples, act_total);
-	}
-}
 
 // ------------------------------------------------------------------------------------------------
 // walk_kernel: one thread per (stream, demod), windows in stream order with carried state
@@ -184,7 +100,6 @@ __global__ void submit_epilogue_kernel(const BackParams p)
 	st->last_q = (int16_t)(lw >> 16);
 	st->carry_in = p.tiles[glast].carry_out;
 	st->blocks_done += job.n_blocks;
-	st->t2_done = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,11 +398,6 @@ __global__ void parse_kernel(const BackParams p)
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_thresh(const BackParams &p, cudaStream_t s)
-{
-	thresh_kernel<<<(p.n_streams + 3) / 4, 128, 0, s>>>(p);
-	return cudaGetLastError();
-}
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s)
 {
 	const int n = p.n_streams * n_demods;

@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 			cont = (end >= (long long)call_len) ? 1u : 0u;   // still running when the data ends: the next call resumes it
 		}
 		st->win_cont[lane] = cont;
+		p.wincnt[stream].n[lane] = n_win;
+		p.wincnt[stream].cum[lane] = cum;
 	}
 	if (lane < nd) {
 		st->win_n[lane] = n_win;
@@ -701,7 +703,7 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + stream;
-	const uint32_t n_win = st->win_n[demod];
+	const uint32_t n_win = p.wincnt[stream].n[demod];
 	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
 	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + stream;
-	const uint32_t n_win = st->win_n[demod];
+	const uint32_t n_win = p.wincnt[stream].n[demod];
 	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
 	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
@@ -1104,7 +1106,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 	if (n_win) atomicAdd(&p.counters->n_windows, (unsigned long long)n_win);
 	if (p.tap_cap) {
 		uint32_t *tc = p.tap_cnt + ((size_t)stream * kMaxDemods + demod) * 3;
-		const uint32_t n = st->win_cum[demod];
+		const uint32_t n = p.wincnt[stream].cum[demod];
 		// taps are written at (cum + offset): the number valid is the demod's active-sample count clipped to the call
 		uint32_t valid = n;
 		if (n_win) {

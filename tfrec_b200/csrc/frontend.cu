@@ -424,7 +424,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	}
 }
 
-// after the last epoch of a submit: remember the FIR history for the next submit (other parity)
+// after the last front-end launch and threshold walk of a call: remember the FIR history for the next call
+// (other parity) and rewind the walk cursor
 __global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int n_streams)
 {
 	const int stream = blockIdx.x;
@@ -436,7 +437,10 @@ __global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int 
 	const uint8_t *src = job.iq + (size_t)job.n_blocks * kBlockBytes - kHistBytes;
 	if (threadIdx.x < kHistBytes) s->hist[par][threadIdx.x] = src[threadIdx.x];
 	__syncthreads();
-	if (threadIdx.x == 0) s->hist_parity = par;
+	if (threadIdx.x == 0) {
+		s->hist_parity = par;
+		s->t2_done = 0;   // the threshold walk of this call is complete; the next call starts at block 0
+	}
 }
 
 cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaStream_t stream)

@@ -75,21 +75,35 @@ struct tfr_handle {
 	// persistent device state
 	DevConfig *d_cfg = nullptr;
 	StreamState *d_state = nullptr;
-	StreamJob *d_jobs = nullptr;
 	Counters *d_counters = nullptr;
 	DevFrame *d_frames = nullptr;
 	DevRecord *d_records = nullptr;
 	uint32_t max_frames = 0, max_records = 0;
-	// per-process work buffers (grown on demand)
-	size_t cap_blocks = 0;
-	TileDesc *d_tiles = nullptr;
-	uint32_t *d_dec = nullptr;
-	BlockTrace *d_trace = nullptr;
-	uint32_t *d_events = nullptr;
-	int32_t *d_devfm = nullptr;
-	size_t cap_wins = 0;
-	WinEntry *d_wins = nullptr;
-	WinRec *d_recs = nullptr;
+	// per-call work buffers (grown on demand), two slots: the back-end of call i (demodulators, verifier, parsers;
+	// latency bound, a few SMs) runs on its own CUDA stream while the front-end and threshold walk of call i+1
+	// (throughput bound) already use the other slot
+	struct Slot {
+		StreamJob *d_jobs = nullptr;
+		TileDesc *d_tiles = nullptr;
+		uint32_t *d_dec = nullptr;
+		BlockTrace *d_trace = nullptr;
+		uint32_t *d_events = nullptr;
+		int32_t *d_devfm = nullptr;
+		WinEntry *d_wins = nullptr;
+		WinRec *d_recs = nullptr;
+		WinCount *d_wincnt = nullptr;
+		size_t cap_blocks = 0, cap_wins = 0;
+		cudaEvent_t front_done = nullptr, back_done = nullptr;   // end of the slot's last front / back work
+		cudaEvent_t fe0 = nullptr, fe1 = nullptr;                // around the speculative front-end launch
+	};
+	Slot slot[2];
+	int cur = 0;                       // slot of the most recent tfr_process
+	cudaStream_t stream_be = nullptr;  // back-end stream
+	bool pipelined = true;             // false: the back-end of a call finishes before the next call starts (taps)
+	cudaEvent_t span0 = nullptr, span1 = nullptr;   // first front-end start / last back-end end since the last tfr_sync
+	bool span_open = false;
+	double fe_ms_acc = 0;              // fallback front-end launches (timed synchronously, rare)
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> fe_pending;   // front-end event pairs not yet read
 	bool has_fm = false, has_whb = false;
 	// input arena for host submits: normally one chunk; more are added when a later submit does not
 	// fit while earlier ones are still pending, and merged into one the next time the arena is idle
@@ -103,8 +117,7 @@ struct tfr_handle {
 	// bookkeeping
 	std::vector<PendingSubmit> pend;
 	std::vector<StreamJob> jobs;       // jobs of the last tfr_process
-	std::vector<cudaEvent_t> ev;       // front-end start/stop pairs (one per front-end launch), then the end of the call
-	int n_fe_last = 0;                 // front-end launches of the last tfr_process (0: nothing to time)
+	std::vector<cudaEvent_t> ev;       // spare events for fallback front-end launches
 	uint32_t *d_progress = nullptr;    // [stream] blocks walked by the threshold kernel
 	uint32_t *h_progress = nullptr;    // pinned host copy
 	cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
@@ -177,15 +190,24 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (!h) return;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_jobs); cudaFree(h->d_counters);
-	cudaFree(h->d_frames); cudaFree(h->d_records); cudaFree(h->d_tiles); cudaFree(h->d_dec);
-	cudaFree(h->d_trace); cudaFree(h->d_events); cudaFree(h->d_devfm); cudaFree(h->d_wins); cudaFree(h->d_recs);
+	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
+	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
+	cudaFree(h->d_frames); cudaFree(h->d_records);
+	for (auto &sl : h->slot) {
+		cudaFree(sl.d_jobs); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
+		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt);
+		for (cudaEvent_t e : { sl.front_done, sl.back_done, sl.fe0, sl.fe1 })
+			if (e) cudaEventDestroy(e);
+	}
 	for (auto &c : h->arena) cudaFree(c.ptr); cudaFree(h->d_tap_i32[0]); cudaFree(h->d_tap_i32[1]);
 	cudaFree(h->d_tap_f64); cudaFree(h->d_tap_cnt); cudaFree(h->d_progress);
 	if (h->h_progress) cudaFreeHost(h->h_progress);
 	for (auto e : h->ev) cudaEventDestroy(e);
 	if (h->ev_h2d0) cudaEventDestroy(h->ev_h2d0);
 	if (h->ev_h2d1) cudaEventDestroy(h->ev_h2d1);
+	if (h->span0) cudaEventDestroy(h->span0);
+	if (h->span1) cudaEventDestroy(h->span1);
+	if (h->stream_be) cudaStreamDestroy(h->stream_be);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 }
@@ -233,6 +255,24 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 					 std::string(#call) + ": " + cudaGetErrorString(e_)));             \
 	} while (0)
 	CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	{   // the back-end kernels are latency bound and small: let their CTAs go first when the front-end of the next
+		// call competes for SMs
+		int prio_lo = 0, prio_hi = 0;
+		CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CUH(cudaStreamCreateWithPriority(&h->stream_be, cudaStreamNonBlocking, prio_hi));
+	}
+	h->pipelined = !(cfg->flags & TFR_FLAG_TAPS);   // the tap buffers are not slotted
+	CUH(cudaEventCreate(&h->span0));
+	CUH(cudaEventCreate(&h->span1));
+	for (auto &sl : h->slot) {
+		CUH(cudaEventCreateWithFlags(&sl.front_done, cudaEventDisableTiming));
+		CUH(cudaEventCreateWithFlags(&sl.back_done, cudaEventDisableTiming));
+		CUH(cudaEventCreate(&sl.fe0));
+		CUH(cudaEventCreate(&sl.fe1));
+		CUH(cudaMalloc(&sl.d_jobs, sizeof(StreamJob) * cfg->n_streams));
+		CUH(cudaMalloc(&sl.d_wincnt, sizeof(WinCount) * cfg->n_streams));
+		CUH(cudaMemset(sl.d_wincnt, 0, sizeof(WinCount) * cfg->n_streams));
+	}
 	CUH(cudaEventCreate(&h->ev_h2d0));
 	CUH(cudaEventCreate(&h->ev_h2d1));
 	CUH(cudaMalloc(&h->d_cfg, sizeof(DevConfig)));
@@ -243,7 +283,6 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		for (auto &s : init) init_state(h->dcfg, s);
 		CUH(cudaMemcpy(h->d_state, init.data(), sizeof(StreamState) * cfg->n_streams, cudaMemcpyHostToDevice));
 	}
-	CUH(cudaMalloc(&h->d_jobs, sizeof(StreamJob) * cfg->n_streams));
 	CUH(cudaMalloc(&h->d_progress, sizeof(uint32_t) * cfg->n_streams));
 	CUH(cudaMemset(h->d_progress, 0, sizeof(uint32_t) * cfg->n_streams));
 	CUH(cudaMallocHost(&h->h_progress, sizeof(uint32_t) * cfg->n_streams));
@@ -265,30 +304,39 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	return TFR_OK;
 }
 
-static int ensure_blocks(tfr_handle *h, size_t blocks, size_t wins)
+static int sync_all(tfr_handle *h)
 {
-	if (blocks > h->cap_blocks) {
-		CU(cudaStreamSynchronize(h->stream));
-		cudaFree(h->d_tiles); cudaFree(h->d_dec); cudaFree(h->d_trace); cudaFree(h->d_events); cudaFree(h->d_devfm);
-		h->d_tiles = nullptr; h->d_dec = nullptr; h->d_trace = nullptr; h->d_events = nullptr; h->d_devfm = nullptr;
-		h->cap_blocks = 0;
-		cudaError_t e = cudaMalloc(&h->d_tiles, blocks * sizeof(TileDesc));
-		if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
-		if (e == cudaSuccess) e = cudaMalloc(&h->d_trace, blocks * sizeof(BlockTrace));
-		if (e == cudaSuccess) e = cudaMalloc(&h->d_events, blocks * (size_t)kMaxEvt * sizeof(uint32_t));
-		if (e == cudaSuccess && h->has_fm) e = cudaMalloc(&h->d_devfm, blocks * (size_t)kBlockDec * sizeof(int32_t));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaStreamSynchronize(h->stream_be));
+	return TFR_OK;
+}
+
+static int ensure_blocks(tfr_handle *h, tfr_handle::Slot &sl, size_t blocks, size_t wins)
+{
+	if (blocks > sl.cap_blocks) {
+		int rc = sync_all(h);
+		if (rc) return rc;
+		cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_devfm);
+		sl.d_tiles = nullptr; sl.d_dec = nullptr; sl.d_trace = nullptr; sl.d_events = nullptr; sl.d_devfm = nullptr;
+		sl.cap_blocks = 0;
+		cudaError_t e = cudaMalloc(&sl.d_tiles, blocks * sizeof(TileDesc));
+		if (e == cudaSuccess) e = cudaMalloc(&sl.d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
+		if (e == cudaSuccess) e = cudaMalloc(&sl.d_trace, blocks * sizeof(BlockTrace));
+		if (e == cudaSuccess) e = cudaMalloc(&sl.d_events, blocks * (size_t)kMaxEvt * sizeof(uint32_t));
+		if (e == cudaSuccess && h->has_fm) e = cudaMalloc(&sl.d_devfm, blocks * (size_t)kBlockDec * sizeof(int32_t));
 		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("work buffers: ") + cudaGetErrorString(e)); }
-		h->cap_blocks = blocks;
+		sl.cap_blocks = blocks;
 	}
-	if (wins > h->cap_wins) {
-		CU(cudaStreamSynchronize(h->stream));
-		cudaFree(h->d_wins); cudaFree(h->d_recs);
-		h->d_wins = nullptr; h->d_recs = nullptr;
-		h->cap_wins = 0;
-		cudaError_t e = cudaMalloc(&h->d_wins, wins * sizeof(WinEntry));
-		if (e == cudaSuccess) e = cudaMalloc(&h->d_recs, wins * sizeof(WinRec));
+	if (wins > sl.cap_wins) {
+		int rc = sync_all(h);
+		if (rc) return rc;
+		cudaFree(sl.d_wins); cudaFree(sl.d_recs);
+		sl.d_wins = nullptr; sl.d_recs = nullptr;
+		sl.cap_wins = 0;
+		cudaError_t e = cudaMalloc(&sl.d_wins, wins * sizeof(WinEntry));
+		if (e == cudaSuccess) e = cudaMalloc(&sl.d_recs, wins * sizeof(WinRec));
 		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("window lists: ") + cudaGetErrorString(e)); }
-		h->cap_wins = wins;
+		sl.cap_wins = wins;
 	}
 	return TFR_OK;
 }
@@ -368,14 +416,14 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	CU(cudaSetDevice(h->device));
 	cudaGetLastError();   // do not inherit a stale error from another user of the runtime
 	const int ns = h->cfg.n_streams;
-	h->jobs.assign(ns, StreamJob{ nullptr, 0, 0, 0, 0 });
+	std::vector<StreamJob> jobs(ns, StreamJob{ nullptr, 0, 0, 0, 0 });
 	size_t total = 0, total_wins = 0;
 	const int ndm = std::max(h->dcfg.n_demods, 1);
 	uint32_t max_blocks = 0;
 	for (int s = 0; s < ns; s++) {
 		PendingSubmit &ps = h->pend[s];
 		if (!ps.pending) continue;
-		StreamJob &j = h->jobs[s];
+		StreamJob &j = jobs[s];
 		j.iq = ps.dev_ptr;
 		j.n_blocks = (uint32_t)(ps.nbytes / TFR_BLOCK_BYTES);
 		j.dec_off = (uint32_t)total;
@@ -387,28 +435,39 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		ps.pending = false;
 	}
 	for (auto &c : h->arena) c.used = 0;   // contents stay valid until the next submit overwrites them (stream ordered)
-	h->n_fe_last = 0;
 	if (total == 0) return TFR_OK;
 	if (total > 0x7ffffffull || total_wins > 0xffffffffull) return fail(TFR_E_INVAL, "tfr_process: too many blocks in one call");
-	int rc = ensure_blocks(h, total, total_wins);
+	const int si = h->cur ^ 1;
+	tfr_handle::Slot &sl = h->slot[si];
+	int rc = ensure_blocks(h, sl, total, total_wins);
 	if (rc) return rc;
-	CU(cudaMemcpyAsync(h->d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, h->stream));
+	h->cur = si;
+	h->jobs = jobs;
+	cudaStream_t sf = h->stream, sb = h->stream_be;
+	// this slot's buffers are free once the back-end of the call before the previous one is done; without
+	// pipelining the front-end also waits for the previous call's back-end
+	CU(cudaStreamWaitEvent(sf, sl.back_done, 0));
+	if (!h->pipelined) CU(cudaStreamWaitEvent(sf, h->slot[si ^ 1].back_done, 0));
+	if (!h->span_open) {
+		CU(cudaEventRecord(h->span0, sf));
+		h->span_open = true;
+	}
+	// h->jobs stays untouched until the copy has run: the next tfr_process first waits for this slot's events
+	CU(cudaMemcpyAsync(sl.d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, sf));
 
 	// Auto threshold: the whole call is first run against a speculative lower bound of the threshold (see
 	// spec_margin in tfr_dev.h).  The threshold kernel stops a stream where the bound fails; the rest of such a
 	// stream is redone in epochs of kEpochBlocks blocks, each with a bound that provably holds for the epoch.
 	const bool auto_mode = (h->dcfg.thresh_cfg == 0);
-	rc = ensure_events(h, 3);
-	if (rc) return rc;
 
 	FrontParams fp;
-	fp.jobs = h->d_jobs;
+	fp.jobs = sl.d_jobs;
 	fp.st = h->d_state;
-	fp.tiles = h->d_tiles;
-	fp.dec = h->d_dec;
+	fp.tiles = sl.d_tiles;
+	fp.dec = sl.d_dec;
 	fp.t_max = h->dcfg.t_max;
 	fp.keep_all = (h->cfg.flags & TFR_FLAG_KEEP_DECIM) ? 1 : 0;
-	fp.events = h->d_events;
+	fp.events = sl.d_events;
 	fp.tile0 = 0;
 	fp.n_tiles = (int)max_blocks;
 	fp.margin = 0;
@@ -416,11 +475,11 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	BackParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.cfg = h->d_cfg;
-	bp.jobs = h->d_jobs;
+	bp.jobs = sl.d_jobs;
 	bp.st = h->d_state;
-	bp.tiles = h->d_tiles;
-	bp.dec = h->d_dec;
-	bp.trace = h->d_trace;
+	bp.tiles = sl.d_tiles;
+	bp.dec = sl.d_dec;
+	bp.trace = sl.d_trace;
 	bp.frames = h->d_frames;
 	bp.records = h->d_records;
 	bp.counters = h->d_counters;
@@ -432,70 +491,82 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.max_frames = h->max_frames;
 	bp.max_records = h->max_records;
 	bp.n_streams = ns;
-	bp.events = h->d_events;
-	bp.wins = h->d_wins;
-	bp.recs = h->d_recs;
-	bp.devfm = h->d_devfm;
+	bp.events = sl.d_events;
+	bp.wins = sl.d_wins;
+	bp.recs = sl.d_recs;
+	bp.devfm = sl.d_devfm;
+	bp.wincnt = sl.d_wincnt;
 	bp.max_blocks = (int)max_blocks;
 	bp.tile0 = 0;
 	bp.n_tiles = (int)max_blocks;
 	bp.margin = 0;
 	bp.progress = h->d_progress;
-	if (h->d_tap_cnt) CU(cudaMemsetAsync(h->d_tap_cnt, 0, (size_t)ns * kMaxDemods * 3 * sizeof(uint32_t), h->stream));   // taps cover one tfr_process
+	if (h->d_tap_cnt) CU(cudaMemsetAsync(h->d_tap_cnt, 0, (size_t)ns * kMaxDemods * 3 * sizeof(uint32_t), sf));   // taps cover one tfr_process
 
-	int n_fe = 0;
-	CU(cudaEventRecord(h->ev[0], h->stream));
-	CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
-	CU(cudaEventRecord(h->ev[1], h->stream));
-	n_fe = 1;
-	CU(launch_thresh2(bp, h->stream));
+	// ---- front: decimate + trigger, threshold walk
+	{   // the pair recorded by this slot's previous call has not been read yet if no tfr_sync came in between
+		float a = 0;
+		if (cudaEventElapsedTime(&a, sl.fe0, sl.fe1) == cudaSuccess) h->fe_ms_acc += a;
+		else cudaGetLastError();
+	}
+	CU(cudaEventRecord(sl.fe0, sf));
+	CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
+	CU(cudaEventRecord(sl.fe1, sf));
+	CU(launch_thresh2(bp, sf));
 	h->stats.kernel_launches += 2;
 	if (auto_mode) {
-		CU(cudaMemcpyAsync(h->h_progress, h->d_progress, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, h->stream));
-		CU(cudaStreamSynchronize(h->stream));
+		CU(cudaMemcpyAsync(h->h_progress, h->d_progress, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, sf));
+		CU(cudaStreamSynchronize(sf));
 		uint32_t remaining = 0;
 		for (int s = 0; s < ns; s++)
 			if (h->jobs[s].n_blocks) remaining = std::max(remaining, h->jobs[s].n_blocks - std::min(h->h_progress[s], h->jobs[s].n_blocks));
 		const int n_fallback = (int)((remaining + kEpochBlocks - 1) / kEpochBlocks);
-		rc = ensure_events(h, (size_t)3 + 2 * n_fallback);
-		if (rc) return rc;
-		fp.use_progress = 1;
-		fp.n_tiles = kEpochBlocks;
-		fp.margin = kEpochMargin;
-		bp.n_tiles = kEpochBlocks;
-		bp.margin = kEpochMargin;
-		for (int e = 0; e < n_fallback; e++) {
-			CU(cudaEventRecord(h->ev[2 * n_fe], h->stream));
-			CU(launch_frontend(fp, ns, h->dcfg.filter, h->stream));
-			CU(cudaEventRecord(h->ev[2 * n_fe + 1], h->stream));
-			n_fe++;
-			CU(launch_thresh2(bp, h->stream));
-			h->stats.kernel_launches += 2;
-		}
-		h->stats.fallback_epochs += (uint32_t)n_fallback;
-	}
-	{
-		// everything below runs once per call, over all blocks
-		bp.tile0 = 0;
-		bp.n_tiles = (int)max_blocks;
-		if (h->dcfg.n_demods) {
-			if (h->has_fm) { CU(launch_devfm(bp, h->stream)); h->stats.kernel_launches += 1; }
-			const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
-			if (has_win) {
-				CU(launch_win(bp, h->dcfg.n_demods, h->stream));
-				h->stats.kernel_launches += 1;
+		if (n_fallback) {
+			rc = ensure_events(h, 2);
+			if (rc) return rc;
+			fp.use_progress = 1;
+			fp.n_tiles = kEpochBlocks;
+			fp.margin = kEpochMargin;
+			bp.n_tiles = kEpochBlocks;
+			bp.margin = kEpochMargin;
+			CU(cudaEventRecord(h->ev[0], sf));
+			for (int e = 0; e < n_fallback; e++) {
+				CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
+				CU(launch_thresh2(bp, sf));
+				h->stats.kernel_launches += 2;
 			}
-			if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, h->stream)); h->stats.kernel_launches += 1; }
-			CU(launch_verify(bp, h->dcfg.n_demods, h->stream));
+			CU(cudaEventRecord(h->ev[1], sf));
+			CU(cudaStreamSynchronize(sf));   // rare path (start-up transients): timed synchronously, threshold walk included
+			float a = 0;
+			CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+			h->fe_ms_acc += a;
+			h->stats.fallback_epochs += (uint32_t)n_fallback;
+		}
+	}
+	CU(launch_save_history(sl.d_jobs, h->d_state, ns, sf));
+	h->stats.kernel_launches += 1;
+	CU(cudaEventRecord(sl.front_done, sf));
+
+	// ---- back: demodulators over the windows, verifier, parsers - once per call, over all blocks
+	CU(cudaStreamWaitEvent(sb, sl.front_done, 0));
+	bp.tile0 = 0;
+	bp.n_tiles = (int)max_blocks;
+	if (h->dcfg.n_demods) {
+		if (h->has_fm) { CU(launch_devfm(bp, sb)); h->stats.kernel_launches += 1; }
+		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
+		if (has_win) {
+			CU(launch_win(bp, h->dcfg.n_demods, sb));
 			h->stats.kernel_launches += 1;
 		}
-		CU(launch_submit_epilogue(bp, h->stream));
-		CU(launch_save_history(h->d_jobs, h->d_state, ns, h->stream));
-		CU(launch_parse(bp, h->stream));
-		h->stats.kernel_launches += 3;
+		if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, sb)); h->stats.kernel_launches += 1; }
+		CU(launch_verify(bp, h->dcfg.n_demods, sb));
+		h->stats.kernel_launches += 1;
 	}
-	CU(cudaEventRecord(h->ev[2 * n_fe], h->stream));
-	h->n_fe_last = n_fe;
+	CU(launch_submit_epilogue(bp, sb));
+	CU(launch_parse(bp, sb));
+	h->stats.kernel_launches += 2;
+	CU(cudaEventRecord(sl.back_done, sb));
+	CU(cudaEventRecord(h->span1, sb));
 	h->stats.blocks += total;
 	h->stats.raw_samples += total * (uint64_t)kBlockRaw;
 	h->results_valid = false;
@@ -506,22 +577,28 @@ extern "C" __attribute__((visibility("default"))) int tfr_sync(tfr_handle *h)
 {
 	if (!h) return fail(TFR_E_INVAL, "tfr_sync: null handle");
 	CU(cudaSetDevice(h->device));
-	CU(cudaStreamSynchronize(h->stream));
-	if (h->n_fe_last) {
-		const int n = h->n_fe_last;
-		double fe = 0;
-		for (int e = 0; e < n; e++) {
+	int rc = sync_all(h);
+	if (rc) return rc;
+	if (h->span_open) {
+		// times cover every tfr_process since the previous tfr_sync (they overlap on the device when pipelined)
+		double fe = h->fe_ms_acc;
+		for (auto &sl : h->slot) {
 			float a = 0;
-			CU(cudaEventElapsedTime(&a, h->ev[2 * e], h->ev[2 * e + 1]));
-			fe += a;
+			if (cudaEventElapsedTime(&a, sl.fe0, sl.fe1) == cudaSuccess) fe += a;
+			else cudaGetLastError();
+			// re-record so that a pair is never counted twice
+			CU(cudaEventRecord(sl.fe0, h->stream));
+			CU(cudaEventRecord(sl.fe1, h->stream));
 		}
+		CU(cudaStreamSynchronize(h->stream));
+		h->fe_ms_acc = 0;
 		float all = 0, tot = 0;
-		CU(cudaEventElapsedTime(&all, h->ev[0], h->ev[2 * n]));
-		CU(cudaEventElapsedTime(&tot, h->h2d_timed ? h->ev_h2d0 : h->ev[0], h->ev[2 * n]));
+		CU(cudaEventElapsedTime(&all, h->span0, h->span1));
+		CU(cudaEventElapsedTime(&tot, h->h2d_timed ? h->ev_h2d0 : h->span0, h->span1));
 		h->stats.last_frontend_ms = fe;
 		h->stats.last_backend_ms = all - fe;
 		h->stats.last_total_ms = tot;
-		h->n_fe_last = 0;
+		h->span_open = false;
 	}
 	if (h->h2d_timed) {
 		float a = 0;
@@ -647,7 +724,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_clear_results(tfr_hand
 {
 	if (!h) return fail(TFR_E_INVAL, "tfr_clear_results: null handle");
 	CU(cudaSetDevice(h->device));
-	CU(cudaStreamSynchronize(h->stream));
+	{ int rc_ = sync_all(h); if (rc_) return rc_; }
 	// keep active_samples running; zero the frame/record cursors
 	Counters c;
 	CU(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -682,7 +759,7 @@ extern "C" __attribute__((visibility("default"))) long tfr_read_block_trace(tfr_
 	if (!out) return (long)j.n_blocks;
 	const size_t n = std::min<size_t>(cap, j.n_blocks);
 	static_assert(sizeof(tfr_block_trace) == sizeof(BlockTrace), "trace layout");
-	if (n) CU(cudaMemcpy(out, h->d_trace + j.dec_off, n * sizeof(BlockTrace), cudaMemcpyDeviceToHost));
+	if (n) CU(cudaMemcpy(out, h->slot[h->cur].d_trace + j.dec_off, n * sizeof(BlockTrace), cudaMemcpyDeviceToHost));
 	return (long)n;
 }
 
@@ -717,7 +794,7 @@ extern "C" __attribute__((visibility("default"))) long tfr_read_decimated(tfr_ha
 	const size_t avail = (size_t)j.n_blocks * kBlockDec * 2;
 	if (!out) return (long)avail;
 	const size_t n = std::min(cap_int16, avail) & ~(size_t)1;
-	if (n) CU(cudaMemcpy(out, h->d_dec + (size_t)j.dec_off * kBlockDec, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+	if (n) CU(cudaMemcpy(out, h->slot[h->cur].d_dec + (size_t)j.dec_off * kBlockDec, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
 	return (long)n;
 }
 
@@ -748,7 +825,7 @@ extern "C" __attribute__((visibility("default"))) long tfr_decimate(int device, 
 		if ((e = cudaMemcpy(d_in, iq, nbytes, mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)) != cudaSuccess) { ret = cuda_fail("copy in", e); break; }
 		if ((rc = tfr_submit(h, 0, d_in, padded, TFR_MEM_DEVICE)) || (rc = tfr_process(h)) || (rc = tfr_sync(h))) { ret = rc; break; }
 		const size_t n_out = (nbytes / 8) * 2;   // nbytes/2 raw samples -> /4 decimated -> 2 int16 each
-		if ((e = cudaMemcpy(out, h->d_dec, n_out * sizeof(int16_t), mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost)) != cudaSuccess) { ret = cuda_fail("copy out", e); break; }
+		if ((e = cudaMemcpy(out, h->slot[h->cur].d_dec, n_out * sizeof(int16_t), mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost)) != cudaSuccess) { ret = cuda_fail("copy out", e); break; }
 		ret = (long)n_out;
 	} while (0);
 	cudaFree(d_in);

@@ -124,6 +124,13 @@ struct StreamJob {
 	uint32_t win_cap;             // window-list capacity per demod = n_blocks*kWinPerBlock + 4
 };
 
+// windows listed for one stream by the threshold kernel of ONE call (per work-buffer slot: the back-end of call
+// i reads it while the threshold kernel of call i+1 is already rewriting StreamState::win_n)
+struct WinCount {
+	uint32_t n[kMaxDemods];
+	uint32_t cum[kMaxDemods];
+};
+
 // one demodulator window = one retriggerable timeout interval, derived from the trigger positions alone
 // (a trigger at t keeps demod d active for samples t .. t+T_d-1; tfa1.cpp:147-148, tfa2.cpp:351-356)
 struct WinEntry {
@@ -236,6 +243,7 @@ struct BackParams {
 	int n_streams;
 	int margin;              // same meaning and value as FrontParams::margin of the front-end launch before it
 	uint32_t *progress;      // [stream] blocks walked so far by the threshold kernel (host reads it back)
+	WinCount *wincnt;        // [stream] window counts of this call (written by the threshold kernel when a stream finishes)
 	const uint32_t *events;  // [gtile][kMaxEvt] (pos<<16 | pwr) of samples with pwr > thresh_lo, in order
 	WinEntry *wins;
 	WinRec *recs;

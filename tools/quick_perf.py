@@ -29,6 +29,20 @@ def main():
             it, dt * 1e3, st["last_frontend_ms"], samples / st["last_frontend_ms"] / 1e6, 2 * samples / st["last_frontend_ms"] / 1e6,
             st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)), "windows", rx.stats()["windows"], "reruns", rx.stats()["reruns"], "sr/bq/edge", rx.stats()["reruns_sr"], rx.stats()["reruns_biquad"], rx.stats()["reruns_edge"])
         rx.records(); rx.clear()
+    # pipelined: K calls in flight, one sync (front-end of call i+1 overlaps the back-end of call i)
+    K = 8
+    for rep in range(2):
+        t0 = time.time()
+        for it in range(K):
+            for s in range(n_streams):
+                rx.submit(s, bufs[s].data_ptr(), nbytes=nbytes)
+            rx.process()
+        rx.sync(); dt = time.time() - t0
+        st = rx.stats()
+        samples = K * n_streams * nbytes / 2
+        print("pipelined x%d: wall %.3f ms/call, device span %.3f ms/call (%.1f GS/s), front-end %.3f ms/call" % (
+            K, dt * 1e3 / K, st["last_total_ms"] / K, samples / st["last_total_ms"] / 1e6, st["last_frontend_ms"] / K), "records", rx.n_records())
+        rx.clear()
 
 if __name__ == "__main__":
     main()
