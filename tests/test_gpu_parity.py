@@ -178,3 +178,93 @@ def test_submit_rejects_partial_blocks(tb):
     rx.process()
     assert rx.frames() == []
     rx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# auto-threshold speculation, the two-slot pipeline and window chains (round-1 session 2 additions)
+# ---------------------------------------------------------------------------------------------------
+def test_auto_threshold_speculation_fallback_and_steady_state(tb):
+    """Noise below the start threshold: the threshold falls from 500 by 2 every 4th block, so the whole-call speculative bound
+    (thresh - spec_margin) fails inside the first call and the rest of it is redone in 64-block epochs; the
+    second call starts near equilibrium and the speculation holds.  Both must match the oracle block by block."""
+    n_raw = 24 * 1024 * 1024 // 2
+    iq = g.make_stream(n_raw, [], seed=21, sigma=4.0)
+    half = (iq.size // 2) // 65536 * 65536
+    rx = tb.Receiver(types=0x07, thresh=0)
+    o = ol.Oracle(types=0x07, thresh=0)
+    rx.submit(0, iq[:half].copy())
+    rx.process()
+    rx.sync()
+    fb1 = rx.stats()["fallback_epochs"]
+    assert fb1 > 0, "the start-up transient must exercise the epoch fallback"
+    o.process(iq[:half])
+    assert np.array_equal(rx.block_trace(0), o.blocks())
+    assert rx.thresh(0) == o.thresh()
+    rx.submit(0, iq[half:].copy())
+    rx.process()
+    rx.sync()
+    assert rx.stats()["fallback_epochs"] == fb1, "at equilibrium the whole-call speculation must hold"
+    o2 = ol.Oracle(types=0x07, thresh=0)
+    o2.process(iq)
+    assert np.array_equal(rx.block_trace(0), o2.blocks()[half // 65536:])
+    assert rx.thresh(0) == o2.thresh()
+    assert [frame_key(f) for f in rx.frames()] == [frame_key(f) for f in o2.frames()]
+    rx.close()
+
+
+def test_pipelined_ragged_multi_stream_calls(tb, hot_fixture):
+    """Several tfr_process calls in flight without a sync in between (front-end of call i+1 overlaps the
+    back-end of call i), streams of different lengths, one stream skipping calls: every stream must still see
+    exactly what one uninterrupted reference run over its bytes produces."""
+    names = ["mixed5", "cont_noisy", "strong_t7"]
+    iqs = [hot_fixture(n) for n in names]
+    step = [5 * 65536, 9 * 65536, 13 * 65536]
+    rx = tb.Receiver(types=0x2F, thresh=0, n_streams=3)
+    offs = [0, 0, 0]
+    call = 0
+    while any(offs[s] < iqs[s].size for s in range(3)):
+        for s in range(3):
+            if s == 2 and call % 3 == 1:
+                continue                      # this stick delivers nothing this time
+            if offs[s] < iqs[s].size:
+                n = min(step[s], iqs[s].size - offs[s])
+                rx.submit(s, iqs[s][offs[s]:offs[s] + n].copy())
+                offs[s] += n
+        rx.process()
+        call += 1
+    frames, records = rx.frames(), rx.records()
+    for s, iq in enumerate(iqs):
+        o = ol.Oracle(types=0x2F)
+        o.process(iq)
+        assert [frame_key(f) for f in frames if f["stream"] == s] == [frame_key(f) for f in o.frames()], names[s]
+        assert [r["exec"] for r in records if r["stream"] == s] == [r["exec"] for r in o.records()], names[s]
+        assert rx.thresh(s) == o.thresh()
+    rx.close()
+
+
+@pytest.mark.parametrize("thresh,types", [(260, 0x0E), (320, 0x07), (0, 0x0E)])
+def test_dense_near_windows_chains(tb, thresh, types):
+    """A threshold inside the noise: windows follow each other within a timeout (`near` windows are run as
+    chains by one thread, with carried biquad state and last_bit_idx) and many speculated biquad start states
+    need the verifier.  Discriminator values, all biquad outputs and the frames are compared with the oracle."""
+    iq = g.make_stream(3 * 1024 * 1024, [], seed=33 + thresh, sigma=4.0)
+    rx = tb.Receiver(types=types, thresh=thresh, flags=tb.FLAG_TAPS)
+    rx.submit(0, iq)
+    rx.process()
+    compare_with_oracle(rx, iq, types, 0, thresh)
+    st = rx.stats()
+    assert st["windows"] > 20, st
+    rx.close()
+
+
+def test_weak_signal_many_retriggers(tb):
+    """Telegrams just above the noise: bursts where triggers come and go, so window chains get long and the
+    block event lists overflow into the dense path of the threshold kernel."""
+    sensors = [g.TFA_1, g.TFA_2, g.TFA_3]
+    iq = g.fixture_continuous(6 * 1024 * 1024, sensors, 500000, seed=17, sigma=5.0, amp=14)[0]
+    for thresh in (0, 280):
+        rx = tb.Receiver(types=0x07, thresh=thresh, flags=tb.FLAG_TAPS)
+        rx.submit(0, iq)
+        rx.process()
+        compare_with_oracle(rx, iq, 0x07, 0, thresh)
+        rx.close()
