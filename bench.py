@@ -314,19 +314,22 @@ def main():
     barrier()
     m0 = sampler.mark()
     l0 = rx.stats()["kernel_launches"]
-    # all K steps are issued back to back and synchronised once: the library keeps two work-buffer slots, so the
-    # front-end of step i+1 overlaps the (latency-bound) back-end of step i.  Device time = first front-end start
-    # to last back-end end (library CUDA events on its own streams).
+    # one step = submit every stream's buffer + tfr_process + tfr_sync.  Device time per step = first front-end
+    # launch to the end of the parsers (library CUDA events on its own streams); front-end time = the CUDA-event
+    # span of the step's front-end launches.  (The library can also keep two calls in flight - the front-end of
+    # call i+1 overlapping the back-end of call i - but then the front-end's own duration is no longer separable,
+    # so the timed region synchronises per step.)
+    dev_ms = fe_ms = be_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
-    rx.sync()
+        rx.sync()
+        st = rx.stats()
+        dev_ms += st["last_total_ms"]
+        fe_ms += st["last_frontend_ms"]
+        be_ms += st["last_backend_ms"]
     decoded = rx.n_records()
-    st = rx.stats()
-    dev_ms = st["last_total_ms"]
-    fe_ms = st["last_frontend_ms"]
-    be_ms = st["last_backend_ms"]
-    windows = st["windows"]
+    windows = rx.stats()["windows"]
     rx.clear()
     barrier()
     wall = time.perf_counter() - t0

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs;
 	int c = st->any_timeout;              // samples at the head of the next block still covered by a trigger
 	const int mode = st->thresh_mode;
-	// the bound the front-end launch before this one kept samples and events for (it read the same st->thresh)
-	const int thresh_lo = (mode == 1) ? thresh - (p.margin ? p.margin : spec_margin(thresh)) : thresh;
+	// the bound the front-end launches of these blocks kept samples and events for
+	const int thresh_lo = (mode == 1) ? (p.margin ? thresh - p.margin : st->spec_lo) : thresh;
 	long long last_trig;                  // position of the latest trigger (negative: in an earlier call)
 	// per-demod window bookkeeping lives in lane d
 	const int T_d = (lane < nd) ? cfg.d[lane].timeout : 0x7fffffff;

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	tma_bulk_g2s(smem_u32(smem + kRow0 + tid * kRowStride), src + tid * kRowBytes, kRowBytes, bar);
 
 	int thresh_lo = st->thresh;
-	if (st->thresh_mode) thresh_lo -= p.margin ? p.margin : spec_margin(thresh_lo);
+	if (st->thresh_mode) thresh_lo = p.margin ? thresh_lo - p.margin : st->spec_lo;
 
 	mbar_wait(bar, 0);
 
@@ -440,6 +440,7 @@ __global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int 
 	if (threadIdx.x == 0) {
 		s->hist_parity = par;
 		s->t2_done = 0;   // the threshold walk of this call is complete; the next call starts at block 0
+		s->spec_lo = s->thresh - spec_margin(s->thresh);   // the next call's speculative bound
 	}
 }
 

@@ -31,6 +31,7 @@ using namespace tfr;
 static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 112,
 	      "public struct layout changed: bump TFR_ABI_VERSION");
 
+static constexpr int kFrontChunks = 8;   // front-end launches per call (each overlaps the previous chunk's threshold walk)
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg)
 {
@@ -99,6 +100,9 @@ struct tfr_handle {
 	Slot slot[2];
 	int cur = 0;                       // slot of the most recent tfr_process
 	cudaStream_t stream_be = nullptr;  // back-end stream
+	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
+	cudaEvent_t chunk_ev[8] = { nullptr };
+	cudaEvent_t walk_ev = nullptr;
 	bool pipelined = true;             // false: the back-end of a call finishes before the next call starts (taps)
 	cudaEvent_t span0 = nullptr, span1 = nullptr;   // first front-end start / last back-end end since the last tfr_sync
 	bool span_open = false;
@@ -172,6 +176,7 @@ static void init_state(const DevConfig &d, StreamState &s)
 		s.thresh = 500;
 		s.thresh_mode = 1;
 	}
+	s.spec_lo = s.thresh - spec_margin(s.thresh);
 	for (int k = 0; k < d.n_demods; k++) {
 		DemodState &q = s.d[k];
 		q.sr_cnt = -1;
@@ -208,6 +213,9 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->span0) cudaEventDestroy(h->span0);
 	if (h->span1) cudaEventDestroy(h->span1);
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
+	if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
+	for (auto e : h->chunk_ev) if (e) cudaEventDestroy(e);
+	if (h->walk_ev) cudaEventDestroy(h->walk_ev);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 }
@@ -258,6 +266,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	// same priority as the front stream: measured on B200, a high-priority back-end stream shortens a pipelined
 	// call from 4.35 to 4.0 ms but stretches the issue-bound front-end kernel from 1.9 to 3.15 ms
 	CUH(cudaStreamCreateWithFlags(&h->stream_be, cudaStreamNonBlocking));
+	CUH(cudaStreamCreateWithFlags(&h->stream_walk, cudaStreamNonBlocking));
+	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	CUH(cudaEventCreateWithFlags(&h->walk_ev, cudaEventDisableTiming));
 	h->pipelined = !(cfg->flags & TFR_FLAG_TAPS);   // the tap buffers are not slotted
 	CUH(cudaEventCreate(&h->span0));
 	CUH(cudaEventCreate(&h->span1));
@@ -304,6 +315,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 static int sync_all(tfr_handle *h)
 {
 	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaStreamSynchronize(h->stream_walk));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
 }
@@ -506,11 +518,30 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		if (cudaEventElapsedTime(&a, sl.fe0, sl.fe1) == cudaSuccess) h->fe_ms_acc += a;
 		else cudaGetLastError();
 	}
+	// The call's blocks go through the front-end in kFrontChunks launches; the threshold walk of chunk k (one warp
+	// per stream, a serial chain) runs on the walk stream while the front-end of chunk k+1 streams on.
 	CU(cudaEventRecord(sl.fe0, sf));
-	CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
-	CU(cudaEventRecord(sl.fe1, sf));
-	CU(launch_thresh2(bp, sf));
-	h->stats.kernel_launches += 2;
+	{
+		const int n_chunks = (max_blocks >= 64u * kFrontChunks) ? kFrontChunks : 1;
+		const int per = (int)((max_blocks + n_chunks - 1) / n_chunks);
+		CU(cudaStreamWaitEvent(h->stream_walk, sl.fe0, 0));   // the walk stream starts after everything queued so far
+		for (int k = 0; k < n_chunks; k++) {
+			fp.tile0 = k * per;
+			fp.n_tiles = std::min(per, (int)max_blocks - fp.tile0);
+			if (fp.n_tiles <= 0) break;
+			CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
+			CU(cudaEventRecord(h->chunk_ev[k], sf));
+			CU(cudaStreamWaitEvent(h->stream_walk, h->chunk_ev[k], 0));
+			bp.n_tiles = fp.n_tiles;
+			CU(launch_thresh2(bp, h->stream_walk));
+			h->stats.kernel_launches += 2;
+		}
+		CU(cudaEventRecord(sl.fe1, sf));
+		CU(cudaEventRecord(h->walk_ev, h->stream_walk));
+		CU(cudaStreamWaitEvent(sf, h->walk_ev, 0));   // rejoin: everything after this on the front stream sees the walk
+		fp.tile0 = 0;
+		bp.n_tiles = (int)max_blocks;
+	}
 	if (auto_mode) {
 		CU(cudaMemcpyAsync(h->h_progress, h->d_progress, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, sf));
 		CU(cudaStreamSynchronize(sf));

@@ -96,7 +96,8 @@ struct alignas(128) StreamState {
 	int32_t call_last_trig;       // position of the last trigger seen so far in this call (negative: before the call)
 	uint32_t call_cursor;         // coverage cursor
 	uint32_t t2_done;             // blocks of this call the threshold kernel has walked (0 between calls)
-	uint32_t t2_pad;
+	int32_t spec_lo;              // auto threshold: the lower bound every speculative front-end launch of the current call keeps
+	                              // (thresh at the start of the call - spec_margin); frozen by save_history_kernel
 	uint32_t win_n[kMaxDemods];   // windows listed so far per demod
 	uint32_t win_cum[kMaxDemods]; // active samples in closed windows
 	uint32_t win_open[kMaxDemods];// 1 if the last listed window is still open
@@ -218,8 +219,8 @@ struct FrontParams {
 	int n_tiles;           // blocks in this epoch (grid.x)
 	int t_max;
 	int keep_all;          // TFR_FLAG_KEEP_DECIM: write every sample
-	int margin;            // auto threshold: the launch keeps every sample with pwr > thresh - margin (thresh as of
-	                       // the launch); 0 = the speculative whole-call margin spec_margin(thresh)
+	int margin;            // auto threshold: > 0 the launch keeps every sample with pwr > thresh - margin (thresh as of
+	                       // the launch, epoch fallback); 0 = the call's frozen speculative bound StreamState::spec_lo
 	int use_progress;      // 1: a stream's first block of this launch is its StreamState::t2_done (epoch fallback)
 	uint32_t *events;      // [gtile][kMaxEvt]
 };
