@@ -1,10 +1,8 @@
 // backend.cu - everything downstream of the decimator, on the device:
 //
-//   walk_kernel    the per-sample demodulator state machines and bit framers
-//                    TFA_1            tfa1_demod::demod      tfa1.cpp:143-190, store_bit :120-134
-//                    TFA_2/TFA_3/TX22 tfa2_demod::demod      tfa2.cpp:346-442, store_bit :281-314
-//                    WeatherHub       whb_demod::demod       whb.cpp:632-707,  store_bit :566-603
-//                  run over the trigger windows the front-end kept, in stream order with carried state
+//   whb_kernel     WeatherHub demodulator + framer (whb_demod::demod whb.cpp:632-707, store_bit :566-603), one
+//                  serial chain per stream over the demod's windows (TFA_1 and the TFA_2 family run
+//                  window-parallel in backend2.cu)
 //   parse_kernel   decoder::flush (tfa1.cpp:47-118, tfa2.cpp:64-279, whb.cpp:477-564) + CRC-8 / CRC-32
 //                  (crc8.cpp, crc32.cpp), one warp per candidate frame
 //
@@ -22,68 +20,235 @@
 namespace tfr {
 
 // ------------------------------------------------------------------------------------------------
-// walk_kernel: one thread per (stream, demod), windows in stream order with carried state
+// whb_kernel: WeatherHub (whb.cpp:632-707), one warp per stream.
+//
+// WeatherHub cannot be cut into independent windows: its averaging biquad (0.0025/spb, whb.cpp:611) has a
+// time constant of ~5800 samples and is never reset, so avg_of at any sample depends on hundreds of earlier
+// windows.  The demodulator therefore stays ONE serial chain per stream - but a tight one:
+//   * the warp walks the demod's window list (threshold kernel), 32 samples per step: every lane loads one
+//     stored sample and its predecessor (coalesced) and computes the discriminator Re(a*conj b) and I^2+Q^2;
+//     the loads of the next 32 samples are issued before the current ones are consumed
+//   * the serial part - pulse biquad, averaging biquad, dip detector - is executed redundantly by all lanes
+//     (uniform control flow, state in registers), fed by shuffles.  The two biquad recurrences are independent
+//     dependency chains (the averaging filter only consumes the pulse filter's truncated output), so they
+//     overlap and a sample costs about one biquad latency
+//   * bits (one per >= 48 samples), the descrambler/framer and the frame buffer are the rare path (lane 0's
+//     local memory is the reference's rdata[])
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) walk_kernel(const BackParams p)
+template <bool TAPS>
+__global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 {
-	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-	const int nd = p.cfg->n_demods;
-	if (gid >= p.n_streams * nd) return;
+	const int stream = blockIdx.x;
+	const int lane = threadIdx.x;
+	if (stream >= p.n_streams) return;
+	int demod = -1;
+	for (int k = 0; k < p.cfg->n_demods; k++)
+		if (p.cfg->d[k].kind == K_WHB) demod = k;
+	if (demod < 0) return;
+	const DemodCfg cfg = p.cfg->d[demod];
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
 	Walk w;
 	w.p = &p;
-	w.stream = gid / nd;
-	w.demod = gid % nd;
-	const DemodCfg cfg = p.cfg->d[w.demod];
-	if (cfg.kind != K_WHB) return;   // TFA_1 / TFA_2 family run window-parallel in backend2.cu
-	const StreamJob job = p.jobs[w.stream];
-	if (job.n_blocks == 0) return;
-	StreamState *st = p.st + w.stream;
-	w.s = st->d[w.demod];
-	for (int k = 0; k < 3; k++) w.tap_n[k] = p.tap_cap ? p.tap_cnt[((size_t)w.stream * kMaxDemods + w.demod) * 3 + k] : 0;
+	w.stream = stream;
+	w.demod = demod;
+	w.s = st->d[demod];
+	for (int k = 0; k < 3; k++) w.tap_n[k] = p.tap_cap ? p.tap_cnt[((size_t)stream * kMaxDemods + demod) * 3 + k] : 0;
+	constexpr bool taps = TAPS;   // compiled out of the production kernel: a branch in the loop body would keep the
+	                              // scheduler from interleaving the two filter chains
+	const uint32_t n_win = p.wincnt[stream].n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	const uint32_t *dec = p.dec + (size_t)job.dec_off * kBlockDec;
+	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
+	const uint32_t prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
+	const int64_t base_pos = st->blocks_done * (int64_t)kBlockDec;
 
-	const int t_end = min(p.tile0 + p.n_tiles, (int)job.n_blocks);
-	const int64_t base_block = st->blocks_done;
-	int carry_in = entry_carry(p, job, st);
-	uint32_t prev_last;   // the sample just before this epoch's first block (every demod's last_i/last_q)
-	if (p.tile0 == 0)
-		prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
-	else
-		prev_last = p.dec[((size_t)job.dec_off + p.tile0 - 1) * kBlockDec + kBlockDec - 1];
+	// hot state in registers (identical in every lane)
+	Biquad lp = w.s.lp, la = w.s.lp_avg;
+	const BiquadCoef kp = cfg.lp, ka = cfg.lp_avg;
+	int last_dev = w.s.last_dev, avg_of = w.s.avg_of, synced = w.s.synced;
+	uint32_t step = w.s.step_lo, last_peak = w.s.last_peak;
+	double rssi = w.s.rssi_d;
+	const double spb12 = __dmul_rn(cfg.spb, 0.5);
+	const int spb34 = (int)floor(__dmul_rn(cfg.spb, 0.75));   // (double)tdiff > 0.75*spb  <=>  tdiff > floor(0.75*spb)
 
-	Regions reg;
-	for (int tile = p.tile0; tile < t_end; tile++) {
-		const size_t gtile = (size_t)job.dec_off + tile;
-		const TileDesc &td = p.tiles[gtile];
-		const uint32_t *d = p.dec + gtile * kBlockDec;
-		const int thresh = p.trace[gtile].thresh;
-		// demodulator::start, decoder.cpp:118-122
-		if (w.s.last_bit_idx) w.s.last_bit_idx -= kIdxPerBlock;
-		build_regions(td, carry_in, reg);
-		int pos = 0;
-		for (int r = 0; r < reg.n; r++) {
-			const int a = reg.start[r], b = reg.end[r];
-			if (cfg.kind == K_WHB) w.s.step_lo += (uint32_t)(a - pos);   // step++ runs on every sample (whb.cpp:705)
-			uint32_t lw = (a == 0) ? prev_last : d[a - 1];
-			for (int m = a; m < b; m++) {
-				const uint32_t cw = d[m];
-				const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
-				const int li = (int)(int16_t)(lw & 0xffff), lq = (int)(int16_t)(lw >> 16);
-				const int pwr = abs(i) + abs(q);
-				w.pos = (base_block + tile) * (int64_t)kBlockDec + m;
-				if (cfg.kind == K_TFA1) tfa1_sample(w, thresh, pwr, 2 * m, i, q, li, lq);
-				else if (cfg.kind == K_WHB) whb_sample(w, cfg, thresh, pwr, i, q, li, lq);
-				else tfa2_sample(w, cfg, thresh, pwr, 2 * m, i, q, li, lq);
-				lw = cw;
-			}
-			pos = b;
+	auto load = [&](uint32_t m, uint32_t last, uint32_t &cw, uint32_t &lw) {
+		cw = lw = 0;
+		if (m <= last) {
+			cw = dec[m];
+			lw = (m == 0) ? prev_last : dec[m - 1];
 		}
-		if (cfg.kind == K_WHB) w.s.step_lo += (uint32_t)(kBlockDec - pos);
-		carry_in = td.carry_out;
-		prev_last = d[kBlockDec - 1];
+	};
+
+	// per 32-sample step: what the lanes prepare in parallel for the serial part
+	__shared__ double s_t2[32], s_u[32], s_d[32];
+	__shared__ int s_pw[32];
+	const size_t tbase = ((size_t)stream * kMaxDemods + demod) * (size_t)p.tap_cap;
+
+	for (uint32_t wi = 0; wi < n_win; wi++) {
+		const WinEntry e = wl[wi];
+		if (e.start >= call_len) break;
+		const uint32_t last = min(e.end, call_len - 1);
+		if (!(e.flags & kWinCont)) {   // whb.cpp:636-642: a trigger with the timeout expired starts a new window
+			w.s.offset = 0;
+			w.s.bitcnt = 0;
+			rssi = 0.0;
+			step = 0;
+			last_peak = 0;
+		}
+		uint32_t cw, lw, cw_nx, lw_nx;
+		load(e.start + lane, last, cw, lw);
+		for (uint32_t m0 = e.start; m0 <= last; m0 += 32) {
+			load(m0 + 32 + lane, last, cw_nx, lw_nx);
+			const int cnt = (int)min(32u, last - m0 + 1);
+			{
+				// the pulse filter's input-only terms, with the reference's roundings (iir2::step as built:
+				// ((b2*dn2 + a1*yn1) + (b0*dn + b1*dn1)) + a2*yn2): u = b2*dn2 and t2 = b0*dn + b1*dn1
+				const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
+				const int cr = fm_dev_nrzs(i, q, (int)(int16_t)(lw & 0xffff), (int)(int16_t)(lw >> 16));
+				const double d = (double)cr;
+				double d1 = __shfl_up_sync(0xffffffffu, d, 1), d2 = __shfl_up_sync(0xffffffffu, d, 2);
+				if (lane == 0) { d1 = lp.d1; d2 = lp.d2; }
+				if (lane == 1) d2 = lp.d1;
+				s_t2[lane] = __dadd_rn(__dmul_rn(kp.b0, d), __dmul_rn(kp.b1, d1));
+				s_u[lane] = __dmul_rn(kp.b2, d2);
+				s_d[lane] = d;
+				s_pw[lane] = i * i + q * q;
+				if (taps) {
+					const uint32_t ti = w.tap_n[1] + (uint32_t)lane;
+					if (lane < cnt && ti < p.tap_cap) p.tap_i32[1][tbase + ti] = cr;
+				}
+			}
+			if (taps) w.tap_n[1] += (uint32_t)cnt;
+			__syncwarp();
+			// Software pipeline: at the top of iteration k, (y_cur, dev_cur) is the pulse filter's output for sample k
+			// and lp has already advanced through it.  Each iteration starts sample k+1's pulse filter (chain A) next
+			// to sample k's averaging filter (chain B) in ONE basic block, so that the two dependency chains overlap.
+			auto pulse = [&](int kk, double &y) {
+				y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[kk], __dmul_rn(kp.a1, lp.y0)), s_t2[kk]), __dmul_rn(kp.a2, lp.y1));
+			};
+			auto phase_change = [&](int tdiff) {
+				// one 0, then a 1 for every further bit period since the last one (whb.cpp:662-674)
+				whb_bit(w.s, 0);
+				w.s.bitcnt++;
+				const int bit0 = __double2int_rz(__ddiv_rn(__dadd_rn((double)tdiff, spb12), cfg.spb));
+				for (int n = 1; n < bit0; n++) {
+					whb_bit(w.s, 1);
+					w.s.bitcnt++;
+				}
+			};
+			double y_cur;
+			pulse(0, y_cur);
+			lp.y1 = lp.y0;
+			lp.y0 = y_cur;
+			int dev_cur = trunc_to_int(y_cur);
+			int k = 0;
+			if (!synced) {
+				// the common case: no frame in progress
+				for (; k < cnt; k++) {
+					const bool more = k + 1 < cnt;
+					double y_nx;
+					pulse(more ? k + 1 : k, y_nx);                                                   // chain A
+					const double a = biquad_step(la, ka, __dmul_rn(0.5, int_to_double(dev_cur)));    // chain B
+					const int dev_nx = trunc_to_int(y_nx);
+					avg_of = trunc_to_int(a);
+					if (more) {
+						lp.y1 = lp.y0;
+						lp.y0 = y_nx;
+					}
+					if (taps && lane == 0) {
+						const uint32_t ti = w.tap_n[2] + 2u * (uint32_t)k;
+						if (ti + 1 < p.tap_cap) {
+							p.tap_f64[tbase + ti] = y_cur;
+							p.tap_f64[tbase + ti + 1] = a;
+						}
+					}
+					const int tdiff = (int)(step - last_peak);
+					const bool hit = dev_cur < avg_of && dev_cur > last_dev && tdiff > spb34;
+					last_dev = dev_cur;
+					y_cur = y_nx;
+					dev_cur = dev_nx;
+					step++;
+					if (hit) {
+						phase_change(tdiff);
+						last_peak = step - 1;
+						if (w.s.synced) {   // the sync word completed on this sample: the frame path takes over
+							synced = 1;
+							rssi = __dadd_rn(rssi, (double)s_pw[k]);
+							k++;
+							break;
+						}
+					}
+				}
+				if (taps) w.tap_n[2] += 2u * (uint32_t)k;
+			}
+			for (; k < cnt; k++) {
+				// a frame is being received (whb.cpp:653,677,693: avg_of frozen, rssi accumulating)
+				const bool more = k + 1 < cnt;
+				double y_nx;
+				pulse(more ? k + 1 : k, y_nx);
+				const int dev_nx = trunc_to_int(y_nx);
+				if (more) {
+					lp.y1 = lp.y0;
+					lp.y0 = y_nx;
+				}
+				if (taps && lane == 0) tap_f64(w, y_cur);
+				const int tdiff = (int)(step - last_peak);
+				if (dev_cur < avg_of && dev_cur > last_dev && tdiff > spb34) {
+					phase_change(tdiff);
+					last_peak = step;
+				}
+				last_dev = dev_cur;
+				rssi = __dadd_rn(rssi, (double)s_pw[k]);
+				y_cur = y_nx;
+				dev_cur = dev_nx;
+				step++;
+			}
+			// the filter's input history after this step
+			if (cnt >= 2) {
+				lp.d1 = s_d[cnt - 1];
+				lp.d2 = s_d[cnt - 2];
+			} else {
+				lp.d2 = lp.d1;
+				lp.d1 = s_d[0];
+			}
+			__syncwarp();
+			cw = cw_nx;
+			lw = lw_nx;
+		}
+		if (last == e.end) {
+			// the timeout ran out on this sample (whb.cpp:691-700)
+			if (synced) {
+				for (int n = 0; n < 16; n++) whb_bit(w.s, 0);
+				w.s.rssi_d = rssi;
+				w.pos = base_pos + e.end;
+				if (lane == 0) whb_flush(w);
+				else { w.s.sr_cnt = -1; w.s.sr = 0; w.s.byte_cnt = 0; w.s.synced = 0; }
+				synced = 0;
+			}
+			w.s.offset = 0;
+			w.s.bitcnt = 0;
+			rssi = 0.0;
+			step = 0;
+			last_peak = 0;
+			w.s.timeout_cnt = 0;
+		} else {
+			w.s.timeout_cnt = (int)(e.end - last);
+		}
 	}
-	st->d[w.demod] = w.s;
+	if (lane != 0) return;
+	w.s.lp = lp;
+	w.s.lp_avg = la;
+	w.s.last_dev = last_dev;
+	w.s.avg_of = avg_of;
+	w.s.synced = synced;
+	w.s.step_lo = step;
+	w.s.last_peak = last_peak;
+	w.s.rssi_d = rssi;
+	st->d[demod] = w.s;
 	if (p.tap_cap)
-		for (int k = 0; k < 3; k++) p.tap_cnt[((size_t)w.stream * kMaxDemods + w.demod) * 3 + k] = w.tap_n[k];
+		for (int k = 0; k < 3; k++) p.tap_cnt[((size_t)stream * kMaxDemods + demod) * 3 + k] = w.tap_n[k];
 }
 
 // after the last epoch of a submit: roll positions, carry and last sample forward
@@ -400,8 +565,9 @@ __global__ void parse_kernel(const BackParams p)
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s)
 {
-	const int n = p.n_streams * n_demods;
-	walk_kernel<<<(n + 31) / 32, 32, 0, s>>>(p);
+	(void)n_demods;
+	if (p.tap_cap) whb_kernel<true><<<p.n_streams, 32, 0, s>>>(p);
+	else whb_kernel<false><<<p.n_streams, 32, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s)

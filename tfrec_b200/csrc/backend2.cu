@@ -440,19 +440,6 @@ struct LdHash {
 	}
 	__device__ __forceinline__ unsigned long long value() const { return ((unsigned long long)b << 32) | a; }
 };
-// (int)y, truncation toward zero, for |y| < 2^31 without the variable-latency F2I.F64: |y| + 2^52 rounded toward
-// zero leaves floor(|y|) in the low mantissa word; the sign comes back from y's high word
-__device__ __forceinline__ int trunc_to_int(double y)
-{
-	const int lo = __double2loint(__dadd_rz(fabs(y), 4503599627370496.0));
-	return (__double2hiint(y) < 0) ? -lo : lo;
-}
-// exact int -> double without the (slow, variable latency) I2F.F64: 2^52 + 2^31 + v, minus the offset
-__device__ __forceinline__ double int_to_double(int v)
-{
-	return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v + 0x80000000u)), 4503601774854144.0);
-}
-
 // tfa1_demod::demod, tfa1.cpp:143-190 over the samples [start, min(end, call_len-1)].
 // exact: s holds the true carried state (continuation or first window of the call); otherwise s.sr == 0
 // is a speculation that is checked with head31/nbits.
