@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "demod_dev.cuh"
 
@@ -440,6 +441,18 @@ struct LdHash {
 	}
 	__device__ __forceinline__ unsigned long long value() const { return ((unsigned long long)b << 32) | a; }
 };
+// Bits are not pushed into the framer from inside the per-sample walk: a warp walks 32 windows in lockstep, and
+// a bit burst on ONE lane (up to 31 framer steps for one edge, tfa2.cpp:400-407) would be executed, masked, by
+// all of them at nearly every sample.  The walk only appends run-length entries ((count << 1) | bit) to a small
+// per-thread list; the list is drained in a loop in which every active lane performs exactly one framer step per
+// iteration, so the lanes stay converged.  The demodulators never read framer state (no has_sync feedback in
+// tfa1_demod / tfa2_demod), so deferring the framer changes nothing.
+constexpr int kBitRuns = 64;
+struct BitRuns {
+	uint16_t run[kBitRuns];
+	int n;
+};
+
 // tfa1_demod::demod, tfa1.cpp:143-190 over the samples [start, min(end, call_len-1)].
 // exact: s holds the true carried state (continuation or first window of the call); otherwise s.sr == 0
 // is a speculation that is checked with head31/nbits.
@@ -456,10 +469,24 @@ static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, Demod
 	uint32_t head = 0;
 	int nbits = 0;
 	int mark = s.mark_lvl, rssi = s.rssi_i, lbi = s.last_bit_idx;   // hot state in registers
-	auto bit = [&](int b) {
-		if (nbits < 31) head |= (uint32_t)b << nbits;
-		nbits++;
-		tfa1_bit(s, b);
+	BitRuns br;
+	br.n = 0;
+	auto drain = [&]() {
+		int i = 0, rem = 0, b = 0;
+		for (;;) {
+			if (rem == 0) {
+				if (i == br.n) break;
+				b = br.run[i] & 1;
+				rem = br.run[i] >> 1;
+				i++;
+				if (rem == 0) continue;
+			}
+			if (nbits < 31) head |= (uint32_t)b << nbits;
+			nbits++;
+			tfa1_bit(s, b);
+			rem--;
+		}
+		br.n = 0;
 	};
 	const uint32_t last = min(e.end, c.call_len - 1);
 	const bool taps = c.p->tap_cap != 0;
@@ -468,10 +495,12 @@ static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, Demod
 	// four samples per 128-bit load, the next load issued before the current four are walked; the walk itself is
 	// ONE copy of the per-sample code (rotating the vector) - unrolled copies thrash the instruction cache
 	const int4 *src4 = reinterpret_cast<const int4 *>(c.dec);
+	if ((e.start & ~31u) + 32 <= last) prefetch_l1(c.dec + (e.start & ~31u) + 32);
 	int4 nxt = src4[(e.start & ~3u) >> 2];
 	for (uint32_t cb = e.start & ~3u; cb <= last; cb += 4) {
 	int4 v4 = nxt;
 	if (cb + 4 <= last) nxt = src4[(cb + 4) >> 2];
+	if ((cb & 31u) == 0 && cb + 64 <= last) prefetch_l1(c.dec + cb + 64);   // the line after next: an L2 round trip is ~1 us
 #pragma unroll 1
 	for (int kk = 0; kk < 4; kk++) {
 		const uint32_t m = cb + kk;
@@ -494,14 +523,17 @@ static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, Demod
 			if (lbi) {
 				const int gap = index - lbi;
 				if (gap > 4) {
-					for (int n = 22; n <= gap; n += 20) bit(1);
-					bit(0);
+					// `for (n = 22; n <= gap; n += 20) bit(1); bit(0);`  (tfa1.cpp:168-173)
+					if (br.n + 2 > kBitRuns) drain();
+					if (gap >= 22) br.run[br.n++] = (uint16_t)(((((gap - 22) / 20) + 1) << 1) | 1);
+					br.run[br.n++] = (uint16_t)(1 << 1);
 				}
 			}
 			if (index - lbi > 2) lbi = index;
 		}
 	}
 	}
+	drain();
 	s.mark_lvl = mark;
 	s.rssi_i = rssi;
 	s.last_bit_idx = lbi;
@@ -546,14 +578,40 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
 	LdHash hash;
 	hash.init();
+	BitRuns br;
+	br.n = 0;
+	auto drain = [&]() {
+		int i = 0, rem = 0, b = 0;
+		for (;;) {
+			if (rem == 0) {
+				if (i == br.n) break;
+				b = br.run[i] & 1;
+				rem = br.run[i] >> 1;
+				i++;
+				if (rem == 0) continue;
+			}
+			tfa2_bit(s, b);
+			rem--;
+		}
+		br.n = 0;
+	};
 	// the slicer levels only move while bitcnt < 10: keep them out of the per-sample chain
 	int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
 	int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
 	const int4 *src4 = reinterpret_cast<const int4 *>(c.devfm);
+	prefetch_l1(c.dec + (e.start & ~31u));        // the first bits' rssi reads I/Q (tfa2.cpp:373)
+	if ((e.start & ~31u) + 32 <= last) {
+		prefetch_l1(c.devfm + (e.start & ~31u) + 32);
+		prefetch_l1(c.dec + (e.start & ~31u) + 32);
+	}
 	int4 nxt = src4[(e.start & ~3u) >> 2];
 	for (uint32_t cb = e.start & ~3u; cb <= last; cb += 4) {
 	int4 v4 = nxt;
 	if (cb + 4 <= last) nxt = src4[(cb + 4) >> 2];
+	if ((cb & 31u) == 0 && cb + 64 <= last) {   // the line after next: an L2 round trip is ~1 us
+		prefetch_l1(c.devfm + cb + 64);
+		if (bitcnt < 10) prefetch_l1(c.dec + cb + 64);
+	}
 #pragma unroll 1
 	for (int kk = 0; kk < 4; kk++) {
 		const uint32_t m = cb + kk;
@@ -624,7 +682,11 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	rec.lbi_end_block = (int)(last >> 13);
 	if (!far && have_edge) rec.flags |= kRecEdge;
 	if (last == e.end) {
-		for (int n = 0; n < 16; n++) tfa2_bit(s, last_bit);
+		if (br.n + 1 > kBitRuns) drain();
+		br.run[br.n++] = (uint16_t)((16 << 1) | last_bit);   // 16 x store_bit(last_bit) before the flush (tfa2.cpp:430-433)
+	}
+	drain();
+	if (last == e.end) {
 		const bool gate = (cfg.kind == K_TX22) ? (s.byte_cnt >= 7 && s.byte_cnt < 64) : (s.byte_cnt >= 7);
 		int fi = -1;
 		if (gate) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, s.offset);
@@ -668,7 +730,13 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 // unless last_bit_idx is the 0 sentinel, which verify_kernel catches) and is cut every kChainMax windows to
 // bound the tail latency.  TFA_1 windows carry only the decoder shift register and stay one per thread.
 // ------------------------------------------------------------------------------------------------
-constexpr int kChainMax = 8;
+#ifndef TFR_CHAIN_MAX
+#define TFR_CHAIN_MAX 8
+#endif
+constexpr int kChainMax = TFR_CHAIN_MAX;
+#ifdef TFR_WIN_PROFILE
+__device__ unsigned long long g_winprof[16];
+#endif
 __device__ __forceinline__ bool win_near(const WinEntry *wl, uint32_t w, int timeout)
 {
 	return wl[w].start - wl[w - 1].end <= (uint32_t)timeout + 1u;
@@ -696,6 +764,9 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
 	const bool chains = (cfg.kind != K_TFA1);
 
+#ifdef TFR_WIN_PROFILE
+	long long prof_t0 = clock64(), prof_warm = 0, prof_run = 0, prof_steps = 0;
+#endif
 	for (uint32_t w0 = blockIdx.x * blockDim.x + threadIdx.x; w0 < n_win; w0 += gridDim.x * blockDim.x) {
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
 		DemodState s;
@@ -749,6 +820,9 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 							have += len;
 						}
 					}
+#ifdef TFR_WIN_PROFILE
+					const long long pw0 = clock64();
+#endif
 					Biquad lp;
 					lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
 					if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
@@ -757,14 +831,23 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 						const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
 						uint32_t m = a;
 						for (; (m & 15u) && m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
-						for (; m + 15 <= b; m += 16) {
-							const Chunk16 ck = load16(c.devfm + m);
+						if (m + 15 <= b) {
+							// two chunks in flight: the next one is loaded before the current one is filtered
+							Chunk16 ck = load16(c.devfm + m);
+							for (; m + 15 <= b; m += 16) {
+								Chunk16 nx = ck;
+								if (m + 31 <= b) nx = load16(c.devfm + m + 16);
 #pragma unroll
-							for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
+								for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
+								ck = nx;
+							}
 						}
 						for (; m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
 					}
 					s.lp = lp;
+#ifdef TFR_WIN_PROFILE
+					prof_warm += clock64() - pw0;
+#endif
 				} else {
 					// chain member: s is what the predecessor left (run_tfa2_window already did the end-of-window
 					// reset); last_bit_idx moves to this window's first block (demodulator::start, decoder.cpp:118-122)
@@ -779,7 +862,14 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 				}
 				rec.u_y0 = s.lp.y0;
 				rec.u_y1 = s.lp.y1;
+#ifdef TFR_WIN_PROFILE
+				const long long pr0 = clock64();
+#endif
 				run_tfa2_window(c, cfg, e, s, rec, cont, far);
+#ifdef TFR_WIN_PROFILE
+				prof_run += clock64() - pr0;
+				prof_steps += min(e.end, c.call_len - 1) - e.start + 1;
+#endif
 				if (rec.flags & kRecEdge) have_lbi = true;
 			}
 			if (rec.flags & kRecUnfinished) st->fin[demod] = s;
@@ -787,6 +877,15 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 			if (rec.flags & kRecUnfinished) break;
 		}
 	}
+#ifdef TFR_WIN_PROFILE
+	{
+		const int kd = cfg.kind;
+		atomicMax(&g_winprof[kd], (unsigned long long)prof_warm);
+		atomicMax(&g_winprof[4 + kd], (unsigned long long)prof_run);
+		atomicMax(&g_winprof[8 + kd], (unsigned long long)prof_steps);
+		atomicMax(&g_winprof[12 + kd], (unsigned long long)(clock64() - prof_t0));
+	}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -882,10 +981,15 @@ static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c
 	};
 	uint32_t m = e.start;
 	for (; (m & 15u) && m <= last; m++) step(m, c.devfm[m]);            // head up to the first 16-aligned sample
-	for (; m + 15 <= last; m += 16) {                                     // whole chunks: no per-sample predicate
-		const Chunk16 ck = load16(c.devfm + m);
+	if (m + 15 <= last) {                                                 // whole chunks: no per-sample predicate
+		Chunk16 ck = load16(c.devfm + m);
+		for (; m + 15 <= last; m += 16) {
+			Chunk16 nx = ck;
+			if (m + 31 <= last) nx = load16(c.devfm + m + 16);   // in flight while the current chunk is filtered
 #pragma unroll
-		for (int kk = 0; kk < 16; kk++) step(m + kk, ck.v[kk]);
+			for (int kk = 0; kk < 16; kk++) step(m + kk, ck.v[kk]);
+			ck = nx;
+		}
 	}
 	for (; m <= last; m++) step(m, c.devfm[m]);                          // tail
 	lp_io = lp;
@@ -1136,6 +1240,19 @@ static dim3 win_grid(const BackParams &p, int n_demods, int threads)
 }
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 {
+#ifdef TFR_WIN_PROFILE
+	{
+		unsigned long long z[16] = { 0 }, r[16];
+		cudaStreamSynchronize(s);
+		cudaMemcpyToSymbol(g_winprof, z, sizeof(z));
+		win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+		cudaStreamSynchronize(s);
+		cudaMemcpyFromSymbol(r, g_winprof, sizeof(r));
+		for (int k = 0; k < 4; k++)
+			fprintf(stderr, "[winprof] kind %d: max warm-up %llu cyc, max slicer %llu cyc over max %llu steps, max thread %llu cyc\n", k, r[k], r[4 + k], r[8 + k], r[12 + k]);
+		return cudaGetLastError();
+	}
+#endif
 	win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
 	return cudaGetLastError();
 }

@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np, torch
 import tfrec_b200 as tb
+if os.environ.get("TFR_LIB"):   # experiments: a library built with other compile-time knobs
+    tb.LIB_PATH = os.environ["TFR_LIB"]
 
 def main():
     n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 16
