@@ -1,6 +1,7 @@
 // demod_dev.cuh - device functions shared by the back-end kernels: region enumeration over the sparse
-// decimated buffer, the discriminators and biquad, and the per-sample demodulator / framer state machines
-// (tfa1.cpp:120-190, tfa2.cpp:281-442, whb.cpp:566-707).  See backend.cu for the floating-point notes.
+// decimated buffer, the discriminators and biquad, and the bit framers (store_bit: tfa1.cpp:120-134,
+// tfa2.cpp:281-314, whb.cpp:566-603).  The demodulators themselves live in backend2.cu (TFA_1, TFA_2 family)
+// and backend.cu (WeatherHub).  See backend.cu for the floating-point notes.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -9,15 +10,6 @@
 #include "tfr_dev.h"
 
 namespace tfr {
-
-// carry_in (samples at the head of the first block of this epoch that an earlier trigger still covers)
-// as it stood when the epoch began: from the stream state for the first block of a submit, else from the
-// previous block's descriptor.  Only submit_epilogue_kernel advances the stream-level copy.
-__device__ __forceinline__ int entry_carry(const BackParams &p, const StreamJob &job, const StreamState *st)
-{
-	if (p.tile0 == 0) return st->carry_in;
-	return p.tiles[(size_t)job.dec_off + p.tile0 - 1].carry_out;
-}
 
 // ------------------------------------------------------------------------------------------------
 // region enumeration: the samples of a block the front-end kept = [0, carry_in) U segments
@@ -173,43 +165,6 @@ __device__ __forceinline__ void tfa1_bit(DemodState &s, int bit)
 	}
 	if (s.sr_cnt >= 0) s.sr_cnt = (s.sr_cnt + 1) & 7;
 }
-static __device__ void tfa1_flush(Walk &w)
-{
-	DemodState &s = w.s;
-	if (s.byte_cnt >= 10) emit_frame(w, (double)s.rssi_i, 0);
-	s.sr_cnt = -1;
-	s.byte_cnt = 0;
-	s.rdata[10] = 0;
-}
-__device__ __forceinline__ void tfa1_sample(Walk &w, int thresh, int pwr, int index, int i, int q, int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) s.timeout_cnt = 400;   // 40*BITPERIOD, tfa1.cpp:34,148
-	if (!s.timeout_cnt) return;
-	const int dev = fm_dev_nrzs(i, q, li, lq);
-	tap_i32(w, 1, dev);
-	if (dev > s.mark_lvl) s.mark_lvl = dev;
-	else s.mark_lvl = __double2int_rz(__dmul_rn((double)s.mark_lvl, 0.95));
-	if (s.mark_lvl > s.rssi_i) s.rssi_i = s.mark_lvl;
-	s.timeout_cnt--;
-	if (dev < s.mark_lvl / 2) {
-		if (s.last_bit_idx) {
-			const int gap = index - s.last_bit_idx;
-			if (gap > 4) {
-				for (int n = 22; n <= gap; n += 20) tfa1_bit(s, 1);
-				tfa1_bit(s, 0);
-			}
-		}
-		if (index - s.last_bit_idx > 2) s.last_bit_idx = index;
-	}
-	if (!s.timeout_cnt) {
-		tfa1_flush(w);
-		s.mark_lvl = 0;
-		s.rssi_i = 0;
-		s.last_bit_idx = 0;
-	}
-}
-
 // ---- TFA_2 / TFA_3 / TX22 ---------------------------------------------------------------------------
 __device__ __forceinline__ void tfa2_bit(DemodState &s, int bit)
 {
@@ -242,66 +197,6 @@ __device__ __forceinline__ void tfa2_reset(DemodState &s)
 	s.last_bit = 0;
 	s.rssi_i = 0;
 }
-static __device__ void tfa2_flush(Walk &w, int kind)
-{
-	DemodState &s = w.s;
-	const bool gate = (kind == K_TX22) ? (s.byte_cnt >= 7 && s.byte_cnt < 64) : (s.byte_cnt >= 7);
-	if (gate) emit_frame(w, (double)s.rssi_i, s.offset);
-	s.sr_cnt = -1;
-	s.sr = 0;
-	s.byte_cnt = 0;
-}
-__device__ __forceinline__ void tfa2_sample(Walk &w, const DemodCfg &cfg, int thresh, int pwr, int index, int i, int q,
-					    int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) {
-		if (!s.timeout_cnt) tfa2_reset(s);
-		s.timeout_cnt = cfg.timeout;
-	}
-	if (!s.timeout_cnt) return;
-	const int dev0 = fm_dev(i, q, li, lq);
-	tap_i32(w, 0, dev0);
-	const double y = biquad_step(s.lp, cfg.lp, (double)dev0);
-	tap_f64(w, y);
-	const int ld = __double2int_rz(y);
-	if (s.bitcnt < 10) {
-		if (ld > s.dmax) s.dmax = (7 * s.dmax + ld) / 8;
-		if (ld < s.dmin) s.dmin = (7 * s.dmin + ld) / 8;
-		s.offset = (s.dmax + s.dmin) / 2;
-		if (s.bitcnt > 4) {
-			const uint32_t sum = (uint32_t)s.rssi_i + (uint32_t)(i * i) + (uint32_t)(q * q);
-			s.rssi_i = (int)((uint32_t)s.rssi_i + (uint32_t)((int)sum / 100));
-		}
-	}
-	s.timeout_cnt--;
-	const int dev = ld;
-	const int noffset = __double2int_rz(__dmul_rn(0.9, (double)s.offset));
-	const int hi = noffset + s.dmax / 32, lo = noffset + s.dmin / 32;
-	const int bit = dev > hi ? 1 : 0;
-	if ((dev > hi || dev < lo) && bit != s.last_bit) {
-		if (index > s.last_bit_idx + 8) {
-			s.bitcnt++;
-			const int tdiff = index - s.last_bit_idx;
-			if ((double)tdiff > __dmul_rn(cfg.spb, 0.25) && (double)tdiff < __dmul_rn(32.0, cfg.spb)) {
-				const int bit_diff = tdiff / 2;
-				const int numbits =
-					__double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, __dmul_rn(cfg.spb, 0.5)), cfg.spb));
-				if (numbits < 32)
-					for (int n = 1; n < numbits; n++) tfa2_bit(s, s.last_bit);
-				tfa2_bit(s, bit);
-				s.last_bit = bit;
-			}
-		}
-		if (index - s.last_bit_idx > 2) s.last_bit_idx = index;
-	}
-	if (!s.timeout_cnt) {
-		for (int n = 0; n < 16; n++) tfa2_bit(s, s.last_bit);
-		tfa2_flush(w, cfg.kind);
-		tfa2_reset(s);
-	}
-}
-
 // ---- WeatherHub ---------------------------------------------------------------------------------
 __device__ __forceinline__ void whb_bit(DemodState &s, int bit)
 {
@@ -326,14 +221,6 @@ __device__ __forceinline__ void whb_bit(DemodState &s, int bit)
 	}
 	if (s.sr_cnt >= 0) s.sr_cnt = (s.sr_cnt + 1) & 7;
 }
-__device__ __forceinline__ void whb_reset(DemodState &s)
-{
-	s.offset = 0;
-	s.bitcnt = 0;
-	s.rssi_d = 0.0;
-	s.step_lo = 0;
-	s.last_peak = 0;
-}
 static __device__ void whb_flush(Walk &w)
 {
 	DemodState &s = w.s;
@@ -343,49 +230,4 @@ static __device__ void whb_flush(Walk &w)
 	s.byte_cnt = 0;
 	s.synced = 0;
 }
-__device__ __forceinline__ void whb_sample(Walk &w, const DemodCfg &cfg, int thresh, int pwr, int i, int q, int li, int lq)
-{
-	DemodState &s = w.s;
-	if (pwr > thresh) {
-		if (!s.timeout_cnt) whb_reset(s);
-		s.timeout_cnt = cfg.timeout;
-	}
-	if (s.timeout_cnt) {
-		const int dev0 = fm_dev_nrzs(i, q, li, lq);
-		tap_i32(w, 1, dev0);
-		const double y = biquad_step(s.lp, cfg.lp, (double)dev0);
-		tap_f64(w, y);
-		const int dev = __double2int_rz(y);
-		if (!s.synced) {
-			const double a = biquad_step(s.lp_avg, cfg.lp_avg, __dmul_rn(0.5, (double)dev));
-			tap_f64(w, a);
-			s.avg_of = __double2int_rz(a);
-		}
-		s.timeout_cnt--;
-		const int tdiff = (int)(s.step_lo - s.last_peak);
-		if (dev < s.avg_of && dev > s.last_dev && (double)tdiff > __dmul_rn(cfg.spb, 0.75)) {
-			whb_bit(s, 0);
-			s.bitcnt++;
-			const int bit0 = __double2int_rz(__ddiv_rn(__dadd_rn((double)tdiff, __dmul_rn(cfg.spb, 0.5)), cfg.spb));
-			for (int n = 1; n < bit0; n++) {
-				whb_bit(s, 1);
-				s.bitcnt++;
-			}
-			s.last_peak = s.step_lo;
-		}
-		s.last_dev = dev;
-		if (s.synced) s.rssi_d = __dadd_rn(s.rssi_d, (double)(i * i + q * q));
-		if (!s.timeout_cnt) {
-			if (s.synced) {
-				for (int n = 0; n < 16; n++) whb_bit(s, 0);
-				whb_flush(w);
-			}
-			whb_reset(s);
-			s.rssi_d = 0.0;
-		}
-	}
-	s.step_lo++;
-}
-
-
 }  // namespace tfr

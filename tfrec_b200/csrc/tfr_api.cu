@@ -522,7 +522,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	// per stream, a serial chain) runs on the walk stream while the front-end of chunk k+1 streams on.
 	CU(cudaEventRecord(sl.fe0, sf));
 	{
-		const int n_chunks = (max_blocks >= 64u * kFrontChunks) ? kFrontChunks : 1;
+		// at least 8192 blocks (512 MiB, ~18 waves of CTAs) per launch: smaller launches only add tails
+		const int n_chunks = (int)std::min<size_t>(kFrontChunks, std::max<size_t>(1, total / 8192));
 		const int per = (int)((max_blocks + n_chunks - 1) / n_chunks);
 		CU(cudaStreamWaitEvent(h->stream_walk, sl.fe0, 0));   // the walk stream starts after everything queued so far
 		for (int k = 0; k < n_chunks; k++) {
