@@ -248,6 +248,8 @@ def main():
 
     import torch
     import tfrec_b200 as tb
+    if os.environ.get("TFR_LIB"):   # A/B experiments only: a library built from another revision
+        tb.LIB_PATH = os.environ["TFR_LIB"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,9 +335,18 @@ def main():
     rx.clear()
     barrier()
     wall = time.perf_counter() - t0
+    # extra (not the headline): the same K steps issued back to back with ONE synchronisation - the library's two
+    # work-buffer slots let the front-end of step i+1 overlap the latency-bound back-end of step i
+    for _ in range(args.steps):
+        step_device()
+    rx.sync()
+    pipe_ms = rx.stats()["last_total_ms"]
+    rx.clear()
+    barrier()
     clocks = sampler.stop(m0, sampler.mark() + 1) if rank == 0 else None
     launches = rx.stats()["kernel_launches"] - l0
     t_dev = allmax(dev_ms / 1e3)
+    t_pipe = allmax(pipe_ms / 1e3)
     t_wall = allmax(wall)
     total_samples = allsum(float(samples_per_step)) * args.steps
     total_decoded = allsum(float(decoded))
@@ -409,6 +420,9 @@ def main():
            "telegrams_per_s": round(total_decoded / t_dev, 2), "telegrams_decoded": int(total_decoded),
            "telegrams_sent": int(total_sent), "wall_ms_per_step": round(1e3 * t_wall / args.steps, 4),
            "gpu_launches": int(launches), "demod_windows_per_step": int(windows // max(args.steps, 1)),
+           "steps_in_flight": {"value": round(total_samples / t_pipe / 1e6, 2), "unit": "MSamples/s",
+                               "ms_per_step": round(1e3 * t_pipe / args.steps, 4),
+                               "note": "same K steps without a per-step sync (front-end of step i+1 overlaps the back-end of step i)"},
            "clocks": clocks, "roofline": roofline}
     if e2e is not None:
         out["e2e"] = e2e

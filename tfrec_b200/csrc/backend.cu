@@ -28,10 +28,9 @@ namespace tfr {
 //   * the warp walks the demod's window list (threshold kernel), 32 samples per step: every lane loads one
 //     stored sample and its predecessor (coalesced) and computes the discriminator Re(a*conj b) and I^2+Q^2;
 //     the loads of the next 32 samples are issued before the current ones are consumed
-//   * the serial part - pulse biquad, averaging biquad, dip detector - is executed redundantly by all lanes
-//     (uniform control flow, state in registers), fed by shuffles.  The two biquad recurrences are independent
-//     dependency chains (the averaging filter only consumes the pulse filter's truncated output), so they
-//     overlap and a sample costs about one biquad latency
+//   * per 32-sample step only the two biquad RECURRENCES are serial (four dependent FP64 operations per sample
+//     each, run redundantly by all lanes); everything around them - input-only filter terms, truncations,
+//     comparisons - is done by the lanes in parallel between the two serial phases
 //   * bits (one per >= 48 samples), the descrambler/framer and the frame buffer are the rare path (lane 0's
 //     local memory is the reference's rdata[])
 // ------------------------------------------------------------------------------------------------
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 	};
 
 	// per 32-sample step: what the lanes prepare in parallel for the serial part
-	__shared__ double s_t2[32], s_u[32], s_d[32];
+	__shared__ double s_t2[32], s_u[32], s_d[32], s_y[32], s_t2s[32], s_us[32], s_x[32], s_a[32];
 	__shared__ int s_pw[32];
 	const size_t tbase = ((size_t)stream * kMaxDemods + demod) * (size_t)p.tap_cap;
 
@@ -122,12 +121,34 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 			}
 			if (taps) w.tap_n[1] += (uint32_t)cnt;
 			__syncwarp();
-			// Software pipeline: at the top of iteration k, (y_cur, dev_cur) is the pulse filter's output for sample k
-			// and lp has already advanced through it.  Each iteration starts sample k+1's pulse filter (chain A) next
-			// to sample k's averaging filter (chain B) in ONE basic block, so that the two dependency chains overlap.
-			auto pulse = [&](int kk, double &y) {
-				y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[kk], __dmul_rn(kp.a1, lp.y0)), s_t2[kk]), __dmul_rn(kp.a2, lp.y1));
-			};
+			// ---- phase 1 (serial): the pulse filter's recurrence alone - four dependent FP64 operations per sample,
+			// nothing else on the chain.  All lanes run it redundantly (uniform), results go to shared memory.
+			{
+				// (the shared-memory operands are fetched three samples ahead: an LDS in front of its use would put
+				// ~30 cycles on top of the 4 x 8-cycle FP64 chain of every sample)
+				double y0 = lp.y0, y1 = lp.y1;
+				double ua = s_u[0], ta = s_t2[0], ub = s_u[1], tb = s_t2[1], uc = s_u[2], tc = s_t2[2];
+#pragma unroll 8
+				for (int k = 0; k < cnt; k++) {
+					const int kn = min(k + 3, 31);
+					const double un = s_u[kn], tn = s_t2[kn];
+					const double y = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(kp.a1, y0)), ta), __dmul_rn(kp.a2, y1));
+					s_y[k] = y;
+					y1 = y0;
+					y0 = y;
+					ua = ub; ta = tb; ub = uc; tb = tc; uc = un; tc = tn;
+				}
+				lp.y0 = y0;
+				lp.y1 = y1;
+			}
+			__syncwarp();
+			// ---- phase 2 (parallel, lane = sample): truncate, compare with the previous sample, and - while no frame
+			// is in progress - the averaging filter's input-only terms
+			const int dev = trunc_to_int(s_y[lane]);
+			int dev_prev = __shfl_up_sync(0xffffffffu, dev, 1);
+			if (lane == 0) dev_prev = last_dev;
+			const bool rising = lane < cnt && dev > dev_prev;
+			const uint32_t step0 = step;
 			auto phase_change = [&](int tdiff) {
 				// one 0, then a 1 for every further bit period since the last one (whb.cpp:662-674)
 				whb_bit(w.s, 0);
@@ -138,73 +159,90 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 					w.s.bitcnt++;
 				}
 			};
-			double y_cur;
-			pulse(0, y_cur);
-			lp.y1 = lp.y0;
-			lp.y0 = y_cur;
-			int dev_cur = trunc_to_int(y_cur);
-			int k = 0;
-			if (!synced) {
-				// the common case: no frame in progress
-				for (; k < cnt; k++) {
-					const bool more = k + 1 < cnt;
-					double y_nx;
-					pulse(more ? k + 1 : k, y_nx);                                                   // chain A
-					const double a = biquad_step(la, ka, __dmul_rn(0.5, int_to_double(dev_cur)));    // chain B
-					const int dev_nx = trunc_to_int(y_nx);
-					avg_of = trunc_to_int(a);
-					if (more) {
-						lp.y1 = lp.y0;
-						lp.y0 = y_nx;
-					}
-					if (taps && lane == 0) {
-						const uint32_t ti = w.tap_n[2] + 2u * (uint32_t)k;
-						if (ti + 1 < p.tap_cap) {
-							p.tap_f64[tbase + ti] = y_cur;
-							p.tap_f64[tbase + ti + 1] = a;
-						}
-					}
-					const int tdiff = (int)(step - last_peak);
-					const bool hit = dev_cur < avg_of && dev_cur > last_dev && tdiff > spb34;
-					last_dev = dev_cur;
-					y_cur = y_nx;
-					dev_cur = dev_nx;
-					step++;
-					if (hit) {
+			// dip decisions over a candidate mask, in sample order (only last_peak chains them); returns the sample on
+			// which the sync word completed, or -1
+			auto decide = [&](unsigned cm, bool stop_at_sync) -> int {
+				while (cm) {
+					const int k = __ffs(cm) - 1;
+					cm &= cm - 1;
+					const int tdiff = (int)(step0 + (uint32_t)k - last_peak);
+					if (tdiff > spb34) {
 						phase_change(tdiff);
-						last_peak = step - 1;
-						if (w.s.synced) {   // the sync word completed on this sample: the frame path takes over
-							synced = 1;
-							rssi = __dadd_rn(rssi, (double)s_pw[k]);
-							k++;
-							break;
-						}
+						last_peak = step0 + (uint32_t)k;
+						if (stop_at_sync && w.s.synced) return k;
 					}
 				}
-				if (taps) w.tap_n[2] += 2u * (uint32_t)k;
-			}
-			for (; k < cnt; k++) {
-				// a frame is being received (whb.cpp:653,677,693: avg_of frozen, rssi accumulating)
-				const bool more = k + 1 < cnt;
-				double y_nx;
-				pulse(more ? k + 1 : k, y_nx);
-				const int dev_nx = trunc_to_int(y_nx);
-				if (more) {
-					lp.y1 = lp.y0;
-					lp.y0 = y_nx;
+				return -1;
+			};
+			// a frame is being received from sample k0 on (whb.cpp:653,677,693): avg_of frozen, rssi accumulating
+			auto frame_part = [&](int k0) {
+				decide(__ballot_sync(0xffffffffu, rising && lane >= k0 && dev < avg_of), false);
+				long long pw = (lane >= k0 && lane < cnt) ? (long long)s_pw[lane] : 0ll;
+				for (int o = 16; o; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+				rssi = __dadd_rn(rssi, (double)pw);   // sums of I^2+Q^2 stay far below 2^53: every partial sum is exact
+				if (taps) {
+					const uint32_t ti = w.tap_n[2] + (uint32_t)(lane - k0);
+					if (lane >= k0 && lane < cnt && ti < p.tap_cap) p.tap_f64[tbase + ti] = s_y[lane];
+					w.tap_n[2] += (uint32_t)(cnt - k0);
 				}
-				if (taps && lane == 0) tap_f64(w, y_cur);
-				const int tdiff = (int)(step - last_peak);
-				if (dev_cur < avg_of && dev_cur > last_dev && tdiff > spb34) {
-					phase_change(tdiff);
-					last_peak = step;
+			};
+			if (!synced) {
+				const double x = __dmul_rn(0.5, int_to_double(dev));
+				double x1 = __shfl_up_sync(0xffffffffu, x, 1), x2 = __shfl_up_sync(0xffffffffu, x, 2);
+				if (lane == 0) { x1 = la.d1; x2 = la.d2; }
+				if (lane == 1) x2 = la.d1;
+				s_t2s[lane] = __dadd_rn(__dmul_rn(ka.b0, x), __dmul_rn(ka.b1, x1));
+				s_us[lane] = __dmul_rn(ka.b2, x2);
+				s_x[lane] = x;
+				__syncwarp();
+				// ---- phase 3 (serial): the averaging filter's recurrence
+				double y0 = la.y0, y1 = la.y1;
+				double ua = s_us[0], ta = s_t2s[0], ub = s_us[1], tb = s_t2s[1], uc = s_us[2], tc = s_t2s[2];
+#pragma unroll 8
+				for (int k = 0; k < cnt; k++) {
+					const int kn = min(k + 3, 31);
+					const double un = s_us[kn], tn = s_t2s[kn];
+					const double a = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(ka.a1, y0)), ta), __dmul_rn(ka.a2, y1));
+					s_a[k] = a;
+					y1 = y0;
+					y0 = a;
+					ua = ub; ta = tb; ub = uc; tb = tc; uc = un; tc = tn;
 				}
-				last_dev = dev_cur;
-				rssi = __dadd_rn(rssi, (double)s_pw[k]);
-				y_cur = y_nx;
-				dev_cur = dev_nx;
-				step++;
+				__syncwarp();
+				// ---- phase 4 (parallel) + 5 (the rare dips, in order)
+				const int avg = trunc_to_int(s_a[lane]);
+				if (taps) {
+					const uint32_t ti = w.tap_n[2] + 2u * (uint32_t)lane;
+					if (lane < cnt && ti + 1 < p.tap_cap) {
+						p.tap_f64[tbase + ti] = s_y[lane];
+						p.tap_f64[tbase + ti + 1] = s_a[lane];
+					}
+				}
+				const int ks = decide(__ballot_sync(0xffffffffu, rising && dev < avg), true);
+				if (ks < 0) {
+					la.d2 = (cnt >= 2) ? s_x[cnt - 2] : la.d1;
+					la.d1 = s_x[cnt - 1];
+					la.y0 = y0;
+					la.y1 = y1;
+					avg_of = __shfl_sync(0xffffffffu, avg, cnt - 1);
+					if (taps) w.tap_n[2] += 2u * (uint32_t)cnt;
+				} else {
+					// the sync word completed on sample ks: the averaging filter stops there, the rest of the step is frame
+					la.y1 = (ks >= 1) ? s_a[ks - 1] : la.y0;
+					la.y0 = s_a[ks];
+					la.d2 = (ks >= 1) ? s_x[ks - 1] : la.d1;
+					la.d1 = s_x[ks];
+					avg_of = __shfl_sync(0xffffffffu, avg, ks);
+					synced = 1;
+					rssi = __dadd_rn(rssi, (double)s_pw[ks]);
+					if (taps) w.tap_n[2] += 2u * (uint32_t)(ks + 1);
+					frame_part(ks + 1);
+				}
+			} else {
+				frame_part(0);
 			}
+			last_dev = __shfl_sync(0xffffffffu, dev, cnt - 1);
+			step += (uint32_t)cnt;
 			// the filter's input history after this step
 			if (cnt >= 2) {
 				lp.d1 = s_d[cnt - 1];
