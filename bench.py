@@ -335,6 +335,8 @@ def main():
     rx.clear()
     barrier()
     wall = time.perf_counter() - t0
+    launches = rx.stats()["kernel_launches"] - l0
+    m1 = sampler.mark() + 1
     # extra (not the headline): the same K steps issued back to back with ONE synchronisation - the library's two
     # work-buffer slots let the front-end of step i+1 overlap the latency-bound back-end of step i
     for _ in range(args.steps):
@@ -343,8 +345,7 @@ def main():
     pipe_ms = rx.stats()["last_total_ms"]
     rx.clear()
     barrier()
-    clocks = sampler.stop(m0, sampler.mark() + 1) if rank == 0 else None
-    launches = rx.stats()["kernel_launches"] - l0
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     t_dev = allmax(dev_ms / 1e3)
     t_pipe = allmax(pipe_ms / 1e3)
     t_wall = allmax(wall)
