@@ -29,6 +29,9 @@
 #include "demod_dev.cuh"
 
 namespace tfr {
+#ifdef TFR_WIN_PROFILE
+__device__ unsigned long long g_slprof[8];   // of one 2784-sample window: fast groups, general groups, cycles in each
+#endif
 
 
 // ------------------------------------------------------------------------------------------------
@@ -604,6 +607,37 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		prefetch_l1(c.devfm + (e.start & ~31u) + 32);
 		prefetch_l1(c.dec + (e.start & ~31u) + 32);
 	}
+	// sample m is an edge candidate: (ld > hi || ld < lo) && bit != last_bit  (tfa2.cpp:386-412)
+	auto edge = [&](uint32_t m, int ld) {
+		const int index = 2 * (int)(m & (kBlockDec - 1));
+		const int bit = ld > hi ? 1 : 0;
+		if (far && !have_edge) {
+			// speculated: index > last_bit_idx+8, tdiff >= 32*spb  ->  bitcnt++, no bits, re-arm
+			rec.first_edge = index;
+			rec.first_edge_block = (int)(m >> 13);
+			rec.flags |= kRecEdge;
+			bitcnt++;
+			lbi = index;
+		} else {
+			if (index > lbi + 8) {
+				bitcnt++;
+				const int tdiff = index - lbi;
+				if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
+					const int bit_diff = tdiff / 2;
+					const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
+					if (br.n + 2 > kBitRuns) drain();
+					if (numbits < 32 && numbits > 1) br.run[br.n++] = (uint16_t)(((numbits - 1) << 1) | last_bit);
+					br.run[br.n++] = (uint16_t)((1 << 1) | bit);
+					last_bit = bit;
+				}
+			}
+			if (index - lbi > 2) lbi = index;
+		}
+		have_edge = true;
+	};
+#ifdef TFR_WIN_PROFILE
+	long long pf_fast = 0, pf_gen = 0, pf_cfast = 0, pf_cgen = 0, pf_t0 = clock64();
+#endif
 	int4 nxt = src4[(e.start & ~3u) >> 2];
 	for (uint32_t cb = e.start & ~3u; cb <= last; cb += 4) {
 	int4 v4 = nxt;
@@ -611,6 +645,32 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	if ((cb & 31u) == 0 && cb + 64 <= last) {   // the line after next: an L2 round trip is ~1 us
 		prefetch_l1(c.devfm + cb + 64);
 		if (bitcnt < 10) prefetch_l1(c.dec + cb + 64);
+	}
+#ifdef TFR_WIN_PROFILE
+	const long long pg0 = clock64();
+#endif
+	if (bitcnt >= 10 && !taps && cb >= e.start && cb + 3 <= last) {
+		// Steady state (the slicer levels are frozen after ten edges, tfa2.cpp:365) on a whole group of four: the
+		// four filter steps, truncations and hash terms form ONE basic block - the FP64 recurrence is the only
+		// chain - and the rare edge candidates are looked at afterwards, in order.
+		if ((cb & (kBlockDec - 1)) == 0 && cb != e.start && lbi) lbi -= kIdxPerBlock;   // demodulator::start of a new block
+		const double y0 = biquad_step(lp, k, int_to_double(v4.x));
+		const double y1 = biquad_step(lp, k, int_to_double(v4.y));
+		const double y2 = biquad_step(lp, k, int_to_double(v4.z));
+		const double y3 = biquad_step(lp, k, int_to_double(v4.w));
+		const int l0 = trunc_to_int(y0), l1 = trunc_to_int(y1), l2 = trunc_to_int(y2), l3 = trunc_to_int(y3);
+		hash.add(l0);
+		hash.add(l1);
+		hash.add(l2);
+		hash.add(l3);
+		if ((l0 > hi || l0 < lo) && (int)(l0 > hi) != last_bit) edge(cb, l0);
+		if ((l1 > hi || l1 < lo) && (int)(l1 > hi) != last_bit) edge(cb + 1, l1);
+		if ((l2 > hi || l2 < lo) && (int)(l2 > hi) != last_bit) edge(cb + 2, l2);
+		if ((l3 > hi || l3 < lo) && (int)(l3 > hi) != last_bit) edge(cb + 3, l3);
+#ifdef TFR_WIN_PROFILE
+		pf_fast++; pf_cfast += clock64() - pg0;
+#endif
+		continue;
 	}
 #pragma unroll 1
 	for (int kk = 0; kk < 4; kk++) {
@@ -631,47 +691,31 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		const int ld = trunc_to_int(y);
 		hash.add(ld);
 		if (bitcnt < 10) {
-			if (ld > dmax) dmax = (7 * dmax + ld) / 8;
-			if (ld < dmin) dmin = (7 * dmin + ld) / 8;
-			offset = (dmax + dmin) / 2;
+			if (ld > dmax || ld < dmin) {
+				// the levels are pure functions of dmax/dmin (tfa2.cpp:366-368, 380-381): recompute them only when one moved
+				if (ld > dmax) dmax = (7 * dmax + ld) / 8;
+				if (ld < dmin) dmin = (7 * dmin + ld) / 8;
+				offset = (dmax + dmin) / 2;
+				noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+				hi = noffset + dmax / 32;
+				lo = noffset + dmin / 32;
+			}
 			if (bitcnt > 4) {
 				const uint32_t cw = c.dec[m];
 				const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
 				const uint32_t sum = (uint32_t)rssi + (uint32_t)(i * i) + (uint32_t)(q * q);
 				rssi = (int)((uint32_t)rssi + (uint32_t)((int)sum / 100));
 			}
-			noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
-			hi = noffset + dmax / 32;
-			lo = noffset + dmin / 32;
 		}
-		const int bit = ld > hi ? 1 : 0;
-		if ((ld > hi || ld < lo) && bit != last_bit) {
-			if (far && !have_edge) {
-				// speculated: index > last_bit_idx+8, tdiff >= 32*spb  ->  bitcnt++, no bits, re-arm
-				rec.first_edge = index;
-				rec.first_edge_block = (int)(m >> 13);
-				rec.flags |= kRecEdge;
-				bitcnt++;
-				lbi = index;
-			} else {
-				if (index > lbi + 8) {
-					bitcnt++;
-					const int tdiff = index - lbi;
-					if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
-						const int bit_diff = tdiff / 2;
-						const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
-						if (numbits < 32)
-							for (int n = 1; n < numbits; n++) tfa2_bit(s, last_bit);
-						tfa2_bit(s, bit);
-						last_bit = bit;
-					}
-				}
-				if (index - lbi > 2) lbi = index;
-			}
-			have_edge = true;
-		}
+		if ((ld > hi || ld < lo) && (int)(ld > hi) != last_bit) edge(m, ld);
 	}
+#ifdef TFR_WIN_PROFILE
+	pf_gen++; pf_cgen += clock64() - pg0;
+#endif
 	}
+#ifdef TFR_WIN_PROFILE
+	atomicAdd(&g_slprof[0], (unsigned long long)pf_fast); atomicAdd(&g_slprof[1], (unsigned long long)pf_gen); atomicAdd(&g_slprof[2], (unsigned long long)pf_cfast); atomicAdd(&g_slprof[3], (unsigned long long)pf_cgen); atomicAdd(&g_slprof[4], (unsigned long long)(clock64() - pf_t0)); atomicAdd(&g_slprof[5], 1ull);
+#endif
 	s.lp = lp;
 	s.bitcnt = bitcnt; s.dmin = dmin; s.dmax = dmax; s.offset = offset; s.last_bit = last_bit; s.rssi_i = rssi;
 	s.last_bit_idx = lbi;
@@ -1245,9 +1289,13 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 		unsigned long long z[16] = { 0 }, r[16];
 		cudaStreamSynchronize(s);
 		cudaMemcpyToSymbol(g_winprof, z, sizeof(z));
+		cudaMemcpyToSymbol(g_slprof, z, 8 * sizeof(unsigned long long));
 		win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
 		cudaStreamSynchronize(s);
 		cudaMemcpyFromSymbol(r, g_winprof, sizeof(r));
+		unsigned long long q[8];
+		cudaMemcpyFromSymbol(q, g_slprof, sizeof(q));
+		fprintf(stderr, "[slprof] all tfa2 windows (%llu): %llu fast groups (%.0f cyc each), %llu general groups (%.0f cyc each), %.0f cyc per window\n", q[5], q[0], (double)q[2] / (q[0] + 1), q[1], (double)q[3] / (q[1] + 1), (double)q[4] / (q[5] + 1));
 		for (int k = 0; k < 4; k++)
 			fprintf(stderr, "[winprof] kind %d: max warm-up %llu cyc, max slicer %llu cyc over max %llu steps, max thread %llu cyc\n", k, r[k], r[4 + k], r[8 + k], r[12 + k]);
 		return cudaGetLastError();
