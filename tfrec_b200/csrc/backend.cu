@@ -72,95 +72,200 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 	const double spb12 = __dmul_rn(cfg.spb, 0.5);
 	const int spb34 = (int)floor(__dmul_rn(cfg.spb, 0.75));   // (double)tdiff > 0.75*spb  <=>  tdiff > floor(0.75*spb)
 
-	auto load = [&](uint32_t m, uint32_t last, uint32_t &cw, uint32_t &lw) {
+	// per step: what the lanes prepare in parallel for the two serial recurrences, and what those produce
+	__shared__ double s_t2[32], s_u[32], s_y[32], s_t2s[32], s_us[32], s_a[32];
+	const size_t tbase = ((size_t)stream * kMaxDemods + demod) * (size_t)p.tap_cap;
+
+	// ---- the stream's samples as a flat sequence of steps of <= 32 samples (a window is cut into equal steps, so
+	// that a 513-sample window gives 17 steps of 30..31 samples and not 16 full ones plus one of a single sample)
+	struct Step {
+		uint32_t m0, last;    // first sample, last sample of the window inside this call
+		int cnt;              // 0: no more steps
+		uint32_t win_end;     // WinEntry::end
+		bool first, final;    // first / last step of its window
+		bool cont;            // the window was already open when the call began
+	};
+	uint32_t g_wi = 0, g_pos = 0, g_last = 0, g_size = 0, g_end = 0;
+	bool g_open = false, g_cont = false;
+	auto next_step = [&]() -> Step {
+		Step q;
+		q.cnt = 0;
+		q.m0 = q.last = q.win_end = 0;
+		q.first = q.final = q.cont = false;
+		if (!g_open) {
+			if (g_wi >= n_win) return q;
+			const WinEntry e = wl[g_wi];
+			if (e.start >= call_len) { g_wi = n_win; return q; }
+			g_pos = e.start;
+			g_end = e.end;
+			g_last = min(e.end, call_len - 1);
+			const uint32_t len = g_last - e.start + 1;
+			g_size = (len + ((len + 31) / 32) - 1) / ((len + 31) / 32);
+			g_cont = (e.flags & kWinCont) != 0;
+			g_open = true;
+			q.first = true;
+		}
+		q.m0 = g_pos;
+		q.last = g_last;
+		q.win_end = g_end;
+		q.cont = g_cont;
+		q.cnt = (int)min(g_size, g_last - g_pos + 1);
+		g_pos += (uint32_t)q.cnt;
+		if (g_pos > g_last) {
+			q.final = true;
+			g_open = false;
+			g_wi++;
+		}
+		return q;
+	};
+	auto load = [&](const Step &q, uint32_t &cw, uint32_t &lw) {
 		cw = lw = 0;
-		if (m <= last) {
+		const uint32_t m = q.m0 + (uint32_t)lane;
+		if (lane < q.cnt) {
 			cw = dec[m];
 			lw = (m == 0) ? prev_last : dec[m - 1];
 		}
 	};
-
-	// per 32-sample step: what the lanes prepare in parallel for the serial part
-	__shared__ double s_t2[32], s_u[32], s_d[32], s_y[32], s_t2s[32], s_us[32], s_x[32], s_a[32];
-	__shared__ int s_pw[32];
-	const size_t tbase = ((size_t)stream * kMaxDemods + demod) * (size_t)p.tap_cap;
-
-	for (uint32_t wi = 0; wi < n_win; wi++) {
-		const WinEntry e = wl[wi];
-		if (e.start >= call_len) break;
-		const uint32_t last = min(e.end, call_len - 1);
-		if (!(e.flags & kWinCont)) {   // whb.cpp:636-642: a trigger with the timeout expired starts a new window
-			w.s.offset = 0;
-			w.s.bitcnt = 0;
-			rssi = 0.0;
-			step = 0;
-			last_peak = 0;
+	auto phase_change = [&](int tdiff) {
+		// one 0, then a 1 for every further bit period since the last one (whb.cpp:662-674)
+		whb_bit(w.s, 0);
+		w.s.bitcnt++;
+		const int bit0 = __double2int_rz(__ddiv_rn(__dadd_rn((double)tdiff, spb12), cfg.spb));
+		for (int n = 1; n < bit0; n++) {
+			whb_bit(w.s, 1);
+			w.s.bitcnt++;
 		}
-		uint32_t cw, lw, cw_nx, lw_nx;
-		load(e.start + lane, last, cw, lw);
-		for (uint32_t m0 = e.start; m0 <= last; m0 += 32) {
-			load(m0 + 32 + lane, last, cw_nx, lw_nx);
-			const int cnt = (int)min(32u, last - m0 + 1);
-			{
-				// the pulse filter's input-only terms, with the reference's roundings (iir2::step as built:
-				// ((b2*dn2 + a1*yn1) + (b0*dn + b1*dn1)) + a2*yn2): u = b2*dn2 and t2 = b0*dn + b1*dn1
-				const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
-				const int cr = fm_dev_nrzs(i, q, (int)(int16_t)(lw & 0xffff), (int)(int16_t)(lw >> 16));
-				const double d = (double)cr;
-				double d1 = __shfl_up_sync(0xffffffffu, d, 1), d2 = __shfl_up_sync(0xffffffffu, d, 2);
-				if (lane == 0) { d1 = lp.d1; d2 = lp.d2; }
-				if (lane == 1) d2 = lp.d1;
-				s_t2[lane] = __dadd_rn(__dmul_rn(kp.b0, d), __dmul_rn(kp.b1, d1));
-				s_u[lane] = __dmul_rn(kp.b2, d2);
-				s_d[lane] = d;
-				s_pw[lane] = i * i + q * q;
-				if (taps) {
-					const uint32_t ti = w.tap_n[1] + (uint32_t)lane;
-					if (lane < cnt && ti < p.tap_cap) p.tap_i32[1][tbase + ti] = cr;
-				}
+	};
+
+	// Software pipeline over the steps.  Iteration i runs, side by side in ONE serial loop, the pulse filter's
+	// recurrence for step i+1 (stage A, it never depends on the framer) and the averaging filter's recurrence for
+	// step i (stage B); the parallel phases before and after belong to both.  Per-lane registers carry step i's
+	// discriminator outputs from stage A to stage B.
+	Step cur = next_step(), nxt;
+	uint32_t cw, lw;
+	int dev_c = 0, pw_c = 0;       // stage A results of `cur` for this lane's sample
+	double x_c = 0.0, y_c = 0.0;
+	// stage A of the very first step, alone
+	auto stage_a_prepare = [&](const Step &q, uint32_t cwv, uint32_t lwv, int &cr, int &pw) {
+		const int i = (int)(int16_t)(cwv & 0xffff), qq = (int)(int16_t)(cwv >> 16);
+		cr = fm_dev_nrzs(i, qq, (int)(int16_t)(lwv & 0xffff), (int)(int16_t)(lwv >> 16));
+		pw = i * i + qq * qq;
+		// the pulse filter's input-only terms, with the reference's roundings (iir2::step as built:
+		// ((b2*dn2 + a1*yn1) + (b0*dn + b1*dn1)) + a2*yn2): u = b2*dn2 and t2 = b0*dn + b1*dn1
+		const double d = (double)cr;
+		double d1 = __shfl_up_sync(0xffffffffu, d, 1), d2 = __shfl_up_sync(0xffffffffu, d, 2);
+		if (lane == 0) { d1 = lp.d1; d2 = lp.d2; }
+		if (lane == 1) d2 = lp.d1;
+		s_t2[lane] = __dadd_rn(__dmul_rn(kp.b0, d), __dmul_rn(kp.b1, d1));
+		s_u[lane] = __dmul_rn(kp.b2, d2);
+		// the filter's input history after this step
+		const double dl = __shfl_sync(0xffffffffu, d, q.cnt - 1), dl2 = __shfl_sync(0xffffffffu, d, max(q.cnt - 2, 0));
+		lp.d2 = (q.cnt >= 2) ? dl2 : lp.d1;
+		lp.d1 = dl;
+		if (taps) {
+			const uint32_t ti = w.tap_n[1] + (uint32_t)lane;
+			if (lane < q.cnt && ti < p.tap_cap) p.tap_i32[1][tbase + ti] = cr;
+			w.tap_n[1] += (uint32_t)q.cnt;
+		}
+	};
+	auto stage_a_finish = [&](int pw, int &dev, double &x, double &y, int &pwo) {
+		y = s_y[lane];
+		dev = trunc_to_int(y);
+		x = __dmul_rn(0.5, int_to_double(dev));
+		pwo = pw;
+	};
+	if (cur.cnt) {
+		load(cur, cw, lw);
+		int cr, pw;
+		stage_a_prepare(cur, cw, lw, cr, pw);
+		__syncwarp();
+		double y0 = lp.y0, y1 = lp.y1;
+		for (int k = 0; k < cur.cnt; k++) {
+			const double y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[k], __dmul_rn(kp.a1, y0)), s_t2[k]), __dmul_rn(kp.a2, y1));
+			s_y[k] = y;
+			y1 = y0;
+			y0 = y;
+		}
+		lp.y0 = y0;
+		lp.y1 = y1;
+		__syncwarp();
+		stage_a_finish(pw, dev_c, x_c, y_c, pw_c);
+		__syncwarp();
+		nxt = next_step();
+		load(nxt, cw, lw);
+	}
+	while (cur.cnt) {
+		// ---- parallel prelude: stage A of nxt (inputs), stage B of cur (the averaging filter's input-only terms)
+		int cr_n = 0, pw_n = 0;
+		if (nxt.cnt) stage_a_prepare(nxt, cw, lw, cr_n, pw_n);
+		const bool run_b = !synced;
+		if (run_b) {
+			double x1 = __shfl_up_sync(0xffffffffu, x_c, 1), x2 = __shfl_up_sync(0xffffffffu, x_c, 2);
+			if (lane == 0) { x1 = la.d1; x2 = la.d2; }
+			if (lane == 1) x2 = la.d1;
+			s_t2s[lane] = __dadd_rn(__dmul_rn(ka.b0, x_c), __dmul_rn(ka.b1, x1));
+			s_us[lane] = __dmul_rn(ka.b2, x2);
+		}
+		__syncwarp();
+		// the loads of the step after next are in flight during the serial loop
+		const Step nn = nxt.cnt ? next_step() : nxt;
+		uint32_t cw2 = 0, lw2 = 0;
+		if (nn.cnt) load(nn, cw2, lw2);
+		// ---- serial: the two recurrences side by side (four dependent FP64 operations per sample each; the
+		// shared-memory operands are fetched two samples ahead)
+		double ya0 = la.y0, ya1 = la.y1;
+		{
+			double yp0 = lp.y0, yp1 = lp.y1;
+			const int na = nxt.cnt, nb = run_b ? cur.cnt : 0;
+			const int nboth = min(na, nb);
+			int k = 0;
+			double ua = s_u[0], ta = s_t2[0], ub = s_u[1], tb = s_t2[1];
+			double va = s_us[0], wa = s_t2s[0], vb = s_us[1], wb = s_t2s[1];
+#pragma unroll 4
+			for (; k < nboth; k++) {
+				const int kn = min(k + 2, 31);
+				const double un = s_u[kn], tn = s_t2[kn], vn = s_us[kn], wn = s_t2s[kn];
+				const double y = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(kp.a1, yp0)), ta), __dmul_rn(kp.a2, yp1));
+				const double a = __dadd_rn(__dadd_rn(__dadd_rn(va, __dmul_rn(ka.a1, ya0)), wa), __dmul_rn(ka.a2, ya1));
+				s_y[k] = y;
+				s_a[k] = a;
+				yp1 = yp0; yp0 = y;
+				ya1 = ya0; ya0 = a;
+				ua = ub; ta = tb; ub = un; tb = tn;
+				va = vb; wa = wb; vb = vn; wb = wn;
 			}
-			if (taps) w.tap_n[1] += (uint32_t)cnt;
-			__syncwarp();
-			// ---- phase 1 (serial): the pulse filter's recurrence alone - four dependent FP64 operations per sample,
-			// nothing else on the chain.  All lanes run it redundantly (uniform), results go to shared memory.
-			{
-				// (the shared-memory operands are fetched three samples ahead: an LDS in front of its use would put
-				// ~30 cycles on top of the 4 x 8-cycle FP64 chain of every sample)
-				double y0 = lp.y0, y1 = lp.y1;
-				double ua = s_u[0], ta = s_t2[0], ub = s_u[1], tb = s_t2[1], uc = s_u[2], tc = s_t2[2];
-#pragma unroll 8
-				for (int k = 0; k < cnt; k++) {
-					const int kn = min(k + 3, 31);
-					const double un = s_u[kn], tn = s_t2[kn];
-					const double y = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(kp.a1, y0)), ta), __dmul_rn(kp.a2, y1));
-					s_y[k] = y;
-					y1 = y0;
-					y0 = y;
-					ua = ub; ta = tb; ub = uc; tb = tc; uc = un; tc = tn;
-				}
-				lp.y0 = y0;
-				lp.y1 = y1;
+			for (; k < na; k++) {
+				const double y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[k], __dmul_rn(kp.a1, yp0)), s_t2[k]), __dmul_rn(kp.a2, yp1));
+				s_y[k] = y;
+				yp1 = yp0; yp0 = y;
 			}
-			__syncwarp();
-			// ---- phase 2 (parallel, lane = sample): truncate, compare with the previous sample, and - while no frame
-			// is in progress - the averaging filter's input-only terms
-			const int dev = trunc_to_int(s_y[lane]);
+			for (; k < nb; k++) {
+				const double a = __dadd_rn(__dadd_rn(__dadd_rn(s_us[k], __dmul_rn(ka.a1, ya0)), s_t2s[k]), __dmul_rn(ka.a2, ya1));
+				s_a[k] = a;
+				ya1 = ya0; ya0 = a;
+			}
+			lp.y0 = yp0;
+			lp.y1 = yp1;
+		}
+		__syncwarp();
+		// ---- parallel + rare serial: stage B of cur
+		{
+			const Step &q = cur;
+			const int cnt = q.cnt;
+			if (q.first && !q.cont) {   // whb.cpp:636-642: a trigger with the timeout expired starts a new window
+				w.s.offset = 0;
+				w.s.bitcnt = 0;
+				rssi = 0.0;
+				step = 0;
+				last_peak = 0;
+			}
+			const int dev = dev_c;
 			int dev_prev = __shfl_up_sync(0xffffffffu, dev, 1);
 			if (lane == 0) dev_prev = last_dev;
 			const bool rising = lane < cnt && dev > dev_prev;
 			const uint32_t step0 = step;
-			auto phase_change = [&](int tdiff) {
-				// one 0, then a 1 for every further bit period since the last one (whb.cpp:662-674)
-				whb_bit(w.s, 0);
-				w.s.bitcnt++;
-				const int bit0 = __double2int_rz(__ddiv_rn(__dadd_rn((double)tdiff, spb12), cfg.spb));
-				for (int n = 1; n < bit0; n++) {
-					whb_bit(w.s, 1);
-					w.s.bitcnt++;
-				}
-			};
-			// dip decisions over a candidate mask, in sample order (only last_peak chains them); returns the sample on
-			// which the sync word completed, or -1
+			// dip decisions over a candidate mask, in sample order (only last_peak chains them); returns the sample
+			// on which the sync word completed, or -1
 			auto decide = [&](unsigned cm, bool stop_at_sync) -> int {
 				while (cm) {
 					const int k = __ffs(cm) - 1;
@@ -177,64 +282,44 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 			// a frame is being received from sample k0 on (whb.cpp:653,677,693): avg_of frozen, rssi accumulating
 			auto frame_part = [&](int k0) {
 				decide(__ballot_sync(0xffffffffu, rising && lane >= k0 && dev < avg_of), false);
-				long long pw = (lane >= k0 && lane < cnt) ? (long long)s_pw[lane] : 0ll;
+				long long pw = (lane >= k0 && lane < cnt) ? (long long)pw_c : 0ll;
 				for (int o = 16; o; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
 				rssi = __dadd_rn(rssi, (double)pw);   // sums of I^2+Q^2 stay far below 2^53: every partial sum is exact
 				if (taps) {
 					const uint32_t ti = w.tap_n[2] + (uint32_t)(lane - k0);
-					if (lane >= k0 && lane < cnt && ti < p.tap_cap) p.tap_f64[tbase + ti] = s_y[lane];
+					if (lane >= k0 && lane < cnt && ti < p.tap_cap) p.tap_f64[tbase + ti] = y_c;
 					w.tap_n[2] += (uint32_t)(cnt - k0);
 				}
 			};
-			if (!synced) {
-				const double x = __dmul_rn(0.5, int_to_double(dev));
-				double x1 = __shfl_up_sync(0xffffffffu, x, 1), x2 = __shfl_up_sync(0xffffffffu, x, 2);
-				if (lane == 0) { x1 = la.d1; x2 = la.d2; }
-				if (lane == 1) x2 = la.d1;
-				s_t2s[lane] = __dadd_rn(__dmul_rn(ka.b0, x), __dmul_rn(ka.b1, x1));
-				s_us[lane] = __dmul_rn(ka.b2, x2);
-				s_x[lane] = x;
-				__syncwarp();
-				// ---- phase 3 (serial): the averaging filter's recurrence
-				double y0 = la.y0, y1 = la.y1;
-				double ua = s_us[0], ta = s_t2s[0], ub = s_us[1], tb = s_t2s[1], uc = s_us[2], tc = s_t2s[2];
-#pragma unroll 8
-				for (int k = 0; k < cnt; k++) {
-					const int kn = min(k + 3, 31);
-					const double un = s_us[kn], tn = s_t2s[kn];
-					const double a = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(ka.a1, y0)), ta), __dmul_rn(ka.a2, y1));
-					s_a[k] = a;
-					y1 = y0;
-					y0 = a;
-					ua = ub; ta = tb; ub = uc; tb = tc; uc = un; tc = tn;
-				}
-				__syncwarp();
-				// ---- phase 4 (parallel) + 5 (the rare dips, in order)
-				const int avg = trunc_to_int(s_a[lane]);
+			if (run_b) {
+				const double a_l = s_a[lane];
+				const int avg = trunc_to_int(a_l);
 				if (taps) {
 					const uint32_t ti = w.tap_n[2] + 2u * (uint32_t)lane;
 					if (lane < cnt && ti + 1 < p.tap_cap) {
-						p.tap_f64[tbase + ti] = s_y[lane];
-						p.tap_f64[tbase + ti + 1] = s_a[lane];
+						p.tap_f64[tbase + ti] = y_c;
+						p.tap_f64[tbase + ti + 1] = a_l;
 					}
 				}
 				const int ks = decide(__ballot_sync(0xffffffffu, rising && dev < avg), true);
 				if (ks < 0) {
-					la.d2 = (cnt >= 2) ? s_x[cnt - 2] : la.d1;
-					la.d1 = s_x[cnt - 1];
-					la.y0 = y0;
-					la.y1 = y1;
+					const double xl = __shfl_sync(0xffffffffu, x_c, cnt - 1), xl2 = __shfl_sync(0xffffffffu, x_c, max(cnt - 2, 0));
+					la.d2 = (cnt >= 2) ? xl2 : la.d1;
+					la.d1 = xl;
+					la.y0 = ya0;
+					la.y1 = ya1;
 					avg_of = __shfl_sync(0xffffffffu, avg, cnt - 1);
 					if (taps) w.tap_n[2] += 2u * (uint32_t)cnt;
 				} else {
 					// the sync word completed on sample ks: the averaging filter stops there, the rest of the step is frame
+					const double xs = __shfl_sync(0xffffffffu, x_c, ks), xs1 = __shfl_sync(0xffffffffu, x_c, max(ks - 1, 0));
 					la.y1 = (ks >= 1) ? s_a[ks - 1] : la.y0;
 					la.y0 = s_a[ks];
-					la.d2 = (ks >= 1) ? s_x[ks - 1] : la.d1;
-					la.d1 = s_x[ks];
+					la.d2 = (ks >= 1) ? xs1 : la.d1;
+					la.d1 = xs;
 					avg_of = __shfl_sync(0xffffffffu, avg, ks);
 					synced = 1;
-					rssi = __dadd_rn(rssi, (double)s_pw[ks]);
+					rssi = __dadd_rn(rssi, (double)__shfl_sync(0xffffffffu, pw_c, ks));
 					if (taps) w.tap_n[2] += 2u * (uint32_t)(ks + 1);
 					frame_part(ks + 1);
 				}
@@ -243,37 +328,35 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 			}
 			last_dev = __shfl_sync(0xffffffffu, dev, cnt - 1);
 			step += (uint32_t)cnt;
-			// the filter's input history after this step
-			if (cnt >= 2) {
-				lp.d1 = s_d[cnt - 1];
-				lp.d2 = s_d[cnt - 2];
-			} else {
-				lp.d2 = lp.d1;
-				lp.d1 = s_d[0];
+			if (q.final) {
+				if (q.last == q.win_end) {
+					// the timeout ran out on this sample (whb.cpp:691-700)
+					if (synced) {
+						for (int n = 0; n < 16; n++) whb_bit(w.s, 0);
+						w.s.rssi_d = rssi;
+						w.pos = base_pos + q.win_end;
+						if (lane == 0) whb_flush(w);
+						else { w.s.sr_cnt = -1; w.s.sr = 0; w.s.byte_cnt = 0; w.s.synced = 0; }
+						synced = 0;
+					}
+					w.s.offset = 0;
+					w.s.bitcnt = 0;
+					rssi = 0.0;
+					step = 0;
+					last_peak = 0;
+					w.s.timeout_cnt = 0;
+				} else {
+					w.s.timeout_cnt = (int)(q.win_end - q.last);
+				}
 			}
-			__syncwarp();
-			cw = cw_nx;
-			lw = lw_nx;
 		}
-		if (last == e.end) {
-			// the timeout ran out on this sample (whb.cpp:691-700)
-			if (synced) {
-				for (int n = 0; n < 16; n++) whb_bit(w.s, 0);
-				w.s.rssi_d = rssi;
-				w.pos = base_pos + e.end;
-				if (lane == 0) whb_flush(w);
-				else { w.s.sr_cnt = -1; w.s.sr = 0; w.s.byte_cnt = 0; w.s.synced = 0; }
-				synced = 0;
-			}
-			w.s.offset = 0;
-			w.s.bitcnt = 0;
-			rssi = 0.0;
-			step = 0;
-			last_peak = 0;
-			w.s.timeout_cnt = 0;
-		} else {
-			w.s.timeout_cnt = (int)(e.end - last);
-		}
+		// ---- stage A of nxt: truncate; it becomes cur
+		if (nxt.cnt) stage_a_finish(pw_n, dev_c, x_c, y_c, pw_c);
+		__syncwarp();
+		cur = nxt;
+		nxt = nn;
+		cw = cw2;
+		lw = lw2;
 	}
 	if (lane != 0) return;
 	w.s.lp = lp;
