@@ -101,6 +101,7 @@ struct tfr_handle {
 	int cur = 0;                       // slot of the most recent tfr_process
 	cudaStream_t stream_be = nullptr;  // back-end stream
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
+	cudaStream_t stream_fe2 = nullptr;    // odd front-end chunks: consecutive chunk launches overlap their tails
 	cudaEvent_t chunk_ev[8] = { nullptr };
 	cudaEvent_t walk_ev = nullptr;
 	bool pipelined = true;             // false: the back-end of a call finishes before the next call starts (taps)
@@ -214,6 +215,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->span1) cudaEventDestroy(h->span1);
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
 	if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
+	if (h->stream_fe2) cudaStreamDestroy(h->stream_fe2);
 	for (auto e : h->chunk_ev) if (e) cudaEventDestroy(e);
 	if (h->walk_ev) cudaEventDestroy(h->walk_ev);
 	if (h->stream) cudaStreamDestroy(h->stream);
@@ -267,6 +269,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	// call from 4.35 to 4.0 ms but stretches the issue-bound front-end kernel from 1.9 to 3.15 ms
 	CUH(cudaStreamCreateWithFlags(&h->stream_be, cudaStreamNonBlocking));
 	CUH(cudaStreamCreateWithFlags(&h->stream_walk, cudaStreamNonBlocking));
+	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	CUH(cudaEventCreateWithFlags(&h->walk_ev, cudaEventDisableTiming));
 	h->pipelined = !(cfg->flags & TFR_FLAG_TAPS);   // the tap buffers are not slotted
@@ -315,6 +318,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 static int sync_all(tfr_handle *h)
 {
 	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaStreamSynchronize(h->stream_fe2));
 	CU(cudaStreamSynchronize(h->stream_walk));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
@@ -526,17 +530,24 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		const int n_chunks = (int)std::min<size_t>(kFrontChunks, std::max<size_t>(1, total / 8192));
 		const int per = (int)((max_blocks + n_chunks - 1) / n_chunks);
 		CU(cudaStreamWaitEvent(h->stream_walk, sl.fe0, 0));   // the walk stream starts after everything queued so far
+		CU(cudaStreamWaitEvent(h->stream_fe2, sl.fe0, 0));
+		int last_odd = -1;
 		for (int k = 0; k < n_chunks; k++) {
 			fp.tile0 = k * per;
 			fp.n_tiles = std::min(per, (int)max_blocks - fp.tile0);
 			if (fp.n_tiles <= 0) break;
-			CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
-			CU(cudaEventRecord(h->chunk_ev[k], sf));
+			// the chunks are independent of each other: alternating two streams lets chunk k+1's first CTAs fill the
+			// SMs that chunk k's last wave leaves idle
+			cudaStream_t sk = (k & 1) ? h->stream_fe2 : sf;
+			CU(launch_frontend(fp, ns, h->dcfg.filter, sk));
+			CU(cudaEventRecord(h->chunk_ev[k], sk));
+			if (k & 1) last_odd = k;
 			CU(cudaStreamWaitEvent(h->stream_walk, h->chunk_ev[k], 0));
 			bp.n_tiles = fp.n_tiles;
 			CU(launch_thresh2(bp, h->stream_walk));
 			h->stats.kernel_launches += 2;
 		}
+		if (last_odd >= 0) CU(cudaStreamWaitEvent(sf, h->chunk_ev[last_odd], 0));
 		CU(cudaEventRecord(sl.fe1, sf));
 		CU(cudaEventRecord(h->walk_ev, h->stream_walk));
 		CU(cudaStreamWaitEvent(sf, h->walk_ev, 0));   // rejoin: everything after this on the front stream sees the walk
