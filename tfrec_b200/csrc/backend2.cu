@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 		last_trig = t;
 	};
 
-	// lane L's block of a chunk: event count and the first eight events
-	auto fetch = [&](int chunk, uint32_t &n, uint4 &ea, uint4 &eb) {
+	// lane L's block of a chunk: event count and the first sixteen events (a block holds 5-10 events above the
+	// speculative bound; a list that does not fit the registers costs one dependent L2 round trip per four events
+	// on the stream's serial chain)
+	auto fetch = [&](int chunk, uint32_t &n, uint4 &ea, uint4 &eb, uint4 &ec, uint4 &ed) {
 		n = 0;
-		ea = eb = make_uint4(0, 0, 0, 0);
+		ea = eb = ec = ed = make_uint4(0, 0, 0, 0);
 		const int b = chunk + lane;
 		if (b >= b0 && b < t_end) {
 			const size_t g = (size_t)job.dec_off + b;
@@ -133,17 +135,19 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 			const uint4 *ev = reinterpret_cast<const uint4 *>(p.events + g * kMaxEvt);
 			ea = ev[0];
 			eb = ev[1];
+			ec = ev[2];
+			ed = ev[3];
 		}
 	};
 
 	bool stop = false;
 	int chunk = b0 & ~31;
 	uint32_t n, n_nx;
-	uint4 ea, eb, ea_nx, eb_nx;
-	fetch(chunk, n, ea, eb);
+	uint4 ea, eb, ec, ed, ea_nx, eb_nx, ec_nx, ed_nx;
+	fetch(chunk, n, ea, eb, ec, ed);
 	int pos = b0;
 	while (pos < t_end && !stop) {
-		fetch(chunk + 32, n_nx, ea_nx, eb_nx);   // in flight while this chunk is walked
+		fetch(chunk + 32, n_nx, ea_nx, eb_nx, ec_nx, ed_nx);   // in flight while this chunk is walked
 		const int jend = min(32, t_end - chunk);
 		const size_t g = (size_t)job.dec_off + chunk + lane;
 		while (pos < chunk + jend && !stop) {
@@ -174,8 +178,24 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 				if (n > 5) own(eb.y);
 				if (n > 6) own(eb.z);
 				if (n > 7) own(eb.w);
-				const uint32_t *ev = p.events + g * kMaxEvt;
-				for (uint32_t j = 8; j < n; j++) own(ev[j]);
+				if (n > 8) {
+					own(ec.x);
+					if (n > 9) own(ec.y);
+					if (n > 10) own(ec.z);
+					if (n > 11) own(ec.w);
+					if (n > 12) own(ed.x);
+					if (n > 13) own(ed.y);
+					if (n > 14) own(ed.z);
+					if (n > 15) own(ed.w);
+					const uint4 *ev4 = reinterpret_cast<const uint4 *>(p.events + g * kMaxEvt);
+					for (uint32_t j = 16; j < n; j += 4) {
+						const uint4 q = ev4[j >> 2];
+						own(q.x);
+						if (j + 1 < n) own(q.y);
+						if (j + 2 < n) own(q.z);
+						if (j + 3 < n) own(q.w);
+					}
+				}
 			}
 			unsigned dense = __ballot_sync(0xffffffffu, active && n > (uint32_t)kMaxEvt);
 			while (dense) {
@@ -189,17 +209,28 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 				int df = -1, dl = -1, dcov = 0, dcnt = 0, dend = 0;
 				for (int sgi = 0; sgi < ns; sgi++) {
 					const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
-					for (int m0 = a; m0 < b; m0 += 32) {
-						const int m = m0 + lane;
-						const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(d[m]) > theta));
-						if (mask) {
-							const int pf = m0 + __ffs(mask) - 1, pl = m0 + 31 - __clz(mask);
-							if (df < 0) df = pf;
-							const int hi = min(pl + t_max, kBlockDec);   // triggers of one chunk are < 32 < t_max apart
-							dcov += max(hi - max(pf, dend), 0);
-							dend = hi;
-							dl = pl;
-							dcnt += __popc(mask);
+					for (int mb = a; mb < b; mb += 256) {
+						// eight loads per lane in flight: this scan sits on the stream's serial chain, one L2 round
+						// trip per 32 samples would cost ~0.1 ms per burst block
+						uint32_t v[8];
+#pragma unroll
+						for (int q = 0; q < 8; q++) {
+							const int m = mb + 32 * q + lane;
+							v[q] = (m < b) ? d[m] : 0u;
+						}
+#pragma unroll
+						for (int q = 0; q < 8; q++) {
+							const int m0 = mb + 32 * q, m = m0 + lane;
+							const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(v[q]) > theta));
+							if (mask) {
+								const int pf = m0 + __ffs(mask) - 1, pl = m0 + 31 - __clz(mask);
+								if (df < 0) df = pf;
+								const int hi = min(pl + t_max, kBlockDec);   // triggers of one chunk are < 32 < t_max apart
+								dcov += max(hi - max(pf, dend), 0);
+								dend = hi;
+								dl = pl;
+								dcnt += __popc(mask);
+							}
 						}
 					}
 				}
@@ -271,13 +302,22 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 					const int ns = td.n_seg;
 					for (int sgi = 0; sgi < ns; sgi++) {
 						const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
-						for (int m0 = a; m0 < b; m0 += 32) {
-							const int m = m0 + lane;
-							const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(d[m]) > theta));
-							if (mask) {
-								const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
-								win_trigger(base + m0 + pf);
-								if (pl != pf) last_trig = base + m0 + pl;   // < 32 apart: they only move the tail
+						for (int mb = a; mb < b; mb += 256) {
+							uint32_t v[8];
+#pragma unroll
+							for (int q = 0; q < 8; q++) {
+								const int m = mb + 32 * q + lane;
+								v[q] = (m < b) ? d[m] : 0u;
+							}
+#pragma unroll
+							for (int q = 0; q < 8; q++) {
+								const int m0 = mb + 32 * q, m = m0 + lane;
+								const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(v[q]) > theta));
+								if (mask) {
+									const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
+									win_trigger(base + m0 + pf);
+									if (pl != pf) last_trig = base + m0 + pl;   // < 32 apart: they only move the tail
+								}
 							}
 						}
 					}
@@ -293,6 +333,8 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 		n = n_nx;
 		ea = ea_nx;
 		eb = eb_nx;
+		ec = ec_nx;
+		ed = ed_nx;
 	}
 
 	const bool finished = (t_stop == (int)job.n_blocks);

@@ -104,6 +104,7 @@ struct tfr_handle {
 	cudaStream_t stream_fe2 = nullptr;    // odd front-end chunks: consecutive chunk launches overlap their tails
 	cudaEvent_t chunk_ev[8] = { nullptr };
 	cudaEvent_t walk_ev = nullptr;
+	cudaEvent_t dbg_ev[4] = { nullptr };   // TFR_DEBUG: walk end, back start, back end of the last call
 	bool pipelined = true;             // false: the back-end of a call finishes before the next call starts (taps)
 	cudaEvent_t span0 = nullptr, span1 = nullptr;   // first front-end start / last back-end end since the last tfr_sync
 	bool span_open = false;
@@ -218,6 +219,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->stream_fe2) cudaStreamDestroy(h->stream_fe2);
 	for (auto e : h->chunk_ev) if (e) cudaEventDestroy(e);
 	if (h->walk_ev) cudaEventDestroy(h->walk_ev);
+	for (auto e : h->dbg_ev) if (e) cudaEventDestroy(e);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 }
@@ -268,10 +270,15 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	// same priority as the front stream: measured on B200, a high-priority back-end stream shortens a pipelined
 	// call from 4.35 to 4.0 ms but stretches the issue-bound front-end kernel from 1.9 to 3.15 ms
 	CUH(cudaStreamCreateWithFlags(&h->stream_be, cudaStreamNonBlocking));
-	CUH(cudaStreamCreateWithFlags(&h->stream_walk, cudaStreamNonBlocking));
+	{   // the walk is 1 warp per stream on the call's critical path: its CTAs go first when an SM has room
+		int prio_lo = 0, prio_hi = 0;
+		CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CUH(cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi));
+	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	CUH(cudaEventCreateWithFlags(&h->walk_ev, cudaEventDisableTiming));
+	for (auto &e : h->dbg_ev) CUH(cudaEventCreate(&e));
 	h->pipelined = !(cfg->flags & TFR_FLAG_TAPS);   // the tap buffers are not slotted
 	CUH(cudaEventCreate(&h->span0));
 	CUH(cudaEventCreate(&h->span1));
@@ -550,6 +557,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		if (last_odd >= 0) CU(cudaStreamWaitEvent(sf, h->chunk_ev[last_odd], 0));
 		CU(cudaEventRecord(sl.fe1, sf));
 		CU(cudaEventRecord(h->walk_ev, h->stream_walk));
+		CU(cudaEventRecord(h->dbg_ev[0], h->stream_walk));
 		CU(cudaStreamWaitEvent(sf, h->walk_ev, 0));   // rejoin: everything after this on the front stream sees the walk
 		fp.tile0 = 0;
 		bp.n_tiles = (int)max_blocks;
@@ -589,6 +597,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 
 	// ---- back: demodulators over the windows, verifier, parsers - once per call, over all blocks
 	CU(cudaStreamWaitEvent(sb, sl.front_done, 0));
+	CU(cudaEventRecord(h->dbg_ev[1], sb));
 	bp.tile0 = 0;
 	bp.n_tiles = (int)max_blocks;
 	if (h->dcfg.n_demods) {
@@ -606,6 +615,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	CU(launch_parse(bp, sb));
 	h->stats.kernel_launches += 2;
 	CU(cudaEventRecord(sl.back_done, sb));
+	CU(cudaEventRecord(h->dbg_ev[2], sb));
 	CU(cudaEventRecord(h->span1, sb));
 	h->stats.blocks += total;
 	h->stats.raw_samples += total * (uint64_t)kBlockRaw;
@@ -639,6 +649,15 @@ extern "C" __attribute__((visibility("default"))) int tfr_sync(tfr_handle *h)
 		h->stats.last_backend_ms = all - fe;
 		h->stats.last_total_ms = tot;
 		h->span_open = false;
+		if (getenv("TFR_DEBUG")) {
+			float a = 0, b = 0, c = 0, d = 0;
+			cudaEventElapsedTime(&a, h->span0, h->slot[h->cur].fe1);
+			cudaEventElapsedTime(&b, h->span0, h->dbg_ev[0]);
+			cudaEventElapsedTime(&c, h->span0, h->dbg_ev[1]);
+			cudaEventElapsedTime(&d, h->span0, h->dbg_ev[2]);
+			cudaGetLastError();
+			fprintf(stderr, "[tfr] timeline of the last call (ms from its start): front-end done %.3f, walk done %.3f, back-end starts %.3f, ends %.3f\n", a, b, c, d);
+		}
 	}
 	if (h->h2d_timed) {
 		float a = 0;
