@@ -20,7 +20,7 @@
 namespace tfr {
 
 // ------------------------------------------------------------------------------------------------
-// whb_kernel: WeatherHub (whb.cpp:632-707), one warp per stream.
+// whb_kernel: WeatherHub (whb.cpp:632-707), one CTA of two warps per stream.
 //
 // WeatherHub cannot be cut into independent windows: its averaging biquad (0.0025/spb, whb.cpp:611) has a
 // time constant of ~5800 samples and is never reset, so avg_of at any sample depends on hundreds of earlier
@@ -35,10 +35,11 @@ namespace tfr {
 //     local memory is the reference's rdata[])
 // ------------------------------------------------------------------------------------------------
 template <bool TAPS>
-__global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
+__global__ void __launch_bounds__(64) whb_kernel(const BackParams p)
 {
 	const int stream = blockIdx.x;
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const int role = threadIdx.x >> 5;   // warp 0: pulse filter (stage A), warp 1: averaging filter, dips, framer (stage B)
 	if (stream >= p.n_streams) return;
 	int demod = -1;
 	for (int k = 0; k < p.cfg->n_demods; k++)
@@ -137,19 +138,17 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 		}
 	};
 
-	// Software pipeline over the steps.  Iteration i runs, side by side in ONE serial loop, the pulse filter's
-	// recurrence for step i+1 (stage A, it never depends on the framer) and the averaging filter's recurrence for
-	// step i (stage B); the parallel phases before and after belong to both.  Per-lane registers carry step i's
-	// discriminator outputs from stage A to stage B.
-	Step cur = next_step(), nxt;
-	uint32_t cw, lw;
-	int dev_c = 0, pw_c = 0;       // stage A results of `cur` for this lane's sample
-	double x_c = 0.0, y_c = 0.0;
-	// stage A of the very first step, alone
-	auto stage_a_prepare = [&](const Step &q, uint32_t cwv, uint32_t lwv, int &cr, int &pw) {
+	// Two warps, two pipeline stages.  In iteration i warp 0 runs stage A of step i+1 - loads, discriminator, the
+	// pulse filter's recurrence, truncation (it never depends on the framer) - while warp 1 runs stage B of step
+	// i: the averaging filter's recurrence, the dip decisions, framer and flush.  Stage A hands each sample's
+	// (dev, 0.5*dev, I^2+Q^2, y) over in a double-buffered shared array; one __syncthreads per step.
+	__shared__ int sb_dev[2][32], sb_pw[2][32];
+	__shared__ double sb_x[2][32], sb_y[2][32];
+	Step cur = next_step(), nxt = cur.cnt ? next_step() : cur;
+	uint32_t cw = 0, lw = 0;
+	auto stage_a = [&](const Step &q, uint32_t cwv, uint32_t lwv, int buf) {
 		const int i = (int)(int16_t)(cwv & 0xffff), qq = (int)(int16_t)(cwv >> 16);
-		cr = fm_dev_nrzs(i, qq, (int)(int16_t)(lwv & 0xffff), (int)(int16_t)(lwv >> 16));
-		pw = i * i + qq * qq;
+		const int cr = fm_dev_nrzs(i, qq, (int)(int16_t)(lwv & 0xffff), (int)(int16_t)(lwv >> 16));
 		// the pulse filter's input-only terms, with the reference's roundings (iir2::step as built:
 		// ((b2*dn2 + a1*yn1) + (b0*dn + b1*dn1)) + a2*yn2): u = b2*dn2 and t2 = b0*dn + b1*dn1
 		const double d = (double)cr;
@@ -167,91 +166,52 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 			if (lane < q.cnt && ti < p.tap_cap) p.tap_i32[1][tbase + ti] = cr;
 			w.tap_n[1] += (uint32_t)q.cnt;
 		}
-	};
-	auto stage_a_finish = [&](int pw, int &dev, double &x, double &y, int &pwo) {
-		y = s_y[lane];
-		dev = trunc_to_int(y);
-		x = __dmul_rn(0.5, int_to_double(dev));
-		pwo = pw;
-	};
-	if (cur.cnt) {
-		load(cur, cw, lw);
-		int cr, pw;
-		stage_a_prepare(cur, cw, lw, cr, pw);
 		__syncwarp();
+		// the recurrence: four dependent FP64 operations per sample, operands fetched two samples ahead
 		double y0 = lp.y0, y1 = lp.y1;
-		for (int k = 0; k < cur.cnt; k++) {
-			const double y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[k], __dmul_rn(kp.a1, y0)), s_t2[k]), __dmul_rn(kp.a2, y1));
+		double ua = s_u[0], ta = s_t2[0], ub = s_u[1], tb = s_t2[1];
+#pragma unroll 4
+		for (int k = 0; k < q.cnt; k++) {
+			const int kn = min(k + 2, 31);
+			const double un = s_u[kn], tn = s_t2[kn];
+			const double y = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(kp.a1, y0)), ta), __dmul_rn(kp.a2, y1));
 			s_y[k] = y;
 			y1 = y0;
 			y0 = y;
+			ua = ub; ta = tb; ub = un; tb = tn;
 		}
 		lp.y0 = y0;
 		lp.y1 = y1;
 		__syncwarp();
-		stage_a_finish(pw, dev_c, x_c, y_c, pw_c);
-		__syncwarp();
-		nxt = next_step();
-		load(nxt, cw, lw);
+		const double y = s_y[lane];
+		const int dev = trunc_to_int(y);
+		sb_dev[buf][lane] = dev;
+		sb_x[buf][lane] = __dmul_rn(0.5, int_to_double(dev));
+		sb_pw[buf][lane] = i * i + qq * qq;
+		if (taps) sb_y[buf][lane] = y;
+	};
+	if (role == 0 && cur.cnt) {
+		load(cur, cw, lw);
+		stage_a(cur, cw, lw, 0);
+		if (nxt.cnt) load(nxt, cw, lw);
 	}
-	while (cur.cnt) {
-		// ---- parallel prelude: stage A of nxt (inputs), stage B of cur (the averaging filter's input-only terms)
-		int cr_n = 0, pw_n = 0;
-		if (nxt.cnt) stage_a_prepare(nxt, cw, lw, cr_n, pw_n);
-		const bool run_b = !synced;
-		if (run_b) {
-			double x1 = __shfl_up_sync(0xffffffffu, x_c, 1), x2 = __shfl_up_sync(0xffffffffu, x_c, 2);
-			if (lane == 0) { x1 = la.d1; x2 = la.d2; }
-			if (lane == 1) x2 = la.d1;
-			s_t2s[lane] = __dadd_rn(__dmul_rn(ka.b0, x_c), __dmul_rn(ka.b1, x1));
-			s_us[lane] = __dmul_rn(ka.b2, x2);
-		}
-		__syncwarp();
-		// the loads of the step after next are in flight during the serial loop
-		const Step nn = nxt.cnt ? next_step() : nxt;
-		uint32_t cw2 = 0, lw2 = 0;
-		if (nn.cnt) load(nn, cw2, lw2);
-		// ---- serial: the two recurrences side by side (four dependent FP64 operations per sample each; the
-		// shared-memory operands are fetched two samples ahead)
-		double ya0 = la.y0, ya1 = la.y1;
-		{
-			double yp0 = lp.y0, yp1 = lp.y1;
-			const int na = nxt.cnt, nb = run_b ? cur.cnt : 0;
-			const int nboth = min(na, nb);
-			int k = 0;
-			double ua = s_u[0], ta = s_t2[0], ub = s_u[1], tb = s_t2[1];
-			double va = s_us[0], wa = s_t2s[0], vb = s_us[1], wb = s_t2s[1];
-#pragma unroll 4
-			for (; k < nboth; k++) {
-				const int kn = min(k + 2, 31);
-				const double un = s_u[kn], tn = s_t2[kn], vn = s_us[kn], wn = s_t2s[kn];
-				const double y = __dadd_rn(__dadd_rn(__dadd_rn(ua, __dmul_rn(kp.a1, yp0)), ta), __dmul_rn(kp.a2, yp1));
-				const double a = __dadd_rn(__dadd_rn(__dadd_rn(va, __dmul_rn(ka.a1, ya0)), wa), __dmul_rn(ka.a2, ya1));
-				s_y[k] = y;
-				s_a[k] = a;
-				yp1 = yp0; yp0 = y;
-				ya1 = ya0; ya0 = a;
-				ua = ub; ta = tb; ub = un; tb = tn;
-				va = vb; wa = wb; vb = vn; wb = wn;
+	__syncthreads();
+	for (int it = 0; cur.cnt; it++) {
+		const Step nn = nxt.cnt ? next_step() : nxt;   // both warps step the (deterministic) generator alike
+		if (role == 0) {
+			if (nxt.cnt) {
+				uint32_t cw2 = 0, lw2 = 0;
+				if (nn.cnt) load(nn, cw2, lw2);   // in flight during this step's recurrence
+				stage_a(nxt, cw, lw, (it + 1) & 1);
+				cw = cw2;
+				lw = lw2;
 			}
-			for (; k < na; k++) {
-				const double y = __dadd_rn(__dadd_rn(__dadd_rn(s_u[k], __dmul_rn(kp.a1, yp0)), s_t2[k]), __dmul_rn(kp.a2, yp1));
-				s_y[k] = y;
-				yp1 = yp0; yp0 = y;
-			}
-			for (; k < nb; k++) {
-				const double a = __dadd_rn(__dadd_rn(__dadd_rn(s_us[k], __dmul_rn(ka.a1, ya0)), s_t2s[k]), __dmul_rn(ka.a2, ya1));
-				s_a[k] = a;
-				ya1 = ya0; ya0 = a;
-			}
-			lp.y0 = yp0;
-			lp.y1 = yp1;
-		}
-		__syncwarp();
-		// ---- parallel + rare serial: stage B of cur
-		{
+		} else {
 			const Step &q = cur;
-			const int cnt = q.cnt;
+			const int cnt = q.cnt, buf = it & 1;
+			const int dev = sb_dev[buf][lane], pw_c = sb_pw[buf][lane];
+			const double x_c = sb_x[buf][lane];
+			const double y_c = taps ? sb_y[buf][lane] : 0.0;
 			if (q.first && !q.cont) {   // whb.cpp:636-642: a trigger with the timeout expired starts a new window
 				w.s.offset = 0;
 				w.s.bitcnt = 0;
@@ -259,7 +219,29 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 				step = 0;
 				last_peak = 0;
 			}
-			const int dev = dev_c;
+			const bool run_b = !synced;
+			double ya0 = la.y0, ya1 = la.y1;
+			if (run_b) {
+				// the averaging filter's input-only terms, then its recurrence
+				double x1 = __shfl_up_sync(0xffffffffu, x_c, 1), x2 = __shfl_up_sync(0xffffffffu, x_c, 2);
+				if (lane == 0) { x1 = la.d1; x2 = la.d2; }
+				if (lane == 1) x2 = la.d1;
+				s_t2s[lane] = __dadd_rn(__dmul_rn(ka.b0, x_c), __dmul_rn(ka.b1, x1));
+				s_us[lane] = __dmul_rn(ka.b2, x2);
+				__syncwarp();
+				double va = s_us[0], wa = s_t2s[0], vb = s_us[1], wb = s_t2s[1];
+#pragma unroll 4
+				for (int k = 0; k < cnt; k++) {
+					const int kn = min(k + 2, 31);
+					const double vn = s_us[kn], wn = s_t2s[kn];
+					const double a = __dadd_rn(__dadd_rn(__dadd_rn(va, __dmul_rn(ka.a1, ya0)), wa), __dmul_rn(ka.a2, ya1));
+					s_a[k] = a;
+					ya1 = ya0;
+					ya0 = a;
+					va = vb; wa = wb; vb = vn; wb = wn;
+				}
+				__syncwarp();
+			}
 			int dev_prev = __shfl_up_sync(0xffffffffu, dev, 1);
 			if (lane == 0) dev_prev = last_dev;
 			const bool rising = lane < cnt && dev > dev_prev;
@@ -350,26 +332,27 @@ __global__ void __launch_bounds__(32) whb_kernel(const BackParams p)
 				}
 			}
 		}
-		// ---- stage A of nxt: truncate; it becomes cur
-		if (nxt.cnt) stage_a_finish(pw_n, dev_c, x_c, y_c, pw_c);
-		__syncwarp();
+		__syncthreads();
 		cur = nxt;
 		nxt = nn;
-		cw = cw2;
-		lw = lw2;
 	}
-	if (lane != 0) return;
-	w.s.lp = lp;
-	w.s.lp_avg = la;
-	w.s.last_dev = last_dev;
-	w.s.avg_of = avg_of;
-	w.s.synced = synced;
-	w.s.step_lo = step;
-	w.s.last_peak = last_peak;
-	w.s.rssi_d = rssi;
-	st->d[demod] = w.s;
-	if (p.tap_cap)
-		for (int k = 0; k < 3; k++) p.tap_cnt[((size_t)stream * kMaxDemods + demod) * 3 + k] = w.tap_n[k];
+	// the carried state: warp 1 owns everything but the pulse filter
+	if (role == 1 && lane == 0) {
+		w.s.lp_avg = la;
+		w.s.last_dev = last_dev;
+		w.s.avg_of = avg_of;
+		w.s.synced = synced;
+		w.s.step_lo = step;
+		w.s.last_peak = last_peak;
+		w.s.rssi_d = rssi;
+		st->d[demod] = w.s;
+		if (p.tap_cap) p.tap_cnt[((size_t)stream * kMaxDemods + demod) * 3 + 2] = w.tap_n[2];
+	}
+	__syncthreads();
+	if (role == 0 && lane == 0) {
+		st->d[demod].lp = lp;
+		if (p.tap_cap) p.tap_cnt[((size_t)stream * kMaxDemods + demod) * 3 + 1] = w.tap_n[1];
+	}
 }
 
 // after the last epoch of a submit: roll positions, carry and last sample forward
@@ -687,8 +670,8 @@ __global__ void parse_kernel(const BackParams p)
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s)
 {
 	(void)n_demods;
-	if (p.tap_cap) whb_kernel<true><<<p.n_streams, 32, 0, s>>>(p);
-	else whb_kernel<false><<<p.n_streams, 32, 0, s>>>(p);
+	if (p.tap_cap) whb_kernel<true><<<p.n_streams, 64, 0, s>>>(p);
+	else whb_kernel<false><<<p.n_streams, 64, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s)
