@@ -248,8 +248,6 @@ def main():
 
     import torch
     import tfrec_b200 as tb
-    if os.environ.get("TFR_LIB"):   # A/B experiments only: a library built from another revision
-        tb.LIB_PATH = os.environ["TFR_LIB"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,3 +1,6 @@
+"""Debug probe: runs a few bench-shaped steps (32 sticks x 128 MiB, -T 7, auto threshold) with TFR_DEBUG=1 so that the
+library prints the timeline of each call (front-end done / threshold walk done / back-end start and end) and, with a
+library built with -DTFR_WIN_PROFILE (TFR_LIB=...), the in-kernel phase clocks of the window kernel."""
 import sys,os
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
 os.environ["TFR_DEBUG"]="1"
