@@ -691,10 +691,11 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 #ifdef TFR_WIN_PROFILE
 	const long long pg0 = clock64();
 #endif
-	if (bitcnt >= 10 && !taps && cb >= e.start && cb + 3 <= last) {
-		// Steady state (the slicer levels are frozen after ten edges, tfa2.cpp:365) on a whole group of four: the
-		// four filter steps, truncations and hash terms form ONE basic block - the FP64 recurrence is the only
-		// chain - and the rare edge candidates are looked at afterwards, in order.
+	if (cb >= e.start && cb + 3 <= last) {
+		// A whole group of four.  The four filter steps, truncations and hash terms are ONE basic block shared by
+		// every lane of the warp, whatever phase its window is in (the FP64 recurrence is the only chain); the
+		// per-sample state machine follows: level tracking while bitcnt < 10 (tfa2.cpp:365-374), then the - rare -
+		// edge candidates, in order.  (A window's first and last partial group take the per-sample loop below.)
 		if ((cb & (kBlockDec - 1)) == 0 && cb != e.start && lbi) lbi -= kIdxPerBlock;   // demodulator::start of a new block
 		const double y0 = biquad_step(lp, k, int_to_double(v4.x));
 		const double y1 = biquad_step(lp, k, int_to_double(v4.y));
@@ -705,10 +706,44 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		hash.add(l1);
 		hash.add(l2);
 		hash.add(l3);
-		if ((l0 > hi || l0 < lo) && (int)(l0 > hi) != last_bit) edge(cb, l0);
-		if ((l1 > hi || l1 < lo) && (int)(l1 > hi) != last_bit) edge(cb + 1, l1);
-		if ((l2 > hi || l2 < lo) && (int)(l2 > hi) != last_bit) edge(cb + 2, l2);
-		if ((l3 > hi || l3 < lo) && (int)(l3 > hi) != last_bit) edge(cb + 3, l3);
+		if (taps) {
+			const uint32_t ti = e.cum + (cb - e.start);
+			if (ti + 3 < c.p->tap_cap) {
+				c.p->tap_i32[0][tbase + ti] = v4.x; c.p->tap_f64[tbase + ti] = y0;
+				c.p->tap_i32[0][tbase + ti + 1] = v4.y; c.p->tap_f64[tbase + ti + 1] = y1;
+				c.p->tap_i32[0][tbase + ti + 2] = v4.z; c.p->tap_f64[tbase + ti + 2] = y2;
+				c.p->tap_i32[0][tbase + ti + 3] = v4.w; c.p->tap_f64[tbase + ti + 3] = y3;
+			} else {
+				const int dv[4] = { v4.x, v4.y, v4.z, v4.w };
+				const double yv[4] = { y0, y1, y2, y3 };
+				for (int j = 0; j < 4; j++)
+					if (ti + j < c.p->tap_cap) { c.p->tap_i32[0][tbase + ti + j] = dv[j]; c.p->tap_f64[tbase + ti + j] = yv[j]; }
+			}
+		}
+		auto sample = [&](uint32_t m, int ld) {
+			if (bitcnt < 10) {
+				if (ld > dmax || ld < dmin) {
+					// the levels are pure functions of dmax/dmin (tfa2.cpp:366-368, 380-381): recompute them only when one moved
+					if (ld > dmax) dmax = (7 * dmax + ld) / 8;
+					if (ld < dmin) dmin = (7 * dmin + ld) / 8;
+					offset = (dmax + dmin) / 2;
+					noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+					hi = noffset + dmax / 32;
+					lo = noffset + dmin / 32;
+				}
+				if (bitcnt > 4) {
+					const uint32_t cw = c.dec[m];
+					const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
+					const uint32_t sum = (uint32_t)rssi + (uint32_t)(i * i) + (uint32_t)(q * q);
+					rssi = (int)((uint32_t)rssi + (uint32_t)((int)sum / 100));
+				}
+			}
+			if ((ld > hi || ld < lo) && (int)(ld > hi) != last_bit) edge(m, ld);
+		};
+		sample(cb, l0);
+		sample(cb + 1, l1);
+		sample(cb + 2, l2);
+		sample(cb + 3, l3);
 #ifdef TFR_WIN_PROFILE
 		pf_fast++; pf_cfast += clock64() - pg0;
 #endif
