@@ -168,6 +168,13 @@ long tfr_read_decimated(tfr_handle *h, int stream, int16_t *out, size_t cap_int1
 /* downconvert(2)::process_iq over a whole buffer with zero initial history; device or host pointers;
  * writes (nbytes/8)*2 int16 (I,Q interleaved at 384 kS/s) and returns that count */
 long tfr_decimate(int device, const uint8_t *iq, size_t nbytes, int filter, int16_t *out, int mem);
+/* downconvert(passes)::process_iq (dsp_stuff.cpp:232-264) for any passes in 1..8, i.e. decimation 2^passes
+ * (BASELINE configs[4] sweeps /2 .. /32): passes-1 times decimate::process2x1 (:204-230) then process2x (:172-202,
+ * `filter` 0 narrow / 1 wide), zero initial history, whole buffer.  Writes (nbytes/2 >> passes) I,Q pairs and
+ * returns the number of int16 written.  `reps` > 1 repeats the stage launches for timing; *kernel_ms (may be
+ * NULL) receives the CUDA-event time of one cascade. */
+long tfr_downconvert(int device, const uint8_t *iq, size_t nbytes, int passes, int filter, int16_t *out, int mem,
+		     int reps, float *kernel_ms);
 /* decoder::store_bytes + flush(0) (main.cpp:45-50, the -X seam) run through the device parser */
 int tfr_parse_bytes(tfr_handle *h, int type, const uint8_t *bytes, int len, tfr_frame *frame,
 		    tfr_record *recs, int max_recs);

@@ -153,6 +153,43 @@ size_t orc_decimate(const uint8_t *iq, size_t nbytes, int filter, int16_t *out)
 	return decim_block(&d, iq, nbytes, out);
 }
 
+/* downconvert(passes)::process_iq, dsp_stuff.cpp:232-264, over a whole buffer with zero history (the reference
+ * carries each stage's window in hist0, so whole-buffer == block-wise): passes-1 times process2x1 (8 taps,
+ * :204-230) on I and on Q, then process2x (20 taps, narrow or wide, :172-202); every stage halves the rate
+ * and stores int16.  Stage output k = sum_n floor(x[2k-(T-2)+n]*t[n] / 2^16), x[<0] = 0.
+ * nbytes of u8 IQ -> (nbytes/2 >> passes) I,Q pairs; returns the number of int16 written. */
+size_t orc_downconvert(const uint8_t *iq, size_t nbytes, int passes, int filter, int16_t *out)
+{
+	if (passes < 1 || passes > 8) return 0;
+	size_t n = nbytes / 2;   /* IQ pairs at the current stage */
+	int16_t *cur = (int16_t *)malloc((n ? n : 1) * 2 * sizeof(int16_t));
+	if (!cur) return 0;
+	for (size_t j = 0; j < 2 * n; j++) cur[j] = (int16_t)((iq[j] - 128) * 64);   /* engine.cpp:77-78 */
+	for (int p = 0; p < passes; p++) {
+		const int last = (p == passes - 1);
+		const int T = last ? 20 : 8;
+		const int16_t *t = last ? (filter ? TAPS_S2_WIDE : TAPS_S2_NARROW) : TAPS_S1;
+		const size_t no = n / 2;
+		int16_t *nx = (int16_t *)malloc((no ? no : 1) * 2 * sizeof(int16_t));
+		if (!nx) { free(cur); return 0; }
+		for (size_t k = 0; k < no; k++)
+			for (int c = 0; c < 2; c++) {
+				int32_t sum = 0;
+				for (int m = 0; m < T; m++) {
+					const long long j = 2 * (long long)k - (T - 2) + m;
+					if (j >= 0) sum += tap_floor(cur[2 * j + c], t[m]);
+				}
+				nx[2 * k + c] = (int16_t)sum;
+			}
+		free(cur);
+		cur = nx;
+		n = no;
+	}
+	memcpy(out, cur, n * 2 * sizeof(int16_t));
+	free(cur);
+	return n * 2;
+}
+
 /* ------------------------------------------------------------------ discriminators, biquad */
 /* dsp_stuff.cpp:269-279 */
 int orc_fm_dev_nrzs(int ar, int aj, int br, int bj)

@@ -67,6 +67,8 @@ def lib():
         L.orc_tap_chan.argtypes = [C.c_void_p, C.c_int]
         L.orc_decimate.restype = C.c_size_t
         L.orc_decimate.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.orc_downconvert.restype = C.c_size_t
+        L.orc_downconvert.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         L.orc_fm_dev.argtypes = [C.c_int] * 4
         L.orc_fm_dev_nrzs.argtypes = [C.c_int] * 4
         L.orc_crc8.restype = C.c_uint8
@@ -160,6 +162,14 @@ def decimate(iq: np.ndarray, filter=0):
     iq = np.ascontiguousarray(iq, dtype=np.uint8)
     out = np.empty(iq.size // 4, dtype=np.int16)
     n = lib().orc_decimate(iq.ctypes.data, iq.size, filter, out.ctypes.data)
+    return out[:n]
+
+
+def downconvert(iq: np.ndarray, passes=2, filter=0):
+    """downconvert(passes)::process_iq, dsp_stuff.cpp:232-264"""
+    iq = np.ascontiguousarray(iq, dtype=np.uint8)
+    out = np.empty(((iq.size // 2) >> passes) * 2 + 2, dtype=np.int16)
+    n = lib().orc_downconvert(iq.ctypes.data, iq.size, passes, filter, out.ctypes.data)
     return out[:n]
 
 

@@ -89,6 +89,53 @@ def test_decimator_ragged_length(tb):
     assert np.array_equal(tb.decimate(iq, 0), ol.decimate(iq, 0))
 
 
+def test_downconvert_all_passes_bit_exact(tb, golden):
+    """BASELINE configs[4]: downconvert(p), p = 1..5 (/2 .. /32), narrow and wide, against the oracle and the
+    compiled reference's hashes"""
+    rng = np.random.default_rng(5)
+    fixtures = {
+        "uniform_bytes": rng.integers(0, 256, size=4 * 65536, dtype=np.uint8),
+        "extremes": np.tile(np.array([0, 255, 255, 0, 0, 0, 255, 255], dtype=np.uint8), 65536 // 8 * 2),
+        "single_tfa1": g.fixture_single_tfa1(seed=1),
+    }
+    for name, iq in fixtures.items():
+        for passes in (1, 2, 3, 4, 5):
+            for filt, key in ((0, "narrow"), (1, "wide")):
+                d = tb.downconvert(iq, passes, filt)
+                ref = ol.downconvert(iq, passes, filt)
+                assert d.size == ref.size == iq.size >> passes
+                assert np.array_equal(d, ref), "%s p=%d %s: %d samples differ" % (name, passes, key, int((d != ref).sum()))
+                assert sha(d.astype("<i2")) == golden["decimator"][name]["passes"][str(passes)][key]["sha256"]
+        assert np.array_equal(tb.downconvert(iq, 2, 0), tb.decimate(iq, 0))   # the fused front-end is the same cascade
+
+
+def test_downconvert_ragged_lengths_and_errors(tb):
+    rng = np.random.default_rng(9)
+    for size in (4, 6, 64, 4096 + 6, 65536 + 4096 + 12, 3 * 65536 + 2):
+        iq = rng.integers(0, 256, size=size, dtype=np.uint8)
+        for passes in (1, 2, 3, 5):
+            assert np.array_equal(tb.downconvert(iq, passes, 1), ol.downconvert(iq, passes, 1)), (size, passes)
+    with pytest.raises(tb.TfrError):
+        tb.downconvert(np.zeros(64, np.uint8), 0, 0)
+    with pytest.raises(tb.TfrError):
+        tb.downconvert(np.zeros(64, np.uint8), 9, 0)
+
+
+def test_downconvert_device_pointers_large(tb):
+    """full-size property check (no oracle at this size): 2^26 raw samples on the device, /8; a causal filter
+    cascade with zero history gives, for a prefix of the input, a prefix of the output"""
+    import torch
+    n = 1 << 27
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    iq = torch.randint(0, 256, (n,), device="cuda", dtype=torch.uint8, generator=gen)
+    out = torch.empty(((n // 2) >> 3) * 2, device="cuda", dtype=torch.int16)
+    cnt, ms = tb.downconvert_device(iq.data_ptr(), n, out.data_ptr(), passes=3, filter=0, reps=3)
+    assert cnt == out.numel() and ms > 0
+    head = tb.downconvert(iq[:1 << 20].cpu().numpy(), 3, 0)
+    assert np.array_equal(out[:head.size].cpu().numpy(), head)
+    assert np.array_equal(head, ol.downconvert(iq[:1 << 20].cpu().numpy(), 3, 0))
+
+
 def test_parser_seam_against_reference(tb, golden):
     rx = tb.Receiver(types=0x2F, thresh=500)
     for k in golden["kat_frames"]:

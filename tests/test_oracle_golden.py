@@ -57,6 +57,39 @@ def test_decimator_against_reference(golden):
             assert sha(d.astype("<i2")) == e[key]["sha256"]
 
 
+def test_downconvert_all_passes_against_reference(golden):
+    """BASELINE configs[4]: every decimation /2 .. /32 of downconvert(p) (dsp_stuff.cpp:232-264) against the
+    compiled reference's output (oracle/_ref/ref_decim, hashes in tests/golden/decimator.json)"""
+    rng = np.random.default_rng(5)
+    fixtures = {
+        "uniform_bytes": rng.integers(0, 256, size=4 * 65536, dtype=np.uint8),
+        "extremes": np.tile(np.array([0, 255, 255, 0, 0, 0, 255, 255], dtype=np.uint8), 65536 // 8 * 2),
+        "single_tfa1": g.fixture_single_tfa1(seed=1),
+    }
+    for name, iq in fixtures.items():
+        for passes in (1, 2, 3, 4, 5):
+            for filt, key in ((0, "narrow"), (1, "wide")):
+                e = golden["decimator"][name]["passes"][str(passes)][key]
+                d = ol.downconvert(iq, passes, filt)
+                assert d.size == e["n"] == iq.size >> passes
+                assert d[:16].tolist() == e["head"] and int(d.min()) == e["min"] and int(d.max()) == e["max"]
+                assert sha(d.astype("<i2")) == e["sha256"]
+        # passes = 2 is the cascade the decode path uses
+        assert np.array_equal(ol.downconvert(iq, 2, 0), ol.decimate(iq, 0))
+
+
+def test_downconvert_ragged_and_tiny():
+    rng = np.random.default_rng(9)
+    iq = rng.integers(0, 256, size=4096 + 6, dtype=np.uint8)      # odd number of pairs at several stages
+    for passes in (1, 2, 3):
+        d = ol.downconvert(iq, passes, 0)
+        assert d.size == ((iq.size // 2) >> passes) * 2
+        # a prefix of the input gives a prefix of the output (causal filters, zero history)
+        d2 = ol.downconvert(iq[:2048], passes, 0)
+        assert np.array_equal(d[:d2.size], d2)
+    assert ol.downconvert(iq[:2], 1, 0).size == 0
+
+
 def test_biquad_coefficients_as_built(golden):
     import ctypes as C
     for k, row in enumerate(golden["biquad_coeffs"]):

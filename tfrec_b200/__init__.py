@@ -23,7 +23,7 @@ FLAG_TAPS, FLAG_KEEP_DECIM = 1, 2
 
 ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_process", "tfr_sync", "tfr_poll_frames",
                "tfr_poll_records", "tfr_clear_results", "tfr_get_thresh", "tfr_read_block_trace", "tfr_read_taps",
-               "tfr_read_decimated", "tfr_decimate", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error",
+               "tfr_read_decimated", "tfr_decimate", "tfr_downconvert", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error",
                "tfr_abi_version"]
 
 
@@ -98,6 +98,9 @@ def load():
     L.tfr_read_decimated.restype = C.c_long
     L.tfr_decimate.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
     L.tfr_decimate.restype = C.c_long
+    L.tfr_downconvert.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float)]
+    L.tfr_downconvert.restype = C.c_long
     L.tfr_parse_bytes.argtypes = [P, C.c_int, C.c_char_p, C.c_int, C.POINTER(Frame), C.POINTER(Record), C.c_int]
     L.tfr_get_stats.argtypes = [P, C.POINTER(Stats)]
     L.tfr_last_error.restype = C.c_char_p
@@ -249,6 +252,21 @@ class Receiver:
                 self.submit(s, iq)
         self.process()
         return self.frames(), self.records()
+
+
+def downconvert(iq: np.ndarray, passes=2, filter=0, device=0):
+    """downconvert(passes)::process_iq (dsp_stuff.cpp:232-264): u8 IQ -> int16 I,Q at 1.536 MS/s / 2^passes"""
+    iq = np.ascontiguousarray(iq, dtype=np.uint8)
+    out = np.empty(((iq.size // 2) >> passes) * 2, dtype=np.int16)
+    n = _check(load().tfr_downconvert(device, iq.ctypes.data, iq.size, passes, filter, out.ctypes.data, MEM_HOST, 1, None))
+    return out[:n]
+
+
+def downconvert_device(iq_ptr, nbytes, out_ptr, passes=2, filter=0, device=0, reps=1):
+    """same with device pointers; returns (int16 written, CUDA-event ms of one cascade)"""
+    ms = C.c_float(0)
+    n = _check(load().tfr_downconvert(device, iq_ptr, nbytes, passes, filter, out_ptr, MEM_DEVICE, reps, C.byref(ms)))
+    return n, float(ms.value)
 
 
 def decimate(iq: np.ndarray, filter=0, device=0):

@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(128) devfm_kernel(const BackParams p)
 		const int a = reg.start[r], b = reg.end[r];
 		for (int m = a + threadIdx.x; m < b; m += blockDim.x) {
 			const uint32_t cw = d[m], lw = (m == 0) ? prev_last : d[m - 1];
-			o[m] = fm_dev((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
-				      (int)(int16_t)(lw >> 16));
+			o[m] = fm_dev_fast((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
+					   (int)(int16_t)(lw >> 16));
 		}
 	}
 }
@@ -855,6 +855,10 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 #define TFR_CHAIN_MAX 8
 #endif
 constexpr int kChainMax = TFR_CHAIN_MAX;
+#ifndef TFR_CHAIN_GROUP
+#define TFR_CHAIN_GROUP 1
+#endif
+constexpr uint32_t kChainGroup = TFR_CHAIN_GROUP;
 #ifdef TFR_WIN_PROFILE
 __device__ unsigned long long g_winprof[16];
 #endif
@@ -867,7 +871,11 @@ __device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int t
 {
 	uint32_t k = 0;
 	while (w - k > 0 && k < 8u * kChainMax && win_near(wl, w - k, timeout)) k++;
-	return (k % kChainMax) == 0;
+	if (k) return (k % kChainMax) == 0;
+	// A window that is not near could be speculated on its own, but every speculated window pays a biquad warm-up of
+	// three timeouts (and 12 % of them a repair): only every kChainGroup-th one is a head, the thread carries the
+	// true filter state and last_bit_idx through the windows in between.
+	return (w % kChainGroup) == 0;
 }
 
 __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
@@ -888,7 +896,11 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 #ifdef TFR_WIN_PROFILE
 	long long prof_t0 = clock64(), prof_warm = 0, prof_run = 0, prof_steps = 0;
 #endif
-	for (uint32_t w0 = blockIdx.x * blockDim.x + threadIdx.x; w0 < n_win; w0 += gridDim.x * blockDim.x) {
+	// thread t looks at the windows [t*G, (t+1)*G): normally the first one is the only head among them and its chain
+	// covers the rest, so consecutive lanes all have work
+	const uint32_t G = chains ? kChainGroup : 1u;
+	for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 * G < n_win; t0 += gridDim.x * blockDim.x)
+	for (uint32_t w0 = t0 * G; w0 < min(n_win, (t0 + 1) * G); w0++) {
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
 		DemodState s;
 		bool have_lbi = false;   // s.last_bit_idx is the value the reference would hold (given the chain head's start state)
@@ -1138,7 +1150,10 @@ static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c
 // round, so the loop ends, and it ends only when every link has been proven.  Finally thread 0 writes the
 // state carried into the next call.
 // ------------------------------------------------------------------------------------------------
-constexpr int kVerifyThreads = 128;
+#ifndef TFR_VERIFY_THREADS
+#define TFR_VERIFY_THREADS 512
+#endif
+constexpr int kVerifyThreads = TFR_VERIFY_THREADS;
 struct VerifyCounts { uint32_t cheap, full, sr, rounds; };
 
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams p)

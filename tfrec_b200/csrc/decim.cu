@@ -1,0 +1,149 @@
+// decim.cu - downconvert(passes)::process_iq (dsp_stuff.cpp:232-264) for ANY number of passes: the decimation
+// sweep of BASELINE configs[4] (/2 .. /32).  The decode path itself always runs passes = 2 through the fused
+// front-end (frontend.cu); this file is the stand-alone cascade: passes-1 first-stage filters (process2x1,
+// 8 taps, dsp_stuff.cpp:204-230), then the 20-tap filter (process2x, narrow or wide, :172-202), one launch per
+// stage, int16 I,Q between stages exactly as the reference stores them in place.
+//
+// One stage: out[k] = sum_n floor(x[2k-(T-2)+n] * t[n] / 2^16) per channel, x[<0] = 0 (zero hist0).  As in the
+// front-end every tap product is ONE round-toward-minus-infinity FMA on an accumulator kept inside
+// [2^23, 2^24), where the fp32 grid is the integers: fma.rm(x, t/2^16, acc) == acc + floor(x*t/2^16) exactly
+// (x and t/2^16 are exact floats, the FMA rounds once), I and Q ride in one fma.rm.f32x2.  Here the inputs are
+// converted with I2F (int16 inputs have no byte structure to exploit), so no offset bookkeeping is needed: the
+// accumulator starts at 2^23+2^22 and moves by less than 20k (sum|t|/2^16 <= 1.43, |x| <= 13.7k).
+//
+// A thread produces 8 consecutive outputs from 2*8+T-2 consecutive inputs held in registers; a warp reads one
+// contiguous span (32- or 64-bit loads, every sector fully used, the T-2 sample overlap between neighbours
+// hits L1) and writes 32 B per thread.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "fir_taps.h"
+#include "tfr_dev.h"
+
+namespace tfr {
+
+typedef unsigned long long f2;   // packed f32x2: lo = I, hi = Q
+
+__device__ __forceinline__ f2 dpack2(float lo, float hi)
+{
+	f2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ f2 dfma2_rm(f2 a, f2 b, f2 c)
+{
+	f2 d;
+	asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
+constexpr int kStageOut = 8;          // outputs per thread
+constexpr int kStageThreads = 256;
+constexpr float kAcc0 = 12582912.0f;  // 2^23 + 2^22
+constexpr uint32_t kAcc0Bits = 0x4B400000u;
+
+template <int TAPS, bool WIDE>
+__device__ __forceinline__ float stage_tap(int n)
+{
+	return (float)(TAPS == 8 ? t2_tap(n) : t1_tap(WIDE, n)) * (1.0f / 65536.0f);
+}
+
+// U8IN: `in` is raw rtl-sdr offset-binary IQ (2 B per pair), converted with (b-128)<<6 (engine.cpp:77-78);
+// otherwise int16 I,Q (4 B per pair) as left by the previous stage.
+template <int TAPS, bool WIDE, bool U8IN>
+__global__ void __launch_bounds__(kStageThreads) decim_stage_kernel(const void *__restrict__ in, int16_t *__restrict__ out, long long n_in,
+								   long long n_out)
+{
+	constexpr int W = 2 * kStageOut + TAPS - 2;   // input pairs a thread needs
+	const long long t = (long long)blockIdx.x * kStageThreads + threadIdx.x;
+	const long long k0 = t * kStageOut;
+	if (k0 >= n_out) return;
+	const long long j0 = 2 * k0 - (TAPS - 2);     // first input pair (even; negative at the start of the buffer)
+	f2 x[W];
+	if (U8IN) {
+		// one 32-bit word = two pairs; j0 is even, so the span is word aligned
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(in);
+#pragma unroll
+		for (int w = 0; w < W / 2; w++) {
+			const long long j = j0 + 2 * w;
+			uint32_t v = 0x80808080u;                                  // zero signal
+			if (j >= 0 && j + 1 < n_in) v = __ldg(src + (j >> 1));
+			else if (j >= 0 && j < n_in) v = (v & 0xffff0000u) | reinterpret_cast<const uint16_t *>(in)[j];
+			x[2 * w] = dpack2((float)(((int)(v & 0xff) - 128) * 64), (float)(((int)((v >> 8) & 0xff) - 128) * 64));
+			x[2 * w + 1] = dpack2((float)(((int)((v >> 16) & 0xff) - 128) * 64), (float)(((int)(v >> 24) - 128) * 64));
+		}
+	} else {
+		// one 64-bit word = two pairs
+		const uint2 *src = reinterpret_cast<const uint2 *>(in);
+#pragma unroll
+		for (int w = 0; w < W / 2; w++) {
+			const long long j = j0 + 2 * w;
+			uint2 v = make_uint2(0u, 0u);
+			if (j >= 0 && j + 1 < n_in) v = __ldg(src + (j >> 1));
+			else if (j >= 0 && j < n_in) v.x = reinterpret_cast<const uint32_t *>(in)[j];
+			x[2 * w] = dpack2((float)(int)(int16_t)(v.x & 0xffff), (float)(int)(int16_t)(v.x >> 16));
+			x[2 * w + 1] = dpack2((float)(int)(int16_t)(v.y & 0xffff), (float)(int)(int16_t)(v.y >> 16));
+		}
+	}
+	uint32_t o[kStageOut];
+#pragma unroll
+	for (int k = 0; k < kStageOut; k++) {
+		f2 acc = dpack2(kAcc0, kAcc0);
+#pragma unroll
+		for (int n = 0; n < TAPS; n++) {
+			const float c = stage_tap<TAPS, WIDE>(n);
+			acc = dfma2_rm(x[2 * k + n], dpack2(c, c), acc);
+		}
+		const uint32_t yi = (uint32_t)(acc & 0xffffffffull) - kAcc0Bits, yq = (uint32_t)(acc >> 32) - kAcc0Bits;
+		o[k] = (yi & 0xffffu) | (yq << 16);
+	}
+	uint32_t *dst = reinterpret_cast<uint32_t *>(out) + k0;
+	if (k0 + kStageOut <= n_out) {
+		reinterpret_cast<uint4 *>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+		reinterpret_cast<uint4 *>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+	} else {
+#pragma unroll
+		for (int k = 0; k < kStageOut; k++)
+			if (k0 + k < n_out) dst[k] = o[k];
+	}
+}
+
+template <int TAPS, bool WIDE, bool U8IN>
+static cudaError_t launch_stage(const void *in, int16_t *out, long long n_in, long long n_out, cudaStream_t s)
+{
+	if (n_out <= 0) return cudaSuccess;
+	const long long threads = (n_out + kStageOut - 1) / kStageOut;
+	const long long blocks = (threads + kStageThreads - 1) / kStageThreads;
+	if (blocks > 0x7fffffffll) return cudaErrorInvalidValue;
+	decim_stage_kernel<TAPS, WIDE, U8IN><<<(unsigned)blocks, kStageThreads, 0, s>>>(in, out, n_in, n_out);
+	return cudaGetLastError();
+}
+
+// iq: device pointer to n_pairs raw IQ pairs; tmp[0], tmp[1]: device int16 buffers of >= n_pairs/2 and >= n_pairs/4
+// pairs; the result (n_pairs >> passes pairs) is in *result (one of the two).  Stages run back to back on `s`.
+cudaError_t launch_downconvert(const uint8_t *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
+			       cudaStream_t s)
+{
+	const void *cur = iq;
+	long long n = n_pairs;
+	int16_t *bufs[2] = { tmp0, tmp1 };
+	int16_t *dst = nullptr;
+	for (int p = 0; p < passes; p++) {
+		dst = bufs[p & 1];
+		const long long no = n / 2;
+		const bool last = (p == passes - 1), first = (p == 0);
+		cudaError_t e;
+		if (!last) e = first ? launch_stage<8, false, true>(cur, dst, n, no, s) : launch_stage<8, false, false>(cur, dst, n, no, s);
+		else if (wide) e = first ? launch_stage<20, true, true>(cur, dst, n, no, s) : launch_stage<20, true, false>(cur, dst, n, no, s);
+		else e = first ? launch_stage<20, false, true>(cur, dst, n, no, s) : launch_stage<20, false, false>(cur, dst, n, no, s);
+		if (e != cudaSuccess) return e;
+		cur = dst;
+		n = no;
+	}
+	*result = dst;
+	return cudaSuccess;
+}
+
+}  // namespace tfr

@@ -78,6 +78,54 @@ __device__ __forceinline__ int fm_dev(int ar, int aj, int br, int bj)
 	return __double2int_rz(__dmul_rn(ang, 5215.189175235227));   // fl(16384/pi), see header
 }
 
+// fm_dev for the bulk of the samples: the same integer as fm_dev() above, ~8x fewer instructions.
+// The result is trunc(angle * fl(16384/pi)); an approximation of the angle with absolute error e gives the same
+// integer unless angle*K lies within e*K of a truncation boundary.  The angle comes from a degree-12 polynomial
+// in q^2 (q = min/max of |cr|,|cj|, octant folding; max error 6e-12 rad = 3.1e-8 output units against glibc's
+// atan2, tools/fit_atan.py) and a Newton reciprocal; every sample whose scaled angle is within 1e-6 of an
+// integer - and the axis / diagonal / zero cases, whose value depends on signed zeros and on glibc's exact
+// return values - takes fm_dev().  Products and sums are exact in int32 (|I|,|Q| <= 12.2k).
+__device__ __forceinline__ int fm_dev_fast(int ar, int aj, int br, int bj)
+{
+	const int cri = aj * bj + ar * br, cji = br * aj - ar * bj;
+	const int axi = abs(cri), ayi = abs(cji);
+	const bool special = (cji == 0 || cri == 0 || axi == ayi);   // (the arithmetic below is then discarded)
+	const int mxi = max(axi, ayi), mni = min(axi, ayi);
+	// non-negative int -> double without I2F.F64: the low mantissa word of 2^52
+	const double mx = __hiloint2double(0x43300000, mxi) - 4503599627370496.0;
+	const double mn = __hiloint2double(0x43300000, mni) - 4503599627370496.0;
+	float rf;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)mxi));
+	double r = (double)rf;                       // 2^-22 relative; two Newton steps -> double precision
+	double e = fma(-mx, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-mx, r, 1.0);
+	r = fma(r, e, r);
+	const double q = mn * r, z = q * q;
+	double p = 0x1.b79940e5536f0p-12;
+	p = fma(p, z, -0x1.a2d5e8268d02fp-9);
+	p = fma(p, z, 0x1.7676be8c4ef52p-7);
+	p = fma(p, z, -0x1.aa15aa0c3e761p-6);
+	p = fma(p, z, 0x1.658dd34696c8fp-5);
+	p = fma(p, z, -0x1.ed56cc14c7895p-5);
+	p = fma(p, z, 0x1.33018fb5c9b3fp-4);
+	p = fma(p, z, -0x1.72a787e7c5385p-4);
+	p = fma(p, z, 0x1.c6df953d05217p-4);
+	p = fma(p, z, -0x1.248fb94625489p-3);
+	p = fma(p, z, 0x1.99997c8640331p-3);
+	p = fma(p, z, -0x1.55555513c3688p-2);
+	p = fma(p, z, 0x1.ffffffffe73b8p-1);
+	double a = q * p;                            // atan(min/max) in (0, pi/4)
+	if (ayi > axi) a = 0x1.921fb54442d18p+0 - a;
+	if (cri < 0) a = 0x1.921fb54442d18p+1 - a;
+	const double v = a * 5215.189175235227;      // in (0, 16384)
+	const double t = __dadd_rz(v, 4503599627370496.0);
+	const double fr = v - (t - 4503599627370496.0);   // v - floor(v), exact
+	if (special || fr < 1e-6 || fr > 1.0 - 1e-6) return fm_dev(ar, aj, br, bj);
+	const int n = __double2loint(t);
+	return cji < 0 ? -n : n;
+}
+
 // iir2::step, dsp_stuff.cpp:47-55, association as built
 __device__ __forceinline__ double biquad_step(Biquad &f, const BiquadCoef &k, double dn)
 {

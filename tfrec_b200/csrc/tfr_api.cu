@@ -24,6 +24,8 @@ cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
 cudaError_t launch_parse(const BackParams &p, cudaStream_t s);
+cudaError_t launch_downconvert(const uint8_t *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
+			       cudaStream_t s);
 }  // namespace tfr
 
 using namespace tfr;
@@ -891,6 +893,57 @@ extern "C" __attribute__((visibility("default"))) long tfr_decimate(int device, 
 	std::string keep = g_err;
 	tfr_destroy(h);
 	g_err = keep;
+	return ret;
+}
+
+// downconvert(passes)::process_iq over a whole buffer (dsp_stuff.cpp:232-264): the decimation sweep entry point
+extern "C" __attribute__((visibility("default"))) long tfr_downconvert(int device, const uint8_t *iq, size_t nbytes, int passes, int filter,
+								       int16_t *out, int mem, int reps, float *kernel_ms)
+{
+	if (!iq || !out || nbytes < 4) return fail(TFR_E_INVAL, "tfr_downconvert: bad argument");
+	if (passes < 1 || passes > 8) return fail(TFR_E_INVAL, "tfr_downconvert: passes must be 1..8");
+	if (mem != TFR_MEM_HOST && mem != TFR_MEM_DEVICE) return fail(TFR_E_INVAL, "tfr_downconvert: mem must be TFR_MEM_HOST or TFR_MEM_DEVICE");
+	if (mem == TFR_MEM_DEVICE && (((uintptr_t)iq & 15) || ((uintptr_t)out & 15))) return fail(TFR_E_INVAL, "tfr_downconvert: device pointers must be 16-byte aligned");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return fail(TFR_E_NODEVICE, "tfr_downconvert: no such CUDA device (there is no CPU fallback)"); }
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) return fail(TFR_E_CUDA, std::string("tfr_downconvert: ") + cudaGetErrorString(e));
+	const long long n_pairs = (long long)(nbytes / 2);
+	const long long n_res = n_pairs >> passes;            // every stage drops an odd trailing sample
+	uint8_t *d_in = nullptr;
+	int16_t *tmp[2] = { nullptr, nullptr }, *res = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	long ret = 0;
+	auto cuda_fail = [&](const char *what, cudaError_t err) { cudaGetLastError(); return (long)fail(err == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("tfr_downconvert: ") + what + ": " + cudaGetErrorString(err)); };
+	do {
+		const uint8_t *src = iq;
+		if (mem == TFR_MEM_HOST) {
+			if ((e = cudaMalloc(&d_in, nbytes)) != cudaSuccess) { ret = cuda_fail("input buffer", e); break; }
+			if ((e = cudaMemcpy(d_in, iq, nbytes, cudaMemcpyHostToDevice)) != cudaSuccess) { ret = cuda_fail("copy in", e); break; }
+			src = d_in;
+		}
+		if ((e = cudaMalloc(&tmp[0], std::max<size_t>((size_t)(n_pairs / 2) * 4, 16))) != cudaSuccess) { ret = cuda_fail("stage buffer", e); break; }
+		if (passes > 1 && (e = cudaMalloc(&tmp[1], std::max<size_t>((size_t)(n_pairs / 4) * 4, 16))) != cudaSuccess) { ret = cuda_fail("stage buffer", e); break; }
+		if ((e = cudaEventCreate(&ev0)) != cudaSuccess || (e = cudaEventCreate(&ev1)) != cudaSuccess) { ret = cuda_fail("events", e); break; }
+		// reps > 1: timing runs (the sweep tool); the result is the same every time
+		const int n_rep = reps < 1 ? 1 : reps;
+		if ((e = launch_downconvert(src, n_pairs, passes, filter, tmp[0], tmp[1], &res, 0)) != cudaSuccess) { ret = cuda_fail("launch", e); break; }
+		cudaEventRecord(ev0, 0);
+		for (int r = 0; r < n_rep && e == cudaSuccess; r++) e = launch_downconvert(src, n_pairs, passes, filter, tmp[0], tmp[1], &res, 0);
+		cudaEventRecord(ev1, 0);
+		if (e != cudaSuccess) { ret = cuda_fail("launch", e); break; }
+		if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) { ret = cuda_fail("kernels", e); break; }
+		if (kernel_ms) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, ev0, ev1);
+			*kernel_ms = ms / (float)n_rep;
+		}
+		if (n_res > 0 && (e = cudaMemcpy(out, res, (size_t)n_res * 4, mem == TFR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost)) != cudaSuccess) { ret = cuda_fail("copy out", e); break; }
+		ret = (long)(n_res * 2);
+	} while (0);
+	if (ev0) cudaEventDestroy(ev0);
+	if (ev1) cudaEventDestroy(ev1);
+	cudaFree(d_in); cudaFree(tmp[0]); cudaFree(tmp[1]);
 	return ret;
 }
 

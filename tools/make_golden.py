@@ -188,6 +188,20 @@ def gen_decimator():
                 assert np.array_equal(d, d2)
                 e["narrow" if filt == 0 else "wide"] = {"n": int(d.size), "sha256": sha(d), "head": d[:48].tolist(),
                                                          "min": int(d.min()), "max": int(d.max())}
+            # downconvert(passes) for every decimation of BASELINE configs[4] (dsp_stuff.cpp:232-264): /2 .. /32
+            e["passes"] = {}
+            for passes in (1, 2, 3, 4, 5):
+                ep = {}
+                for filt in (0, 1):
+                    q = p + ".s16"
+                    subprocess.run([os.path.join(REF, "ref_decim"), p, q, str(filt), "65536", str(passes)], check=True)
+                    d = np.fromfile(q, dtype="<i2")
+                    subprocess.run([os.path.join(REF, "ref_decim"), p, q, str(filt), "4096", str(passes)], check=True)
+                    assert np.array_equal(d, np.fromfile(q, dtype="<i2"))
+                    ep["narrow" if filt == 0 else "wide"] = {"n": int(d.size), "sha256": sha(d), "head": d[:16].tolist(),
+                                                             "min": int(d.min()), "max": int(d.max())}
+                e["passes"][str(passes)] = ep
+            assert e["passes"]["2"]["narrow"]["sha256"] == e["narrow"]["sha256"]
             out[name] = e
             print("decimator", name, e["narrow"]["n"])
     return out
@@ -233,8 +247,11 @@ def main():
     if not os.path.exists(os.path.join(REF, "tfrec_taps")):
         sys.exit("oracle/_ref missing: run `make -C oracle ref` where /root/reference exists")
     os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]   # e.g. `make_golden.py decimator` regenerates one file
     for name, fn in (("kat_frames", gen_kat), ("decimator", gen_decimator), ("biquad_coeffs", gen_biquad),
                      ("hotpath", gen_hotpath)):
+        if only and name not in only:
+            continue
         with open(os.path.join(GOLD, name + ".json"), "w") as f:
             json.dump(fn(), f, indent=1)
             f.write("\n")
