@@ -377,28 +377,38 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) devfm_kernel(const BackParams p)
 {
+	// One CTA per block; the kernel is a chain of dependent loads (job -> descriptor -> samples), so what matters is
+	// how many of them are in flight: every thread reads the (L1-resident after the first touch) segment table itself
+	// instead of waiting at a barrier for a serially built region list, and strides the kept samples by the CTA width.
 	const int stream = blockIdx.y;
 	const StreamJob job = p.jobs[stream];
 	const int tile = blockIdx.x;
 	if (tile >= (int)job.n_blocks) return;
 	const size_t gtile = (size_t)job.dec_off + tile;
 	const TileDesc &td = p.tiles[gtile];
+	const int n_seg = td.n_seg;
 	const int carry_in = (tile == 0) ? p.st[stream].carry_in : p.tiles[gtile - 1].carry_out;
-	__shared__ Regions reg;
-	if (threadIdx.x == 0) build_regions(td, carry_in, reg);
-	__syncthreads();
+	if (n_seg == 0 && carry_in == 0) return;
 	const uint32_t *d = p.dec + gtile * kBlockDec;
 	int32_t *o = p.devfm + gtile * kBlockDec;
 	uint32_t prev_last;
 	if (tile == 0) prev_last = ((uint32_t)(uint16_t)p.st[stream].last_i) | ((uint32_t)(uint16_t)p.st[stream].last_q << 16);
 	else prev_last = d[-1];   // the previous block's last sample is always stored
-	for (int r = 0; r < reg.n; r++) {
-		const int a = reg.start[r], b = reg.end[r];
-		for (int m = a + threadIdx.x; m < b; m += blockDim.x) {
+	// the kept samples are [0, carry_in) U segments (build_regions): walk them in order, skipping what is covered
+	int covered = 0;
+	for (int k = -1; k < n_seg; k++) {
+		int a = 0, b = carry_in;
+		if (k >= 0) {
+			const int s0 = td.seg_start[k];
+			a = max(s0, covered);
+			b = s0 + td.seg_len[k];
+		}
+		for (int m = a + (int)threadIdx.x; m < b; m += (int)blockDim.x) {
 			const uint32_t cw = d[m], lw = (m == 0) ? prev_last : d[m - 1];
 			o[m] = fm_dev_fast((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
 					   (int)(int16_t)(lw >> 16));
 		}
+		covered = max(covered, b);
 	}
 }
 
@@ -960,22 +970,45 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 					lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
 					if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
 					const BiquadCoef k = cfg.lp;
-					for (int u = v; u < (int)w; u++) {
-						const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
-						uint32_t m = a;
-						for (; (m & 15u) && m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
-						if (m + 15 <= b) {
-							// two chunks in flight: the next one is loaded before the current one is filtered
-							Chunk16 ck = load16(c.devfm + m);
-							for (; m + 15 <= b; m += 16) {
-								Chunk16 nx = ck;
-								if (m + 31 <= b) nx = load16(c.devfm + m + 16);
-#pragma unroll
-								for (int kk = 0; kk < 16; kk++) biquad_step(lp, k, int_to_double(ck.v[kk]));
-								ck = nx;
-							}
+					// ONE loop for every lane of the warp: a step is an aligned group of four samples of the lane's current
+					// history window, samples outside [m, b] masked.  (A loop nest per window - head, 16-sample chunks,
+					// tail - ran the lanes of a warp through different loops at different times.)  One group is in flight
+					// in registers, the line after next is prefetched into L1; a four-group register FIFO was measured
+					// slower (156 registers: two CTAs fewer per SM).
+					{
+						const int4 *src4 = reinterpret_cast<const int4 *>(c.devfm);
+						int u = v;
+						uint32_t m = from, b = (u < (int)w) ? wl[u].end : 0u;
+						int4 cur = make_int4(0, 0, 0, 0);
+						if (u < (int)w) {
+							cur = src4[m >> 2];
+							prefetch_l1(c.devfm + (m & ~31u) + 32);
 						}
-						for (; m <= b; m++) biquad_step(lp, k, int_to_double(c.devfm[m]));
+						while (u < (int)w) {
+							const uint32_t g = m & ~3u;
+							const int4 v4 = cur;
+							// where the next group is: the load goes out before the four filter steps
+							int nu = u;
+							uint32_t nm = g + 4, nb = b;
+							if (nm > b) {
+								nu = u + 1;
+								if (nu < (int)w) {
+									nm = wl[nu].start;
+									nb = wl[nu].end;
+									prefetch_l1(c.devfm + (nm & ~31u) + 32);
+								}
+							} else if ((g & 31u) == 0 && g + 64 <= b) {
+								prefetch_l1(c.devfm + g + 64);   // the line after next
+							}
+							if (nu < (int)w) cur = src4[nm >> 2];
+							if (g >= m) biquad_step(lp, k, int_to_double(v4.x));
+							if (g + 1 >= m && g + 1 <= b) biquad_step(lp, k, int_to_double(v4.y));
+							if (g + 2 >= m && g + 2 <= b) biquad_step(lp, k, int_to_double(v4.z));
+							if (g + 3 <= b) biquad_step(lp, k, int_to_double(v4.w));
+							u = nu;
+							m = nm;
+							b = nb;
+						}
 					}
 					s.lp = lp;
 #ifdef TFR_WIN_PROFILE
@@ -1119,6 +1152,7 @@ static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c
 		for (; m + 15 <= last; m += 16) {
 			Chunk16 nx = ck;
 			if (m + 31 <= last) nx = load16(c.devfm + m + 16);   // in flight while the current chunk is filtered
+			if (m + 63 <= last) prefetch_l1(c.devfm + m + 48);   // a chunk is ~600 cycles of filter, an L2 round trip more
 #pragma unroll
 			for (int kk = 0; kk < 16; kk++) step(m + kk, ck.v[kk]);
 			ck = nx;
@@ -1155,6 +1189,9 @@ static __device__ __forceinline__ unsigned long long biquad_only(const WinCtx &c
 #endif
 constexpr int kVerifyThreads = TFR_VERIFY_THREADS;
 struct VerifyCounts { uint32_t cheap, full, sr, rounds; };
+#ifdef TFR_VER_PROFILE
+__device__ unsigned long long g_verprof[8];   // max over CTAs: cycles in flags / run starts / repair phases, rounds, whole CTA; max thread repair cycles, windows
+#endif
 
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams p)
 {
@@ -1177,6 +1214,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 	__shared__ uint32_t s_runs[kVerifyThreads];
 	__shared__ uint32_t s_nruns, s_first;
 	uint32_t n_cheap = 0, n_full = 0, n_sr = 0, rounds = 0;
+#ifdef TFR_VER_PROFILE
+	long long vp_flags = 0, vp_starts = 0, vp_repair = 0, vp_t0 = clock64(), vp_mine = 0, vp_wins = 0;
+#endif
 
 	// is window w (> 0) consistent with the records before it?  edge_bad reports a wrong last_bit_idx assumption
 	auto good = [&](uint32_t w, const WinRec &rec, bool &edge_bad) -> bool {
@@ -1195,6 +1235,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 	};
 
 	for (;;) {
+#ifdef TFR_VER_PROFILE
+		long long vp_a = clock64();
+#endif
 		if (tid == 0) {
 			s_nruns = 0;
 			s_first = 0xffffffffu;
@@ -1209,6 +1252,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 			rl[w].pad = pad;
 		}
 		__syncthreads();
+#ifdef TFR_VER_PROFILE
+		vp_flags += clock64() - vp_a; vp_a = clock64();
+#endif
 		// ---- run starts
 		for (uint32_t w = 1 + tid; w < n_win; w += kVerifyThreads) {
 			if (!(rl[w].pad & kPadOk) && (rl[w - 1].pad & kPadOk)) {
@@ -1225,6 +1271,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 		if (tid == 0 && s_nruns > (uint32_t)kVerifyThreads) s_runs[0] = s_first;
 		__syncthreads();
 		rounds++;
+#ifdef TFR_VER_PROFILE
+		vp_starts += clock64() - vp_a; vp_a = clock64();
+#endif
 		// ---- repair, one thread per run
 		if ((uint32_t)tid < n_runs) {
 			const uint32_t w = s_runs[tid];
@@ -1287,12 +1336,30 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 						n_full++;
 					}
 					rl[v] = rec;
+#ifdef TFR_VER_PROFILE
+					vp_wins++;
+#endif
 					if (rec.flags & kRecUnfinished) break;
 				}
 			}
+#ifdef TFR_VER_PROFILE
+			vp_mine += clock64() - vp_a;
+#endif
 		}
 		__syncthreads();
+#ifdef TFR_VER_PROFILE
+		vp_repair += clock64() - vp_a;
+#endif
 	}
+#ifdef TFR_VER_PROFILE
+	atomicMax(&g_verprof[5], (unsigned long long)vp_mine);
+	atomicMax(&g_verprof[6], (unsigned long long)vp_wins);
+	if (tid == 0) {
+		atomicMax(&g_verprof[0], (unsigned long long)vp_flags); atomicMax(&g_verprof[1], (unsigned long long)vp_starts);
+		atomicMax(&g_verprof[2], (unsigned long long)vp_repair); atomicMax(&g_verprof[3], (unsigned long long)rounds);
+		atomicMax(&g_verprof[4], (unsigned long long)(clock64() - vp_t0));
+	}
+#endif
 
 	if (n_cheap) atomicAdd(&p.counters->par_cheap, n_cheap);
 	if (n_full) atomicAdd(&p.counters->ver_full, n_full);
@@ -1398,6 +1465,18 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 }
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s)
 {
+#ifdef TFR_VER_PROFILE
+	{
+		unsigned long long z[8] = { 0 }, r[8];
+		cudaStreamSynchronize(s);
+		cudaMemcpyToSymbol(g_verprof, z, sizeof(z));
+		verify_kernel<<<p.n_streams * n_demods, kVerifyThreads, 0, s>>>(p);
+		cudaStreamSynchronize(s);
+		cudaMemcpyFromSymbol(r, g_verprof, sizeof(r));
+		fprintf(stderr, "[verprof] max over CTAs: flags %llu cyc, run starts %llu cyc, repair %llu cyc, rounds %llu, whole CTA %llu cyc | max thread: repair %llu cyc, %llu windows\n", r[0], r[1], r[2], r[3], r[4], r[5], r[6]);
+		return cudaGetLastError();
+	}
+#endif
 	verify_kernel<<<p.n_streams * n_demods, kVerifyThreads, 0, s>>>(p);
 	return cudaGetLastError();
 }

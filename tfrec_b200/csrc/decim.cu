@@ -7,9 +7,10 @@
 // One stage: out[k] = sum_n floor(x[2k-(T-2)+n] * t[n] / 2^16) per channel, x[<0] = 0 (zero hist0).  As in the
 // front-end every tap product is ONE round-toward-minus-infinity FMA on an accumulator kept inside
 // [2^23, 2^24), where the fp32 grid is the integers: fma.rm(x, t/2^16, acc) == acc + floor(x*t/2^16) exactly
-// (x and t/2^16 are exact floats, the FMA rounds once), I and Q ride in one fma.rm.f32x2.  Here the inputs are
-// converted with I2F (int16 inputs have no byte structure to exploit), so no offset bookkeeping is needed: the
-// accumulator starts at 2^23+2^22 and moves by less than 20k (sum|t|/2^16 <= 1.43, |x| <= 13.7k).
+// (x and t/2^16 are exact floats, the FMA rounds once), I and Q ride in one fma.rm.f32x2.  int16 inputs are
+// converted with I2F (no byte structure to exploit): the accumulator starts at 2^23+2^22 and moves by less than
+// 20k (sum|t|/2^16 <= 1.43, |x| <= 13.7k).  Raw bytes (the first stage) use the front-end's integer-only
+// byte->float trick, whose known integer offset is removed at the end (see kCvtBase below).
 //
 // A thread produces 8 consecutive outputs from 2*8+T-2 consecutive inputs held in registers; a warp reads one
 // contiguous span (32- or 64-bit loads, every sector fully used, the T-2 sample overlap between neighbours
@@ -45,10 +46,35 @@ constexpr float kAcc0 = 12582912.0f;  // 2^23 + 2^22
 constexpr uint32_t kAcc0Bits = 0x4B400000u;
 
 template <int TAPS, bool WIDE>
-__device__ __forceinline__ float stage_tap(int n)
+__host__ __device__ constexpr int stage_tap_int(int n)
 {
-	return (float)(TAPS == 8 ? t2_tap(n) : t1_tap(WIDE, n)) * (1.0f / 65536.0f);
+	return TAPS == 8 ? t2_tap(n) : t1_tap(WIDE, n);
 }
+// Raw bytes are turned into floats with integer instructions only, as in the front-end: bits 0x47038000 + (b << 8)
+// are the float 33664 + b = 33*1024 + (b-128) (binade [2^15, 2^16), ulp 1/256).  With the tap scaled by 1/1024
+// (x = (b-128)<<6, so x*t/2^16 = (b-128)*t/1024) every FMA then adds floor((b-128)*t/1024) + 33*t: the wanted
+// term plus an integer that is removed when the accumulator bits are read back.
+constexpr uint32_t kCvtBase = 0x47038000u;
+constexpr int kCvtMul = 33;
+template <int TAPS, bool WIDE>
+__host__ __device__ constexpr int u8_offset()
+{
+	int s = 0;
+	for (int n = 0; n < TAPS; n++) s += kCvtMul * stage_tap_int<TAPS, WIDE>(n);
+	return s;
+}
+template <int TAPS, bool WIDE>
+__host__ __device__ constexpr bool u8_chain_in_range()
+{
+	int s = (1 << 23) + (1 << 22);
+	for (int n = 0; n < TAPS; n++) {
+		s += kCvtMul * stage_tap_int<TAPS, WIDE>(n);
+		if (s - 20000 < (1 << 23) || s + 20000 >= (1 << 24)) return false;
+	}
+	return true;
+}
+static_assert(u8_chain_in_range<8, false>() && u8_chain_in_range<20, false>() && u8_chain_in_range<20, true>(),
+	      "u8 stage accumulator leaves the integer binade");
 
 // U8IN: `in` is raw rtl-sdr offset-binary IQ (2 B per pair), converted with (b-128)<<6 (engine.cpp:77-78);
 // otherwise int16 I,Q (4 B per pair) as left by the previous stage.
@@ -71,8 +97,8 @@ __global__ void __launch_bounds__(kStageThreads) decim_stage_kernel(const void *
 			uint32_t v = 0x80808080u;                                  // zero signal
 			if (j >= 0 && j + 1 < n_in) v = __ldg(src + (j >> 1));
 			else if (j >= 0 && j < n_in) v = (v & 0xffff0000u) | reinterpret_cast<const uint16_t *>(in)[j];
-			x[2 * w] = dpack2((float)(((int)(v & 0xff) - 128) * 64), (float)(((int)((v >> 8) & 0xff) - 128) * 64));
-			x[2 * w + 1] = dpack2((float)(((int)((v >> 16) & 0xff) - 128) * 64), (float)(((int)(v >> 24) - 128) * 64));
+			x[2 * w] = dpack2(__uint_as_float(__byte_perm(v, 0, 0x4404) + kCvtBase), __uint_as_float(__byte_perm(v, 0, 0x4414) + kCvtBase));
+			x[2 * w + 1] = dpack2(__uint_as_float(__byte_perm(v, 0, 0x4424) + kCvtBase), __uint_as_float(__byte_perm(v, 0, 0x4434) + kCvtBase));
 		}
 	} else {
 		// one 64-bit word = two pairs
@@ -93,10 +119,11 @@ __global__ void __launch_bounds__(kStageThreads) decim_stage_kernel(const void *
 		f2 acc = dpack2(kAcc0, kAcc0);
 #pragma unroll
 		for (int n = 0; n < TAPS; n++) {
-			const float c = stage_tap<TAPS, WIDE>(n);
+			const float c = (float)stage_tap_int<TAPS, WIDE>(n) * (U8IN ? 1.0f / 1024.0f : 1.0f / 65536.0f);
 			acc = dfma2_rm(x[2 * k + n], dpack2(c, c), acc);
 		}
-		const uint32_t yi = (uint32_t)(acc & 0xffffffffull) - kAcc0Bits, yq = (uint32_t)(acc >> 32) - kAcc0Bits;
+		constexpr uint32_t bias = kAcc0Bits + (U8IN ? (uint32_t)u8_offset<TAPS, WIDE>() : 0u);
+		const uint32_t yi = (uint32_t)(acc & 0xffffffffull) - bias, yq = (uint32_t)(acc >> 32) - bias;
 		o[k] = (yi & 0xffffu) | (yq << 16);
 	}
 	uint32_t *dst = reinterpret_cast<uint32_t *>(out) + k0;
