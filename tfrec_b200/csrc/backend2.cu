@@ -883,12 +883,41 @@ __device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int t
 	while (w - k > 0 && k < 8u * kChainMax && win_near(wl, w - k, timeout)) k++;
 	if (k) return (k % kChainMax) == 0;
 	// A window that is not near could be speculated on its own, but every speculated window pays a biquad warm-up of
-	// three timeouts (and 12 % of them a repair): only every kChainGroup-th one is a head, the thread carries the
-	// true filter state and last_bit_idx through the windows in between.
+	// several timeouts (and some of them a repair): only every kChainGroup-th one is a head, the thread carries the
+	// true filter state and last_bit_idx through the windows in between.  (Measured slower for every G > 1.)
 	return (w % kChainGroup) == 0;
 }
 
-__global__ void __launch_bounds__(64) win_kernel(const BackParams p)
+#ifndef TFR_LONG_X
+#define TFR_LONG_X 4
+#endif
+// A chain is LONG when its windows add up to more than TFR_LONG_X timeouts (a telegram; noise that kept retriggering
+// stays below that: a warp per chain only pays for the few really long ones).
+// One thread walks a chain sample by sample at ~500 cycles per sample (every instruction waits for the one before);
+// the few long chains of a call are therefore the window kernel's critical path.  They are taken out of the
+// thread-per-chain kernel and run by winlong_kernel, one WARP per chain (below).
+__device__ __forceinline__ bool chain_is_long(const WinEntry *wl, uint32_t w0, uint32_t n_win, uint32_t call_len, bool chains, int timeout)
+{
+	uint32_t tot = 0;
+	for (uint32_t w = w0; w < n_win; w++) {
+		if (w != w0 && (!chains || chain_head(wl, w, timeout))) break;
+		if (wl[w].start >= call_len) break;
+		tot += min(wl[w].end, call_len - 1) - wl[w].start + 1;
+	}
+	return tot > (uint32_t)TFR_LONG_X * (uint32_t)timeout;
+}
+
+// 64-thread CTAs, at least ten per SM (96 registers, no spills): the kernel is a crowd of divergent, latency-bound
+// chains, so resident warps are what buys throughput (measured in one session: 128 registers / 12 warps per SM
+// 2.17 ms back-end, 96 / 20 warps 2.02 ms, 80 / 24 warps with spills 2.05 ms, 64 / 32 warps 2.30 ms)
+#ifndef TFR_WIN_MINBLOCKS
+#define TFR_WIN_MINBLOCKS 10
+#endif
+#ifndef TFR_WIN_THREADS
+#define TFR_WIN_THREADS 64
+#endif
+constexpr int kWinThreads = TFR_WIN_THREADS;
+__global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(const BackParams p)
 {
 	const int stream = blockIdx.y;
 	const int demod = (int)gridDim.z - 1 - (int)blockIdx.z;
@@ -912,6 +941,7 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 	for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 * G < n_win; t0 += gridDim.x * blockDim.x)
 	for (uint32_t w0 = t0 * G; w0 < min(n_win, (t0 + 1) * G); w0++) {
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
+		if (p.long_split && chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;   // winlong_kernel's
 		DemodState s;
 		bool have_lbi = false;   // s.last_bit_idx is the value the reference would hold (given the chain head's start state)
 		for (uint32_t w = w0; w < n_win; w++) {
@@ -944,11 +974,14 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 				} else if (w == w0) {
 					// biquad warm-up over the samples of the preceding windows of this demod (they are the
 					// filter's actual history); reaching window 0 means the true carried state can be used
-					// (three timeouts.  The start-state error itself decays below one ulp within about one timeout - pole
-					// radius 0.905 .. 0.946 - but the two trajectories then sit in a +-1 ulp dead band and only merge when
-					// the output passes through a smaller binade; measured on B200: 12 % of the windows need the
-					// verifier's biquad-only repair after 3 timeouts, 31 % after 2)
-					const uint32_t want = 3u * (uint32_t)cfg.timeout;
+					// (four timeouts.  The start-state error itself decays below one ulp within about one timeout - pole
+					// radius 0.905 .. 0.946 - but the two trajectories then sit in a +-1 ulp dead band and only merge by
+					// chance; measured on B200, windows that need the verifier's biquad-only repair / back-end time of a
+					// 32 x 128 MiB call: 2 timeouts 21 % 2.04 ms, 2.5: 13 % 1.90, 3: 8 % 1.90, 3.5: 5 % 1.85, 4: 3.3 % 1.84)
+#ifndef TFR_WARM_X4
+#define TFR_WARM_X4 12   // warm-up length in quarter timeouts
+#endif
+					const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)cfg.timeout) / 4u;
 					uint32_t have = 0;
 					int v = (int)w;
 					uint32_t from = e.start;
@@ -1052,6 +1085,430 @@ __global__ void __launch_bounds__(64) win_kernel(const BackParams p)
 		atomicMax(&g_winprof[12 + kd], (unsigned long long)(clock64() - prof_t0));
 	}
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// winlong_kernel: one WARP per long window chain.
+//
+// Every lane holds the same copy of the demodulator state and runs the same control flow (warp-uniform); the lanes
+// only differ inside a batch of 32 consecutive samples: coalesced loads, int->double, the filter's input-only
+// terms, truncation, hash terms and the slicer's threshold tests are done by lane = sample; the filter recurrence -
+// four dependent FP64 operations per sample, the only true chain - and the rare edge events (taken in order from a
+// ballot mask) are executed by all lanes redundantly.  A sample then costs ~40 cycles instead of ~500.  The
+// arithmetic, its order and every recorded value are those of run_tfa1_window / run_tfa2_window.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// 32 (n <= 32) consecutive filter steps over devfm[base .. base+n): returns this lane's output y[base+lane] and its
+// discriminator value; lp moves to the state after the batch (uniform).
+__device__ __forceinline__ double biquad_batch(Biquad &lp, const BiquadCoef &k, const int32_t *devfm, uint32_t base, uint32_t n, int lane, int &dv)
+{
+	dv = ((uint32_t)lane < n) ? devfm[base + lane] : 0;
+	const double xd = int_to_double(dv);
+	double x1 = __shfl_up_sync(kFullMask, xd, 1), x2 = __shfl_up_sync(kFullMask, xd, 2);
+	if (lane == 0) {
+		x1 = lp.d1;
+		x2 = lp.d2;
+	} else if (lane == 1) {
+		x2 = lp.d1;
+	}
+	// iir2::step as built (biquad_step): t2 = b0*x[n] + b1*x[n-1], t1 = b2*x[n-2] + a1*y[n-1], y = (t1 + t2) + a2*y[n-2]
+	const double t2 = __dadd_rn(__dmul_rn(k.b0, xd), __dmul_rn(k.b1, x1));
+	const double p2 = __dmul_rn(k.b2, x2);
+	double y0 = lp.y0, y1 = lp.y1, mine = 0.0;
+#pragma unroll 8
+	for (uint32_t j = 0; j < n; j++) {
+		const double t2j = __shfl_sync(kFullMask, t2, (int)j), p2j = __shfl_sync(kFullMask, p2, (int)j);
+		const double t1 = __dadd_rn(p2j, __dmul_rn(k.a1, y0));
+		const double y = __dadd_rn(__dadd_rn(t1, t2j), __dmul_rn(k.a2, y1));
+		y1 = y0;
+		y0 = y;
+		if (lane == (int)j) mine = y;
+	}
+	const double xl = __shfl_sync(kFullMask, xd, (int)n - 1);
+	const double xl2 = __shfl_sync(kFullMask, xd, n >= 2 ? (int)n - 2 : 0);
+	lp.d2 = (n >= 2) ? xl2 : lp.d1;
+	lp.d1 = xl;
+	lp.y0 = y0;
+	lp.y1 = y1;
+	return mine;
+}
+
+static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, const WinEntry &e, DemodState &s, WinRec &rec,
+					 bool resume, bool far, int lane)
+{
+	if (!resume) {
+		tfa2_reset(s);
+		s.sr_cnt = -1;
+		s.sr = 0;
+		s.byte_cnt = 0;
+	}
+	const uint32_t last = min(e.end, c.call_len - 1);
+	const bool taps = c.p->tap_cap != 0;
+	const size_t tbase = ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap;
+	bool have_edge = false;
+	rec.flags &= ~kRecEdge;
+	Biquad lp = s.lp;
+	const BiquadCoef k = cfg.lp;
+	int bitcnt = s.bitcnt, dmin = s.dmin, dmax = s.dmax, offset = s.offset, last_bit = s.last_bit, rssi = s.rssi_i,
+	    lbi = s.last_bit_idx;
+	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
+	uint32_t ha = 0, hb = 0;   // this lane's share of the LdHash sums
+	BitRuns br;
+	br.n = 0;
+	auto drain = [&]() {
+		int i = 0, rem = 0, b = 0;
+		for (;;) {
+			if (rem == 0) {
+				if (i == br.n) break;
+				b = br.run[i] & 1;
+				rem = br.run[i] >> 1;
+				i++;
+				if (rem == 0) continue;
+			}
+			tfa2_bit(s, b);
+			rem--;
+		}
+		br.n = 0;
+	};
+	int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+	int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
+	auto edge = [&](uint32_t m, int ld) {   // as in run_tfa2_window
+		const int index = 2 * (int)(m & (kBlockDec - 1));
+		const int bit = ld > hi ? 1 : 0;
+		if (far && !have_edge) {
+			rec.first_edge = index;
+			rec.first_edge_block = (int)(m >> 13);
+			rec.flags |= kRecEdge;
+			bitcnt++;
+			lbi = index;
+		} else {
+			if (index > lbi + 8) {
+				bitcnt++;
+				const int tdiff = index - lbi;
+				if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
+					const int bit_diff = tdiff / 2;
+					const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
+					if (br.n + 2 > kBitRuns) drain();
+					if (numbits < 32 && numbits > 1) br.run[br.n++] = (uint16_t)(((numbits - 1) << 1) | last_bit);
+					br.run[br.n++] = (uint16_t)((1 << 1) | bit);
+					last_bit = bit;
+				}
+			}
+			if (index - lbi > 2) lbi = index;
+		}
+		have_edge = true;
+	};
+	// demodulator::start of every block that begins inside the window (not at its first sample), applied when the
+	// walk reaches the block's first sample
+	uint32_t nb = ((e.start >> 13) + 1u) << 13;
+	auto cross = [&](uint32_t m) {
+		while (nb <= m) {
+			if (lbi) lbi -= kIdxPerBlock;
+			nb += (uint32_t)kBlockDec;
+		}
+	};
+	for (uint32_t base = e.start; base <= last; base += 32) {
+		const uint32_t n = min(32u, last - base + 1);
+		const bool on = (uint32_t)lane < n;
+		const uint32_t m = base + lane;
+		int dv;
+		const double y = biquad_batch(lp, k, c.devfm, base, n, lane, dv);
+		const int ld = trunc_to_int(y);
+		if (on) {
+			const uint32_t i = m - e.start;
+			ha += (uint32_t)ld * (2u * i + 1u);
+			hb += (uint32_t)ld * (i * i + i + 1u);
+			if (taps) {
+				const uint32_t ti = e.cum + i;
+				if (ti < c.p->tap_cap) {
+					c.p->tap_i32[0][tbase + ti] = dv;
+					c.p->tap_f64[tbase + ti] = y;
+				}
+			}
+		}
+		if (bitcnt < 10) {
+			// the slicer levels still move (tfa2.cpp:365-374): this batch sample by sample, every lane the same steps
+			const uint32_t cwl = on ? c.dec[m] : 0u;
+			for (uint32_t j = 0; j < n; j++) {
+				const int ldj = __shfl_sync(kFullMask, ld, (int)j);
+				const uint32_t cw = __shfl_sync(kFullMask, cwl, (int)j);
+				cross(base + j);
+				if (bitcnt < 10) {
+					if (ldj > dmax || ldj < dmin) {
+						if (ldj > dmax) dmax = (7 * dmax + ldj) / 8;
+						if (ldj < dmin) dmin = (7 * dmin + ldj) / 8;
+						offset = (dmax + dmin) / 2;
+						noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
+						hi = noffset + dmax / 32;
+						lo = noffset + dmin / 32;
+					}
+					if (bitcnt > 4) {
+						const int i = (int)(int16_t)(cw & 0xffff), q = (int)(int16_t)(cw >> 16);
+						const uint32_t sum = (uint32_t)rssi + (uint32_t)(i * i) + (uint32_t)(q * q);
+						rssi = (int)((uint32_t)rssi + (uint32_t)((int)sum / 100));
+					}
+				}
+				if ((ldj > hi || ldj < lo) && (int)(ldj > hi) != last_bit) edge(base + j, ldj);
+			}
+		} else {
+			// levels frozen: the threshold tests of the 32 samples at once; an edge candidate is a sample beyond a level
+			// whose bit differs from last_bit (which only an accepted edge changes), taken in order
+			const bool valid = on && (ld > hi || ld < lo);
+			const int bitl = ld > hi ? 1 : 0;
+			unsigned done = 0;
+			for (;;) {
+				const unsigned mask = __ballot_sync(kFullMask, valid && bitl != last_bit) & ~done;
+				if (!mask) break;
+				const int j = __ffs((int)mask) - 1;
+				done = (2u << j) - 1u;
+				const int ldj = __shfl_sync(kFullMask, ld, j);
+				cross(base + (uint32_t)j);
+				edge(base + (uint32_t)j, ldj);
+			}
+		}
+		cross(base + n - 1);
+	}
+	ha = __reduce_add_sync(kFullMask, ha);
+	hb = __reduce_add_sync(kFullMask, hb);
+	s.lp = lp;
+	s.bitcnt = bitcnt; s.dmin = dmin; s.dmax = dmax; s.offset = offset; s.last_bit = last_bit; s.rssi_i = rssi;
+	s.last_bit_idx = lbi;
+	rec.e_y0 = lp.y0;
+	rec.e_y1 = lp.y1;
+	rec.ld_hash = ((unsigned long long)hb << 32) | ha;
+	rec.lbi_end = lbi;
+	rec.lbi_end_block = (int)(last >> 13);
+	if (!far && have_edge) rec.flags |= kRecEdge;
+	if (last == e.end) {
+		if (br.n + 1 > kBitRuns) drain();
+		br.run[br.n++] = (uint16_t)((16 << 1) | last_bit);   // 16 x store_bit(last_bit) before the flush (tfa2.cpp:430-433)
+	}
+	drain();
+	if (last == e.end) {
+		const bool gate = (cfg.kind == K_TX22) ? (s.byte_cnt >= 7 && s.byte_cnt < 64) : (s.byte_cnt >= 7);
+		int fi = -1;
+		if (lane == 0) {
+			if (gate) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, s.offset);
+			else drop_frame(c, rec.frame_idx);
+		}
+		fi = __shfl_sync(kFullMask, fi, 0);
+		rec.frame_idx = fi;
+		s.sr_cnt = -1;
+		s.sr = 0;
+		s.byte_cnt = 0;
+		tfa2_reset(s);
+		s.timeout_cnt = 0;
+		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan;
+	} else {
+		s.timeout_cnt = (int)(e.end - last);
+		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan | kRecUnfinished;
+	}
+}
+
+static __device__ void run_tfa1_window_w(const WinCtx &c, const WinEntry &e, DemodState &s, WinRec &rec, bool resume, int lane)
+{
+	if (!resume) {
+		s.mark_lvl = 0;
+		s.rssi_i = 0;
+		s.last_bit_idx = 0;
+		s.sr_cnt = -1;
+		s.byte_cnt = 0;
+		s.rdata[10] = 0;
+	}
+	uint32_t head = 0;
+	int nbits = 0;
+	int mark = s.mark_lvl, rssi = s.rssi_i, lbi = s.last_bit_idx;
+	BitRuns br;
+	br.n = 0;
+	auto drain = [&]() {
+		int i = 0, rem = 0, b = 0;
+		for (;;) {
+			if (rem == 0) {
+				if (i == br.n) break;
+				b = br.run[i] & 1;
+				rem = br.run[i] >> 1;
+				i++;
+				if (rem == 0) continue;
+			}
+			if (nbits < 31) head |= (uint32_t)b << nbits;
+			nbits++;
+			tfa1_bit(s, b);
+			rem--;
+		}
+		br.n = 0;
+	};
+	const uint32_t last = min(e.end, c.call_len - 1);
+	const bool taps = c.p->tap_cap != 0;
+	int32_t *tap = taps ? c.p->tap_i32[1] + ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap : nullptr;
+	uint32_t lw0 = (e.start == 0) ? c.prev_last : c.dec[e.start - 1];   // the sample before the batch
+	uint32_t nb = ((e.start >> 13) + 1u) << 13;
+	for (uint32_t base = e.start; base <= last; base += 32) {
+		const uint32_t n = min(32u, last - base + 1);
+		const bool on = (uint32_t)lane < n;
+		const uint32_t m = base + lane;
+		const uint32_t cw = on ? c.dec[m] : 0u;
+		uint32_t lw = __shfl_up_sync(kFullMask, cw, 1);
+		if (lane == 0) lw = lw0;
+		lw0 = __shfl_sync(kFullMask, cw, (int)n - 1);
+		const int dev = fm_dev_nrzs((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
+					    (int)(int16_t)(lw >> 16));
+		if (taps && on) {
+			const uint32_t ti = e.cum + (m - e.start);
+			if (ti < c.p->tap_cap) tap[ti] = dev;
+		}
+		// the peak-hold / decay recurrence and the dip test chain every sample to the one before: all lanes, in order
+		for (uint32_t j = 0; j < n; j++) {
+			const int dj = __shfl_sync(kFullMask, dev, (int)j);
+			const uint32_t mj = base + j;
+			while (nb <= mj) {
+				if (lbi) lbi -= kIdxPerBlock;
+				nb += (uint32_t)kBlockDec;
+			}
+			const int index = 2 * (int)(mj & (kBlockDec - 1));
+			if (dj > mark) mark = dj;
+			else mark = __double2int_rz(__dmul_rn((double)mark, 0.95));
+			if (mark > rssi) rssi = mark;
+			if (dj < mark / 2) {
+				if (lbi) {
+					const int gap = index - lbi;
+					if (gap > 4) {
+						if (br.n + 2 > kBitRuns) drain();
+						if (gap >= 22) br.run[br.n++] = (uint16_t)(((((gap - 22) / 20) + 1) << 1) | 1);
+						br.run[br.n++] = (uint16_t)(1 << 1);
+					}
+				}
+				if (index - lbi > 2) lbi = index;
+			}
+		}
+	}
+	drain();
+	s.mark_lvl = mark;
+	s.rssi_i = rssi;
+	s.last_bit_idx = lbi;
+	rec.head31 = head;
+	rec.nbits = nbits;
+	rec.sr_final = s.sr;
+	if (last == e.end) {
+		int fi = -1;
+		if (lane == 0) {
+			if (s.byte_cnt >= 10) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, 0);
+			else drop_frame(c, rec.frame_idx);
+		}
+		fi = __shfl_sync(kFullMask, fi, 0);
+		rec.frame_idx = fi;
+		rec.flags = (rec.flags & kRecExact) | kRecRan;
+	} else {
+		s.timeout_cnt = (int)(e.end - last);
+		rec.flags = (rec.flags & kRecExact) | kRecRan | kRecUnfinished;
+	}
+}
+
+constexpr int kLongWarps = 4;
+__global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackParams p)
+{
+	const int lane = threadIdx.x & 31;
+	const int stream = blockIdx.y;
+	const int demod = (int)gridDim.z - 1 - (int)blockIdx.z;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	if (cfg.kind == K_WHB) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	const uint32_t n_win = p.wincnt[stream].n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	const bool chains = (cfg.kind != K_TFA1);
+	const uint32_t n_warps = gridDim.x * kLongWarps;
+	for (uint32_t w0 = blockIdx.x * kLongWarps + (threadIdx.x >> 5); w0 < n_win; w0 += n_warps) {   // warp-uniform
+		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;
+		if (!chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;
+		// the chain loop of win_kernel, every lane the same
+		DemodState s;
+		bool have_lbi = false;
+		for (uint32_t w = w0; w < n_win; w++) {
+			if (w != w0 && (!chains || chain_head(wl, w, cfg.timeout))) break;
+			const WinEntry e = wl[w];
+			if (e.start >= c.call_len) break;
+			WinRec rec;
+			rec.frame_idx = -1;
+			rec.flags = 0;
+			rec.first_edge = rec.first_edge_block = 0;
+			rec.pad = 0;
+			rec.lbi_in = 0;
+			rec.head31 = rec.sr_final = 0;
+			rec.nbits = 0;
+			rec.lbi_end = rec.lbi_end_block = 0;
+			rec.u_y0 = rec.u_y1 = rec.e_y0 = rec.e_y1 = 0.0;
+			rec.ld_hash = 0;
+			rec.pad3 = 0;
+			const bool cont = (e.flags & kWinCont) != 0;
+			if (w == 0) {
+				s = st->d[demod];
+				if (!cont && cfg.kind != K_TFA1) s.last_bit_idx = lbi_at_block(s.last_bit_idx, -1, (int)(e.start >> 13));
+				if (cont && s.last_bit_idx) s.last_bit_idx -= kIdxPerBlock;
+				rec.flags = kRecExact;
+				have_lbi = true;
+			} else if (w == w0) {
+				memset(&s, 0, sizeof(s));
+			}
+			if (cfg.kind == K_TFA1) {
+				run_tfa1_window_w(c, e, s, rec, cont, lane);
+			} else {
+				bool far = true;
+				if (w == 0) {
+					far = false;
+				} else if (w == w0) {
+					// the same warm-up history as win_kernel, filtered in batches of 32
+					const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)cfg.timeout) / 4u;
+					uint32_t have = 0;
+					int v = (int)w;
+					uint32_t from = e.start;
+					while (v > 0 && have < want) {
+						v--;
+						const uint32_t len = wl[v].end - wl[v].start + 1;
+						if (have + len >= want && v > 0) {
+							from = wl[v].end + 1 - (want - have);
+							have = want;
+						} else {
+							from = wl[v].start;
+							have += len;
+						}
+					}
+					Biquad lp;
+					lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
+					if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
+					for (int u = v; u < (int)w; u++) {
+						const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
+						for (uint32_t base = a; base <= b; base += 32) {
+							int dv;
+							biquad_batch(lp, cfg.lp, c.devfm, base, min(32u, b - base + 1), lane, dv);
+						}
+					}
+					s.lp = lp;
+				} else {
+					far = !have_lbi;
+					memset(s.rdata, 0, sizeof(s.rdata));
+					if (have_lbi) {
+						const uint32_t plast = min(wl[w - 1].end, c.call_len - 1);
+						s.last_bit_idx = lbi_at_block(s.last_bit_idx, (int)(plast >> 13), (int)(e.start >> 13));
+						rec.flags |= kRecLbiIn;
+						rec.lbi_in = s.last_bit_idx;
+					}
+				}
+				rec.u_y0 = s.lp.y0;
+				rec.u_y1 = s.lp.y1;
+				run_tfa2_window_w(c, cfg, e, s, rec, cont, far, lane);
+				if (rec.flags & kRecEdge) have_lbi = true;
+			}
+			if (lane == 0) {
+				if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+				rl[w] = rec;
+			}
+			if (rec.flags & kRecUnfinished) break;
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1449,7 +1906,7 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 		cudaStreamSynchronize(s);
 		cudaMemcpyToSymbol(g_winprof, z, sizeof(z));
 		cudaMemcpyToSymbol(g_slprof, z, 8 * sizeof(unsigned long long));
-		win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+		win_kernel<<<win_grid(p, n_demods, kWinThreads), kWinThreads, 0, s>>>(p);
 		cudaStreamSynchronize(s);
 		cudaMemcpyFromSymbol(r, g_winprof, sizeof(r));
 		unsigned long long q[8];
@@ -1460,7 +1917,15 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 		return cudaGetLastError();
 	}
 #endif
-	win_kernel<<<win_grid(p, n_demods, 64), 64, 0, s>>>(p);
+	win_kernel<<<win_grid(p, n_demods, kWinThreads), kWinThreads, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	// one warp per window slot; nearly all of them leave at once (not a chain head, or not long)
+	int gx = (p.max_blocks * 2 + kLongWarps - 1) / kLongWarps;
+	gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);   // the warps stride over the window list
+	winlong_kernel<<<dim3(gx, p.n_streams, n_demods), 32 * kLongWarps, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s)

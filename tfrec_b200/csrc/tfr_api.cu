@@ -20,6 +20,7 @@ cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_st
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
+cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
@@ -102,6 +103,9 @@ struct tfr_handle {
 	Slot slot[2];
 	int cur = 0;                       // slot of the most recent tfr_process
 	cudaStream_t stream_be = nullptr;  // back-end stream
+	cudaStream_t stream_long = nullptr; // winlong_kernel (the long window chains, one warp each) beside win_kernel; high priority
+	cudaEvent_t long_ev[2] = { nullptr, nullptr };
+	bool long_split = true;
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
 	cudaStream_t stream_fe2 = nullptr;    // odd front-end chunks: consecutive chunk launches overlap their tails
 	cudaEvent_t chunk_ev[8] = { nullptr };
@@ -199,6 +203,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (!h) return;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->stream_long) cudaStreamSynchronize(h->stream_long);
 	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
@@ -217,6 +222,8 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->span0) cudaEventDestroy(h->span0);
 	if (h->span1) cudaEventDestroy(h->span1);
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
+	if (h->stream_long) cudaStreamDestroy(h->stream_long);
+	for (auto &e : h->long_ev) if (e) cudaEventDestroy(e);
 	if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
 	if (h->stream_fe2) cudaStreamDestroy(h->stream_fe2);
 	for (auto e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -276,6 +283,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		int prio_lo = 0, prio_hi = 0;
 		CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 		CUH(cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi));
+		CUH(cudaStreamCreateWithPriority(&h->stream_long, cudaStreamNonBlocking, prio_hi));
+		for (auto &e : h->long_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		if (getenv("TFR_NO_LONG")) h->long_split = false;   // experiments: every chain in the thread-per-chain kernel
 	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -329,6 +339,7 @@ static int sync_all(tfr_handle *h)
 	CU(cudaStreamSynchronize(h->stream));
 	CU(cudaStreamSynchronize(h->stream_fe2));
 	CU(cudaStreamSynchronize(h->stream_walk));
+	CU(cudaStreamSynchronize(h->stream_long));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
 }
@@ -606,8 +617,18 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		if (h->has_fm) { CU(launch_devfm(bp, sb)); h->stats.kernel_launches += 1; }
 		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
 		if (has_win) {
+			if (h->long_split) {
+				// the long window chains (telegrams, retriggered noise), one warp each, first and beside the rest
+				bp.long_split = 1;
+				CU(cudaEventRecord(h->long_ev[0], sb));
+				CU(cudaStreamWaitEvent(h->stream_long, h->long_ev[0], 0));
+				CU(launch_winlong(bp, h->dcfg.n_demods, h->stream_long));
+				CU(cudaEventRecord(h->long_ev[1], h->stream_long));
+				h->stats.kernel_launches += 1;
+			}
 			CU(launch_win(bp, h->dcfg.n_demods, sb));
 			h->stats.kernel_launches += 1;
+			if (h->long_split) CU(cudaStreamWaitEvent(sb, h->long_ev[1], 0));
 		}
 		if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, sb)); h->stats.kernel_launches += 1; }
 		CU(launch_verify(bp, h->dcfg.n_demods, sb));

@@ -251,6 +251,7 @@ struct BackParams {
 	int32_t *devfm;          // fm_dev per stored sample, direct mapped like dec
 	int demod;               // kernels that run per registered demod: which one
 	int max_blocks;
+	int long_split;          // 1: win_kernel leaves the long window chains to winlong_kernel
 };
 
 }  // namespace tfr

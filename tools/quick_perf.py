@@ -16,10 +16,14 @@ def main():
     nbytes = mib << 20
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     bufs = []
-    for s in range(n_streams):
-        x = torch.randn(nbytes, device="cuda", generator=g) * sigma + 128.0
-        bufs.append(x.round_().clamp_(0, 255).to(torch.uint8))
-        del x
+    if os.environ.get("TFR_QP_BENCH"):   # the bench workload (telegram every 10 s) instead of noise only
+        import bench
+        bufs = [bench.make_stream_gpu(s, nbytes, sigma, torch.device("cuda", 0))[0] for s in range(n_streams)]
+    else:
+        for s in range(n_streams):
+            x = torch.randn(nbytes, device="cuda", generator=g) * sigma + 128.0
+            bufs.append(x.round_().clamp_(0, 255).to(torch.uint8))
+            del x
     rx = tb.Receiver(types=types, thresh=thresh, n_streams=n_streams)
     for it in range(4):
         for s in range(n_streams):
