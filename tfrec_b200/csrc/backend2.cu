@@ -1099,11 +1099,11 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned kFullMask = 0xffffffffu;
 
-// 32 (n <= 32) consecutive filter steps over devfm[base .. base+n): returns this lane's output y[base+lane] and its
-// discriminator value; lp moves to the state after the batch (uniform).
-__device__ __forceinline__ double biquad_batch(Biquad &lp, const BiquadCoef &k, const int32_t *devfm, uint32_t base, uint32_t n, int lane, int &dv)
+// n <= 32 consecutive filter steps; dv = this lane's discriminator value devfm[base+lane] (0 for lane >= n), loaded by
+// the caller one batch ahead (an L2/HBM round trip is about as long as the 32 serial steps).  Returns this lane's
+// output y[base+lane]; lp moves to the state after the batch (uniform).
+__device__ __forceinline__ double biquad_batch(Biquad &lp, const BiquadCoef &k, int dv, uint32_t n, int lane)
 {
-	dv = ((uint32_t)lane < n) ? devfm[base + lane] : 0;
 	const double xd = int_to_double(dv);
 	double x1 = __shfl_up_sync(kFullMask, xd, 1), x2 = __shfl_up_sync(kFullMask, xd, 2);
 	if (lane == 0) {
@@ -1116,14 +1116,27 @@ __device__ __forceinline__ double biquad_batch(Biquad &lp, const BiquadCoef &k, 
 	const double t2 = __dadd_rn(__dmul_rn(k.b0, xd), __dmul_rn(k.b1, x1));
 	const double p2 = __dmul_rn(k.b2, x2);
 	double y0 = lp.y0, y1 = lp.y1, mine = 0.0;
-#pragma unroll 8
-	for (uint32_t j = 0; j < n; j++) {
-		const double t2j = __shfl_sync(kFullMask, t2, (int)j), p2j = __shfl_sync(kFullMask, p2, (int)j);
-		const double t1 = __dadd_rn(p2j, __dmul_rn(k.a1, y0));
-		const double y = __dadd_rn(__dadd_rn(t1, t2j), __dmul_rn(k.a2, y1));
-		y1 = y0;
-		y0 = y;
-		if (lane == (int)j) mine = y;
+	if (n == 32) {
+		// the common case, fully unrolled: the 64 broadcasts have constant source lanes and no dependence on the
+		// recurrence, so they are all issued ahead of it and a step costs its four dependent FP64 operations
+#pragma unroll
+		for (int j = 0; j < 32; j++) {
+			const double t2j = __shfl_sync(kFullMask, t2, j), p2j = __shfl_sync(kFullMask, p2, j);
+			const double t1 = __dadd_rn(p2j, __dmul_rn(k.a1, y0));
+			const double y = __dadd_rn(__dadd_rn(t1, t2j), __dmul_rn(k.a2, y1));
+			y1 = y0;
+			y0 = y;
+			if (lane == j) mine = y;
+		}
+	} else {
+		for (uint32_t j = 0; j < n; j++) {
+			const double t2j = __shfl_sync(kFullMask, t2, (int)j), p2j = __shfl_sync(kFullMask, p2, (int)j);
+			const double t1 = __dadd_rn(p2j, __dmul_rn(k.a1, y0));
+			const double y = __dadd_rn(__dadd_rn(t1, t2j), __dmul_rn(k.a2, y1));
+			y1 = y0;
+			y0 = y;
+			if (lane == (int)j) mine = y;
+		}
 	}
 	const double xl = __shfl_sync(kFullMask, xd, (int)n - 1);
 	const double xl2 = __shfl_sync(kFullMask, xd, n >= 2 ? (int)n - 2 : 0);
@@ -1208,12 +1221,14 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 			nb += (uint32_t)kBlockDec;
 		}
 	};
+	int dvn = (e.start + lane <= last) ? c.devfm[e.start + lane] : 0;
 	for (uint32_t base = e.start; base <= last; base += 32) {
 		const uint32_t n = min(32u, last - base + 1);
 		const bool on = (uint32_t)lane < n;
 		const uint32_t m = base + lane;
-		int dv;
-		const double y = biquad_batch(lp, k, c.devfm, base, n, lane, dv);
+		const int dv = dvn;
+		dvn = (m + 32 <= last) ? c.devfm[m + 32] : 0;   // the next batch, in flight during this one
+		const double y = biquad_batch(lp, k, dv, n, lane);
 		const int ld = trunc_to_int(y);
 		if (on) {
 			const uint32_t i = m - e.start;
@@ -1343,11 +1358,13 @@ static __device__ void run_tfa1_window_w(const WinCtx &c, const WinEntry &e, Dem
 	int32_t *tap = taps ? c.p->tap_i32[1] + ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap : nullptr;
 	uint32_t lw0 = (e.start == 0) ? c.prev_last : c.dec[e.start - 1];   // the sample before the batch
 	uint32_t nb = ((e.start >> 13) + 1u) << 13;
+	uint32_t cwn = (e.start + lane <= last) ? c.dec[e.start + lane] : 0u;
 	for (uint32_t base = e.start; base <= last; base += 32) {
 		const uint32_t n = min(32u, last - base + 1);
 		const bool on = (uint32_t)lane < n;
 		const uint32_t m = base + lane;
-		const uint32_t cw = on ? c.dec[m] : 0u;
+		const uint32_t cw = cwn;
+		cwn = (m + 32 <= last) ? c.dec[m + 32] : 0u;   // the next batch, in flight during this one
 		uint32_t lw = __shfl_up_sync(kFullMask, cw, 1);
 		if (lane == 0) lw = lw0;
 		lw0 = __shfl_sync(kFullMask, cw, (int)n - 1);
@@ -1481,9 +1498,11 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 					if (v == 0 && from == wl[0].start) lp = st->d[demod].lp;
 					for (int u = v; u < (int)w; u++) {
 						const uint32_t a = (u == v) ? from : wl[u].start, b = wl[u].end;
+						int dvn = (a + lane <= b) ? c.devfm[a + lane] : 0;
 						for (uint32_t base = a; base <= b; base += 32) {
-							int dv;
-							biquad_batch(lp, cfg.lp, c.devfm, base, min(32u, b - base + 1), lane, dv);
+							const int dv = dvn;
+							dvn = (base + 32 + lane <= b) ? c.devfm[base + 32 + lane] : 0;
+							biquad_batch(lp, cfg.lp, dv, min(32u, b - base + 1), lane);
 						}
 					}
 					s.lp = lp;

@@ -7,8 +7,9 @@ idx = [i for i, n in enumerate(names) if 'parse_kernel' in n]
 a, b = (idx[-2] + 1, idx[-1] + 1) if len(idx) > 1 else (0, len(rows))
 d = collections.OrderedDict()
 for r, n in zip(rows[a:b], names[a:b]):
-    if not n.startswith('tfr::'):
+    if not (n.startswith('tfr::') or n.split('<')[0].endswith('_kernel')):   # the namespace is dropped when ncu ran with -k
         continue
+    n = n if n.startswith('tfr::') else 'tfr::' + n
     d.setdefault(n, [0, 0.0])
     d[n][0] += 1
     d[n][1] += float(r[-1])
