@@ -60,6 +60,21 @@ def test_no_cpu_fallback_without_device(lib):
         tb.Receiver()
 
 
+def test_downconvert_validates_arguments_without_a_device(lib):
+    import numpy as np
+    iq = np.full(64, 128, np.uint8)
+    out = np.zeros(64, np.int16)
+    call = lambda passes, mem=tb.MEM_HOST, n=iq.size: lib.tfr_downconvert(0, iq.ctypes.data, n, passes, 0, out.ctypes.data, mem, 1, None)
+    assert call(0) == -1 and b"passes" in lib.tfr_last_error()        # TFR_E_INVAL
+    assert call(9) == -1
+    assert call(2, mem=7) == -1
+    assert call(2, n=2) == -1                                           # fewer than two IQ pairs
+    assert lib.tfr_downconvert(0, None, 64, 2, 0, out.ctypes.data, tb.MEM_HOST, 1, None) == -1
+    import torch
+    if not torch.cuda.is_available():
+        assert call(2) == -2 and b"no CPU fallback" in lib.tfr_last_error()   # TFR_E_NODEVICE
+
+
 def test_product_does_not_touch_the_oracle():
     # the product path must never import, link or execute anything under oracle/
     for dirpath, _, files in os.walk(os.path.join(ROOT, "tfrec_b200")):
