@@ -228,10 +228,9 @@ class Receiver:
     def parse_bytes(self, sensor_type, data: bytes):
         f = Frame()
         recs = (Record * 8)()
-        n = self.L.tfr_parse_bytes(self.h, sensor_type, data, len(data), C.byref(f), recs, 8)
-        if n == -1:
+        n = _check(self.L.tfr_parse_bytes(self.h, sensor_type, data, len(data), C.byref(f), recs, 8))
+        if f.status == -1:      # below the length gate of the type's flush(): the reference does nothing
             return None, []
-        _check(n)
         out = []
         for r in recs[:n]:
             d = {"stream": 0, "type": r.type, "id": r.id, "temp": r.temp, "humidity": r.humidity, "alarm": r.alarm,

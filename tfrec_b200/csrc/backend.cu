@@ -622,7 +622,7 @@ __global__ void parse_kernel(const BackParams p)
 	__shared__ uint8_t s_r[8][kMaxRdata + 8];
 	uint8_t *r = s_r[threadIdx.x >> 5];
 	for (uint32_t fi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; fi < n_frames; fi += n_warps) {
-	if (p.frames[fi].status >= 0) continue;   // parsed by an earlier tfr_process
+	if (p.frames[fi].status != -1) continue;   // >= 0: parsed by an earlier tfr_process; -2: retired by the verifier (dead)
 	DevFrame *f = p.frames + fi;
 	__syncwarp();
 	for (int k = lane; k < kMaxRdata; k += 32) r[k] = f->rdata[k];

@@ -579,8 +579,13 @@ static __device__ void run_tfa1_window(const WinCtx &c, const WinEntry &e, Demod
 				const int gap = index - lbi;
 				if (gap > 4) {
 					// `for (n = 22; n <= gap; n += 20) bit(1); bit(0);`  (tfa1.cpp:168-173)
-					if (br.n + 2 > kBitRuns) drain();
-					if (gap >= 22) br.run[br.n++] = (uint16_t)(((((gap - 22) / 20) + 1) << 1) | 1);
+					// a run entry holds 15 bits of count: a gap beyond ~655k index units (a carrier held above the
+					// threshold for 0.85 s without a dip) is split into several entries
+					for (int ones = (gap >= 22) ? (gap - 22) / 20 + 1 : 0; ones > 0; ones -= 32767) {
+						if (br.n + 2 > kBitRuns) drain();
+						br.run[br.n++] = (uint16_t)((min(ones, 32767) << 1) | 1);
+					}
+					if (br.n + 1 > kBitRuns) drain();
 					br.run[br.n++] = (uint16_t)(1 << 1);
 				}
 			}
@@ -1390,8 +1395,11 @@ static __device__ void run_tfa1_window_w(const WinCtx &c, const WinEntry &e, Dem
 				if (lbi) {
 					const int gap = index - lbi;
 					if (gap > 4) {
-						if (br.n + 2 > kBitRuns) drain();
-						if (gap >= 22) br.run[br.n++] = (uint16_t)(((((gap - 22) / 20) + 1) << 1) | 1);
+						for (int ones = (gap >= 22) ? (gap - 22) / 20 + 1 : 0; ones > 0; ones -= 32767) {   // as in run_tfa1_window
+							if (br.n + 2 > kBitRuns) drain();
+							br.run[br.n++] = (uint16_t)((min(ones, 32767) << 1) | 1);
+						}
+						if (br.n + 1 > kBitRuns) drain();
 						br.run[br.n++] = (uint16_t)(1 << 1);
 					}
 				}

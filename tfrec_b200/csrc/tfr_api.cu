@@ -137,6 +137,7 @@ struct tfr_handle {
 	tfr_stats stats;
 	// host copies of results
 	bool results_valid = false;
+	bool overflow_reported = false;    // TFR_E_OVERFLOW is returned by one poll, then the truncated results are served
 	std::vector<tfr_frame> frames;
 	std::vector<tfr_record> records;
 };
@@ -714,8 +715,12 @@ static int fetch_results(tfr_handle *h)
 	if (nf) CU(cudaMemcpy(df.data(), h->d_frames, sizeof(DevFrame) * nf, cudaMemcpyDeviceToHost));
 	if (nr) CU(cudaMemcpy(dr.data(), h->d_records, sizeof(DevRecord) * nr, cudaMemcpyDeviceToHost));
 	// reference output order: time, then registration order (SURVEY.md §8b "Threading")
-	std::vector<uint32_t> order(nf);
-	for (uint32_t k = 0; k < nf; k++) order[k] = k;
+	// a slot the verifier retired (a re-run with the true carry-in no longer passed the byte_cnt gate, status -2)
+	// is not a flush the reference performs: it never reaches the caller
+	std::vector<uint32_t> order;
+	order.reserve(nf);
+	for (uint32_t k = 0; k < nf; k++)
+		if (df[k].status != -2) order.push_back(k);
 	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
 		const DevFrame &x = df[a], &y = df[b];
 		if (x.stream != y.stream) return x.stream < y.stream;
@@ -776,7 +781,11 @@ static int fetch_results(tfr_handle *h)
 	if (getenv("TFR_DEBUG")) fprintf(stderr, "[tfr] windows %llu par_cheap %u edge_par %u | verify: checked %u cheap %u full %u sr %u\n", c.n_windows, c.par_cheap, c.rerun_edge, c.ver_checked, c.ver_cheap, c.ver_full, c.rerun_sr);
 	h->stats.reruns_edge = c.rerun_edge;
 	h->results_valid = true;
-	if (c.overflow) return fail(TFR_E_OVERFLOW, "frame/record buffer overflowed; raise tfr_config.max_frames");
+	if (c.overflow && !h->overflow_reported) {
+		h->overflow_reported = true;
+		return fail(TFR_E_OVERFLOW, "a frame/record/window buffer overflowed: results are truncated; raise tfr_config.max_frames "
+					    "(reported once; polling again returns the truncated results)");
+	}
 	return TFR_OK;
 }
 
@@ -784,7 +793,7 @@ extern "C" __attribute__((visibility("default"))) long tfr_poll_frames(tfr_handl
 {
 	if (!h) return fail(TFR_E_INVAL, "tfr_poll_frames: null handle");
 	int rc = fetch_results(h);
-	if (rc && rc != TFR_E_OVERFLOW) return rc;
+	if (rc) return rc;
 	if (!out) return (long)h->frames.size();
 	const size_t n = std::min(cap, h->frames.size());
 	if (n) memcpy(out, h->frames.data(), n * sizeof(tfr_frame));
@@ -795,7 +804,7 @@ extern "C" __attribute__((visibility("default"))) long tfr_poll_records(tfr_hand
 {
 	if (!h) return fail(TFR_E_INVAL, "tfr_poll_records: null handle");
 	int rc = fetch_results(h);
-	if (rc && rc != TFR_E_OVERFLOW) return rc;
+	if (rc) return rc;
 	if (!out) return (long)h->records.size();
 	const size_t n = std::min(cap, h->records.size());
 	if (n) memcpy(out, h->records.data(), n * sizeof(tfr_record));
@@ -819,6 +828,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_clear_results(tfr_hand
 	h->frames.clear();
 	h->records.clear();
 	h->results_valid = false;
+	h->overflow_reported = false;
 	return TFR_OK;
 }
 
@@ -985,7 +995,17 @@ extern "C" __attribute__((visibility("default"))) int tfr_parse_bytes(tfr_handle
 	else if (kind == K_TX22) gate = bc >= 7 && bc < 64;
 	else if (kind == K_WHB) gate = !(bc < 11 || bc > 60);
 	else gate = bc >= 7;
-	if (!gate) return -1;
+	if (!gate) {
+		// flush() does nothing below its length gate: no frame, no records (frame->status -1 says so; 0 is not an error)
+		if (frame) {
+			memset(frame, 0, sizeof(*frame));
+			frame->type = type;
+			frame->status = -1;
+			frame->byte_cnt = bc;
+			frame->pos = -1;
+		}
+		return 0;
+	}
 	DevFrame f;
 	memset(&f, 0, sizeof(f));
 	f.stream = 0;
@@ -1002,26 +1022,31 @@ extern "C" __attribute__((visibility("default"))) int tfr_parse_bytes(tfr_handle
 	Counters c;
 	memset(&c, 0, sizeof(c));
 	c.n_frames = 1;
-	CU(cudaMalloc(&d_f, sizeof(DevFrame)));
-	CU(cudaMalloc(&d_r, sizeof(DevRecord) * 8));
-	CU(cudaMalloc(&d_c, sizeof(Counters)));
-	CU(cudaMemcpy(d_f, &f, sizeof(f), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(d_c, &c, sizeof(c), cudaMemcpyHostToDevice));
-	BackParams bp;
-	memset(&bp, 0, sizeof(bp));
-	bp.cfg = h->d_cfg;
-	bp.frames = d_f;
-	bp.records = d_r;
-	bp.counters = d_c;
-	bp.max_frames = 1;
-	bp.max_records = 8;
-	CU(launch_parse(bp, h->stream));
-	h->stats.kernel_launches += 1;
-	CU(cudaStreamSynchronize(h->stream));
 	DevRecord r[8];
-	CU(cudaMemcpy(&f, d_f, sizeof(f), cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(r, d_r, sizeof(r), cudaMemcpyDeviceToHost));
-	cudaFree(d_f); cudaFree(d_r); cudaFree(d_c);
+	{
+		cudaError_t e = cudaMalloc(&d_f, sizeof(DevFrame));
+		if (e == cudaSuccess) e = cudaMalloc(&d_r, sizeof(DevRecord) * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&d_c, sizeof(Counters));
+		if (e == cudaSuccess) e = cudaMemcpy(d_f, &f, sizeof(f), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(d_c, &c, sizeof(c), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) {
+			BackParams bp;
+			memset(&bp, 0, sizeof(bp));
+			bp.cfg = h->d_cfg;
+			bp.frames = d_f;
+			bp.records = d_r;
+			bp.counters = d_c;
+			bp.max_frames = 1;
+			bp.max_records = 8;
+			e = launch_parse(bp, h->stream);
+			h->stats.kernel_launches += 1;
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (e == cudaSuccess) e = cudaMemcpy(&f, d_f, sizeof(f), cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess) e = cudaMemcpy(r, d_r, sizeof(r), cudaMemcpyDeviceToHost);
+		cudaFree(d_f); cudaFree(d_r); cudaFree(d_c);   // on every path
+		if (e != cudaSuccess) { cudaGetLastError(); return fail(TFR_E_CUDA, std::string("tfr_parse_bytes: ") + cudaGetErrorString(e)); }
+	}
 	if (frame) {
 		memset(frame, 0, sizeof(*frame));
 		frame->type = type;

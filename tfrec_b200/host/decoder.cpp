@@ -135,24 +135,40 @@ std::string tfr_format_line(const tfr_frame &f, const sensordata_t *recs, int n_
 				append(s, " PTEMP_IN %g PHUM_IN %i PTEMP_OUT %g PHUM_OUT %i", t11(be(m + 10, 2)), be(m + 12, 2) & 0xff,
 				       t11(be(m + 14, 2)), be(m + 16, 2) & 0xff);
 			break;
-		case 0x08: append(s, "WHB08 ID %llx cnt %i", pid, be(m + 4, 2)); break;
-		case 0x0b: {
-			const unsigned v = be(m + 3, 4);
-			const float dir = 22.5 * (v >> 28), speed = (((v >> 16) & 0xff) + 256 * ((v >> 25) & 1)) * 0.1,
-				    gust = (((v >> 8) & 0xff) + 256 * ((v >> 24) & 1)) * 0.1;
-			append(s, "WHB0b ID %llx #%i DIR %f SPEED %f GUST %f time %i", pid, 0, dir, speed, gust, (v & 0xff) * 2);
+		case 0x08: {
+			static const unsigned tu[4] = { 86400, 3600, 60, 1 };   // timeunit_tab, whb.cpp:65-70
+			append(s, "WHB08 ID %llx cnt %i", pid, be(m + 4, 2));
+			if (dbg > 1)   // whb.cpp:311-312, one line per stored time
+				for (int i = 0; i < 10; i++) {
+					const unsigned x = be(m + 6 + 2 * i, 2);
+					append(s, "\nWHB08 ID %llx #%i time %i", pid, i, tu[(x >> 14) & 3] * (x & 0x3fff));
+				}
 			break;
 		}
+		case 0x0b:
+			for (int i = 0; i < 6 && (i == 0 || dbg > 0); i++) {   // whb.cpp:344-348: the history entries with -D
+				const unsigned v = be(m + 3 + 4 * i, 4);
+				const float dir = 22.5 * (v >> 28), speed = (((v >> 16) & 0xff) + 256 * ((v >> 25) & 1)) * 0.1,
+					    gust = (((v >> 8) & 0xff) + 256 * ((v >> 24) & 1)) * 0.1;
+				append(s, "%sWHB0b ID %llx #%i DIR %f SPEED %f GUST %f time %i", i ? "\n" : "", pid, i, dir, speed, gust, (v & 0xff) * 2);
+			}
+			break;
 		case 0x10: {
 			static const unsigned tu[4] = { 86400, 3600, 60, 1 };
-			const unsigned x = be(m + 2, 2);
-			append(s, "WHB10 ID %llx #%i %i %i", pid, 0, x >> 15, tu[(x >> 13) & 3] * (x & 0x1fff));
+			for (int i = 0; i < 4 && (i == 0 || dbg > 0); i++) {   // whb.cpp:376-379
+				const unsigned x = be(m + 2 + 2 * i, 2);
+				append(s, "%sWHB10 ID %llx #%i %i %i", i ? "\n" : "", pid, i, x >> 15, tu[(x >> 13) & 3] * (x & 0x1fff));
+			}
 			break;
 		}
 		case 0x11:
 			append(s, "WHB11 %llx TEMP1 %g HUM1 %i TEMP2 %g HUM2 %i TEMP3 %g HUM3 %i TEMP_IN %g HUM_IN %i", pid, t11(be(m + 2, 2)),
 			       be(m + 4, 2) & 0xff, t11(be(m + 6, 2)), be(m + 8, 2) & 0xff, t11(be(m + 10, 2)), be(m + 12, 2) & 0xff,
 			       t11(be(m + 14, 2)), be(m + 16, 2) & 0xff);
+			if (dbg > 1)   // whb.cpp:410-412
+				append(s, " PTEMP1 %g PHUM1 %i PTEMP2 %g PHUM2 %i PTEMP3 %g PHUM3 %i PTEMP_IN %g PHUM_IN %i", t11(be(m + 18, 2)),
+				       be(m + 20, 2) & 0xff, t11(be(m + 22, 2)), be(m + 24, 2) & 0xff, t11(be(m + 26, 2)), be(m + 28, 2) & 0xff,
+				       t11(be(m + 30, 2)), be(m + 32, 2) & 0xff);
 			break;
 		case 0x12:
 			append(s, "WHB12 %llx TEMP %g HUM %i HUM3h %i HUM24h %i HUM7d %i HUM30d %i", pid, t11(be(m + 6, 2)), m[8] & 0x7f,
@@ -201,13 +217,13 @@ void decoder::flush(int rssi, int offset)
 	tfr_frame f;
 	tfr_record rec[8];
 	const int n = tfr_parse_bytes(handle, (int)type, rdata, byte_cnt, &f, rec, 8);
-	if (n == -1) {   // shorter than the type's minimum frame: the reference's flush() does nothing either
-		byte_cnt = 0;
-		synced = 0;
-		return;
-	}
 	if (n < 0) {
 		fprintf(stderr, "tfr_parse_bytes: %s\n", tfr_last_error());
+		return;
+	}
+	if (f.status == -1) {   // shorter than the type's minimum frame: the reference's flush() does nothing either
+		byte_cnt = 0;
+		synced = 0;
 		return;
 	}
 	f.rssi = rssi;
@@ -256,7 +272,14 @@ void decoder::deliver_frame(const tfr_frame &f, sensordata_t *recs, int n_recs)
 		return;
 	}
 	bad++;
-	if (!dbg) return;
+	// whb.cpp:505-508 prints this at dbg >= 0, i.e. also without -D
+	uint32_t whb_unknown_init = 0;
+	const bool whb_unknown = type == TFA_WHB && f.status != 1 && r[4] <= 60 && !whb_init(r[5], whb_unknown_init);
+	if (whb_unknown && dbg >= 0) printf("WHB: Probably unsupported sensor type %02x! Please report\n", r[5]);
+	if (!dbg) {
+		fflush(stdout);
+		return;
+	}
 	if (type == TFA_1) {
 		if (f.status == 1) printf("TFA1 BAD %i RSSI %i (CRC %02x %02x)\n", bad, f.rssi, r[10], crc8_31(r + 2, 8));
 		else printf("TFA1 BAD %i RSSI %i (SANITY)\n", bad, f.rssi);
@@ -275,11 +298,8 @@ void decoder::deliver_frame(const tfr_frame &f, sensordata_t *recs, int n_recs)
 		if (f.status == 1 && plen <= 60 && whb_init(r[5], init))
 			printf("\nWHB BAD %i RSSI %i (CRC is %08x, should be %08x, len %i, plen %i)\n", bad, f.rssi, be(r + plen, 4),
 			       crc32_msb(r + 4, plen > 4 ? plen - 4 : 0, init), f.byte_cnt, plen);
-		else {
-			if (plen <= 60 && !whb_init(r[5], init) && dbg >= 0)
-				printf("WHB: Probably unsupported sensor type %02x! Please report\n", r[5]);
+		else
 			printf("\nWHB BAD %i RSSI %i (SANITY)\n", bad, f.rssi);
-		}
 	}
 	fflush(stdout);
 }

@@ -1,5 +1,6 @@
-// engine.h - sample pump (reference engine.h:19-44).  Same constructor and run(); only -L replay (dumpmode -1)
-// is supported: live capture needs librtlsdr, which is outside the accelerated path.
+// engine.h - sample pump (reference engine.h:19-44).  Same constructor and run(): -L replay (dumpmode -1), and a
+// live mode fed with raw u8 IQ on stdin in place of librtlsdr (hardware I/O, outside this path), -S saving the
+// consumed bytes (dumpmode 1).
 #ifndef TFRB200_HOST_ENGINE_H
 #define TFRB200_HOST_ENGINE_H
 #include <stdint.h>

@@ -54,9 +54,11 @@ static void usage(void)
 		" -T <types>  : HEX Bitmask of sensor types, default: 7 = TFA_1 | TFA_2 | TFA_3\n"
 		"               %x: TFA_1, %x: TFA_2, %x: TFA_3, %x: TX22, %x: WeatherHub\n"
 		" -q          : Quiet, do not print message to stdout\n"
-		" -L <file>   : Load IQ-file (rtl-sdr u8 dump) and decode it on the GPU\n"
+		" -S <file>   : Live mode: save the raw IQ bytes that are decoded (replay them with -L)\n"
+		" -L <file>   : Load IQ-file (rtl-sdr u8 dump, '-' = stdin) and decode it on the GPU\n"
 		" -X <file>   : Load hexdump file and decode (test mode)\n"
-		" -d -f -g -S : accepted for compatibility; live capture is not part of this path\n",
+		" without -L/-X: live mode, raw u8 IQ at 1.536 MS/s is read from stdin (rtl_sdr -s 1536000 - | ...)\n"
+		" -d -f -g    : accepted for compatibility; tuning the stick is the feeder's job\n",
 		1 << TFA_1, 1 << TFA_2, 1 << TFA_3, 1 << TX22, 1 << TFA_WHB);
 }
 

@@ -117,6 +117,31 @@ def frame_whb03(sensor_id48, seq, temp_c, hum, ptemp_c=None, phum=None):
     return bytes([0x4B, 0x2D, 0xD4, 0x2B] + body + [(c >> 24) & 0xFF, (c >> 16) & 0xFF, (c >> 8) & 0xFF, c & 0xFF])
 
 
+def frame_tx22_words(sensor_id, words, ok=1, lowbat=0):
+    """TX22 frame from raw 16-bit words (type nibble | 12-bit value): every word type of tfa2.cpp:103-151
+    (0 temp, 1 hum, 2 rain, 3 wind dir/speed, 4 gust, others ignored), num = len(words) <= 7 (rdata[3]&7)."""
+    assert len(words) <= 7
+    body = [0xA0 | ((sensor_id >> 2) & 0xF), ((sensor_id & 3) << 6) | ((ok & 1) << 4) | ((lowbat & 1) << 3) | len(words)]
+    for w in words:
+        body += [(w >> 8) & 0xFF, w & 0xFF]
+    return bytes([0x2D, 0xD4] + body + [crc8(body)])
+
+
+# payload bytes each WeatherHub parser reads (whb.cpp:126-475): decode_02 .. decode_12
+WHB_PAYLOAD_LEN = {0x02: 6, 0x03: 11, 0x04: 12, 0x06: 14, 0x07: 18, 0x08: 26, 0x09: 14, 0x0B: 27,
+                   0x10: 10, 0x11: 34, 0x12: 9}
+
+
+def frame_whb(stype, ident40, payload):
+    """4b 2d d4 2b LL TT II*5 payload CC*4 for any WeatherHub type of whb.cpp:50-62: LL is the offset of the
+    CRC-32 counted from the first sync byte (whb.cpp:497,513-514), the CRC covers LL.. with the type's init."""
+    ident = [stype] + [(ident40 >> (8 * i)) & 0xFF for i in range(4, -1, -1)]
+    plen = 4 + 1 + 6 + len(payload)
+    body = [plen] + ident + list(payload)
+    c = crc32(body, WHB_CRC_INIT[stype])
+    return bytes([0x4B, 0x2D, 0xD4, 0x2B] + body + [(c >> 24) & 0xFF, (c >> 16) & 0xFF, (c >> 8) & 0xFF, c & 0xFF])
+
+
 # ----------------------------------------------------------------------------- bit streams
 def bits_lsb(data):
     return [(b >> i) & 1 for b in data for i in range(8)]

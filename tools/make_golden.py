@@ -87,6 +87,46 @@ def kat_frames():
     out.append((g.TFA_2, g.frame_tfa2(0x04, 59.9, 0x6A)))
     out.append((g.TX22, g.frame_tx22(63, temp_c=-5.5)))
     out.append((g.TX22, g.frame_tx22(1, hum=40)))
+    # every WeatherHub payload parser and CRC-32 init value (whb.cpp:50-62, 126-475): random payloads of the
+    # length each parser reads, plus one corrupted copy per type; an unknown type; a length byte beyond 60
+    rng = np.random.default_rng(2025)
+    for stype, plen in g.WHB_PAYLOAD_LEN.items():
+        for k in range(4):
+            f = g.frame_whb(stype, int(rng.integers(0, 1 << 40)), rng.integers(0, 256, size=plen).tolist())
+            f = f + bytes(int(rng.integers(0, 4)))   # byte count usually 2-3 bytes longer than the payload (whb.cpp:487)
+            out.append((g.TFA_WHB, f))
+        bad = bytearray(f)
+        bad[int(rng.integers(4, len(f) - 3))] ^= 1 << int(rng.integers(0, 8))
+        out.append((g.TFA_WHB, bytes(bad)))
+    # temperatures at the 11-bit sign boundary and extremes (cvt_temp, whb.cpp:109-123), type 09's 12-bit second probe
+    for t in (0x000, 0x3FF, 0x400, 0x7FF):
+        out.append((g.TFA_WHB, g.frame_whb(0x02, 0x1122334455, [0x3F, 0xFF, t >> 8, t & 0xFF, (t ^ 0x7FF) >> 8, (t ^ 0x7FF) & 0xFF])))
+    out.append((g.TFA_WHB, g.frame_whb(0x09, 0xA1B2C3D4E5, [0, 1, 0x07, 0xFF, 0x0F, 0xFF, 0, 50, 0x04, 0x00, 0x08, 0x00, 0, 99])))
+    unk = bytearray(g.frame_whb(0x03, 0x0102030405, [0] * 11))
+    unk[5] = 0x05                                       # not in crc_initvals -> "Probably unsupported sensor type"
+    out.append((g.TFA_WHB, bytes(unk)))
+    long_len = bytearray(g.frame_whb(0x03, 0x0102030405, [0] * 11))
+    long_len[4] = 61                                    # plen > 60 (whb.cpp:499-500)
+    out.append((g.TFA_WHB, bytes(long_len)))
+    out.append((g.TFA_WHB, g.frame_whb(0x11, 0x0F0E0D0C0B, rng.integers(0, 256, size=34).tolist()) + bytes(8)))   # 61 bytes: > 60 gate
+    # TX22: every word type, several records per frame (sub-ids 2/3/4), num up to 7, flag bits, unknown word types
+    W = lambda t, v: ((t & 0xF) << 12) | (v & 0xFFF)
+    bcd = lambda v: (v // 100 % 10) << 8 | (v // 10 % 10) << 4 | v % 10
+    out.append((g.TX22, g.frame_tx22_words(5, [W(0, bcd(613)), W(1, bcd(55)), W(2, 0x123), W(3, 0x7FE), W(4, 0x0A5)])))
+    out.append((g.TX22, g.frame_tx22_words(63, [W(2, 0xFFF)])))
+    out.append((g.TX22, g.frame_tx22_words(0, [W(3, 0xF00), W(4, 0xFFF)], ok=0)))
+    out.append((g.TX22, g.frame_tx22_words(17, [W(4, 0x001), W(2, 0), W(0, bcd(0))], lowbat=1)))
+    out.append((g.TX22, g.frame_tx22_words(33, [W(7, 0x123), W(0xF, 0xFFF), W(1, bcd(100))], ok=0, lowbat=1)))
+    out.append((g.TX22, g.frame_tx22_words(9, [W(0, bcd(400)), W(0, bcd(999)), W(1, bcd(1)), W(1, bcd(99)), W(2, 1), W(3, 0x10A), W(4, 0x3E8)])))
+    out.append((g.TX22, g.frame_tx22_words(21, [])))
+    for _ in range(8):
+        n = int(rng.integers(1, 8))
+        words = [W(int(rng.integers(0, 6)), int(rng.integers(0, 4096))) for _ in range(n)]
+        f = g.frame_tx22_words(int(rng.integers(0, 64)), words, ok=int(rng.integers(0, 2)), lowbat=int(rng.integers(0, 2)))
+        out.append((g.TX22, f))
+    bad = bytearray(f)
+    bad[4] ^= 0x10
+    out.append((g.TX22, bytes(bad)))
     return out
 
 
