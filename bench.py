@@ -42,8 +42,10 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "tfrec")
 
 
 def workload_name(args):
-    return ("T7 default mix, auto threshold, %d streams x %d MiB u8 IQ per GPU, 1.536 MS/s, telegram every 10 s, "
-            "noise sigma %.1f LSB" % (args.streams, args.mib, args.sigma))
+    t = int(args.types, 16)
+    mix = "T7 default mix" if t == 7 else "T%x (all five decoders)" % t if t == 0x2f else "T%x" % t
+    return ("%s, auto threshold, %d streams x %d MiB u8 IQ per GPU, 1.536 MS/s, telegram every 10 s, "
+            "noise sigma %.1f LSB" % (mix, args.streams, args.mib, args.sigma))
 
 
 # ------------------------------------------------------------------------------------------------- data
@@ -151,23 +153,85 @@ def write_sample_files(td, n_files, nbytes, sigma):
     return paths
 
 
-def run_reference_once(paths):
-    """one reference process per file/core, all in parallel; returns (wall seconds, decoded telegram lines)"""
+def run_reference_once(paths, exec_echo=False, types=TYPES_MASK):
+    """one reference process per file/core, all in parallel; returns (wall seconds, decoded telegram lines), or with
+    exec_echo the per-file lists of `-e /bin/echo` argument lines (decoder.cpp:72-94) instead of the line count"""
     t0 = time.perf_counter()
     procs = []
     for k, p in enumerate(paths):
-        cmd = [REF_BIN, "-T", "%x" % TYPES_MASK, "-L", p]
+        cmd = [REF_BIN, "-T", "%x" % types] + (["-q", "-e", "/bin/echo"] if exec_echo else []) + ["-L", p]
         if os.path.exists("/usr/bin/taskset"):
             cmd = ["taskset", "-c", str(sorted(os.sched_getaffinity(0))[k % n_cores()])] + cmd
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL))
     outs = [pr.communicate()[0] for pr in procs]
     dt = time.perf_counter() - t0
+    if exec_echo:
+        import re
+        pat = re.compile(r"([0-9a-f]+ [+-][0-9.]+ \S+ -?\d+ -?\d+ -?\d+ -?\d+) \d+")
+        return dt, [[m.group(1) for m in (pat.fullmatch(ln.strip()) for ln in o.decode("latin1").splitlines()) if m]
+                    for o in outs]
     lines = sum(sum(1 for ln in o.decode("latin1").splitlines() if ln.startswith(("TFA1 ID", "TFA2 ID", "TFA3 ID")))
                 for o in outs)
     return dt, lines
 
 
-def cpu_baseline(sigma, sample_mib=256, gpu_bufs=None):
+def executed(lines):
+    """the -e lines decoder::store_data lets through in mode 0 (decoder.cpp:46-65): a WeatherHub (13-digit id) repeat
+    only when its sequence number differs from the last one stored for that id; everything else always"""
+    seen, out = {}, []
+    for ln in lines:
+        f = ln.split()
+        if len(f[0]) == 13:
+            if f[0] in seen and seen[f[0]] == f[3]:
+                continue
+            seen[f[0]] = f[3]
+        out.append(ln)
+    return out
+
+
+def parity_check(tb, bufs, types, thresh, device, n_check):
+    """Parity gate: the first n_check streams of THIS rank's workload, whole buffers, decoded by a
+    fresh handle through the C ABI, against what the unmodified reference binary hands to `-e /bin/echo` for the very
+    same bytes (the oracle port stands in only where oracle/_ref was not built).  Returns (streams checked, checker,
+    first mismatch or None)."""
+    n_check = min(n_check, len(bufs))
+    if n_check <= 0:
+        return 0, "none", None
+    nbytes = int(bufs[0].numel())
+    rx = tb.Receiver(types=types, thresh=thresh, n_streams=n_check, device=device, max_blocks_per_submit=nbytes // 65536)
+    for s in range(n_check):
+        rx.submit(s, bufs[s].data_ptr(), nbytes=nbytes)
+    rx.process()
+    recs = rx.records()
+    rx.close()
+    got = [executed([r["exec"] for r in recs if r["stream"] == s]) for s in range(n_check)]
+    if os.path.exists(REF_BIN):
+        checker = "oracle/_ref/tfrec -q -e /bin/echo"
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+            paths = []
+            for s in range(n_check):
+                p = os.path.join(td, "p%d.iq" % s)
+                bufs[s].cpu().numpy().tofile(p)
+                paths.append(p)
+            _, want = run_reference_once(paths, exec_echo=True, types=types)
+    else:
+        checker = "oracle port (oracle/_ref not built)"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        want = []
+        for s in range(n_check):
+            o = ol.Oracle(types=types, thresh=thresh)
+            o.process(bufs[s].cpu().numpy())
+            want.append(executed([r["exec"] for r in o.records()]))
+            o.close()
+    for s in range(n_check):
+        if got[s] != want[s]:
+            return n_check, checker, {"stream": s, "gpu": got[s][:8], "reference": want[s][:8],
+                                      "n_gpu": len(got[s]), "n_reference": len(want[s])}
+    return n_check, checker, None
+
+
+def cpu_baseline(sigma, sample_mib=256, gpu_bufs=None, types=TYPES_MASK):
     """the unmodified reference on all host cores, one process per core, each on the first sample_mib MiB of one
     of THIS run's stream buffers (copied back from the GPU, so the bytes are the ones the GPU decoded)"""
     cores = n_cores()
@@ -186,14 +250,14 @@ def cpu_baseline(sigma, sample_mib=256, gpu_bufs=None):
                 paths.append(p)
         else:
             paths = write_sample_files(td, cores, nbytes, sigma)
-        run_reference_once(paths[:1])                    # page cache / binary warm-up
-        dt, lines = run_reference_once(paths)
+        run_reference_once(paths[:1], types=types)       # page cache / binary warm-up
+        dt, lines = run_reference_once(paths, types=types)
     sample_mib = nbytes >> 20
     samples = cores * (nbytes // 2)
     return {"value": round(samples / dt / 1e6, 2), "unit": "MSamples/s", "cores": cores, "kind": "reference",
             "telegrams_per_s": round(lines / dt, 3),
-            "sample": "unmodified reference `tfrec -T 7 -L` (auto threshold), %d processes x %d MiB (first %d MiB of "
-                      "streams 0..%d of this workload), wall %.2f s" % (cores, sample_mib, sample_mib, cores - 1, dt)}
+            "sample": "unmodified reference `tfrec -T %x -L` (auto threshold), %d processes x %d MiB (first %d MiB of "
+                      "streams 0..%d of this workload), wall %.2f s" % (types, cores, sample_mib, sample_mib, cores - 1, dt)}
 
 
 def main_reference(args):
@@ -208,11 +272,12 @@ def main_reference(args):
     nbytes = sample_mib << 20
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
         paths = write_sample_files(td, cores, nbytes, args.sigma)
+        rtypes = int(args.types, 16)
         for _ in range(args.warmup):
-            run_reference_once(paths)
+            run_reference_once(paths, types=rtypes)
         tot, lines = 0.0, 0
         for _ in range(args.steps):
-            dt, ln = run_reference_once(paths)
+            dt, ln = run_reference_once(paths, types=rtypes)
             tot += dt
             lines += ln
     samples = cores * (nbytes // 2) * args.steps
@@ -223,7 +288,7 @@ def main_reference(args):
            "telegrams_per_s": round(lines / tot, 3),
            "config": {"workload": workload_name(args), "step": "bounded sample: %d processes x %d MiB" % (cores, sample_mib)},
            "cpu_baseline": {"value": round(v, 2), "unit": "MSamples/s", "cores": cores, "kind": "reference",
-                            "sample": "unmodified reference `tfrec -T 7 -L`, %d processes x %d MiB per step" % (cores, sample_mib)},
+                            "sample": "unmodified reference `tfrec -T %x -L`, %d processes x %d MiB per step" % (rtypes, cores, sample_mib)},
            "e2e": {"value": round(v, 2), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -240,6 +305,11 @@ def main():
     ap.add_argument("--sigma", type=float, default=4.0)
     ap.add_argument("--thresh", type=int, default=0, help="0 = auto (reference default)")
     ap.add_argument("--ref-mib", type=int, default=64, help="reference arm: MiB per process per step")
+    ap.add_argument("--types", default="7", help="hex mask of registered decoders for the headline pass (7 = TFA_1/2/3, "
+                    "2f = all five incl. TX22 and WeatherHub, BASELINE.json configs[2])")
+    ap.add_argument("--parity-streams", type=int, default=-1, help="streams per rank checked against the reference "
+                    "before timing (-1: all host cores' worth at N=1, 2 per rank under torchrun)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the all-five-decoders (-T 2f) extra leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -290,7 +360,25 @@ def main():
         sent += n
     samples_per_step = S * (nbytes // 2)
 
-    rx = tb.Receiver(types=TYPES_MASK, thresh=args.thresh, n_streams=S, device=local, max_blocks_per_submit=nbytes // 65536)
+    types_mask = int(args.types, 16)
+
+    # ---- parity gate: no number is printed for a workload the GPU decodes differently from the reference ----------
+    n_par = args.parity_streams if args.parity_streams >= 0 else (min(n_cores(), S) if world == 1 else 2)
+    par_n, par_checker, par_bad = parity_check(tb, bufs, types_mask, args.thresh, local, n_par)
+    n_bad = allsum(1.0 if par_bad is not None else 0.0)
+    par_total = int(allsum(float(par_n)))
+    if n_bad:
+        if par_bad is not None:
+            sys.stderr.write("rank %d: PARITY MISMATCH against %s: %s\n" % (rank, par_checker, json.dumps(par_bad)))
+        if rank == 0:
+            print(json.dumps({"metric": "iq_msamples_per_s", "value": None, "unit": "MSamples/s", "n_gpus": world,
+                              "parity_checked_streams": par_total, "parity": "MISMATCH on %d rank(s): no value reported" % int(n_bad),
+                              "parity_checker": par_checker, "first_mismatch": par_bad}))
+        if dist is not None:
+            dist.destroy_process_group()
+        sys.exit(1)
+
+    rx = tb.Receiver(types=types_mask, thresh=args.thresh, n_streams=S, device=local, max_blocks_per_submit=nbytes // 65536)
 
     def step_device():
         for s in range(S):
@@ -387,6 +475,27 @@ def main():
                "ms_per_step": round(1e3 * t_e2e / args.steps, 3)}
         del host
 
+    # ---- extra: all five decoders (BASELINE.json configs[2], `-T 2f`) on the same buffers ----------------------------
+    extra = None
+    if not args.no_extra and types_mask != 0x2f:
+        rx.close()
+        rx = None
+        rx5 = tb.Receiver(types=0x2f, thresh=args.thresh, n_streams=S, device=local, max_blocks_per_submit=nbytes // 65536)
+        ms5, k5 = 0.0, max(3, min(5, args.steps))
+        for i in range(2 + k5):
+            for s in range(S):
+                rx5.submit(s, bufs[s].data_ptr(), nbytes=nbytes)
+            rx5.process()
+            rx5.sync()
+            if i >= 2:
+                ms5 += rx5.stats()["last_total_ms"]
+            rx5.clear()
+        rx5.close()
+        t5 = allmax(ms5 / 1e3)
+        extra = {"all_five_decoders_T2f": {"value": round(allsum(float(samples_per_step)) * k5 / t5 / 1e6, 2), "unit": "MSamples/s",
+                                           "ms_per_step": round(1e3 * t5 / k5, 4), "steps": k5, "warmup": 2,
+                                           "note": "same streams, TX22 and WeatherHub registered too (resident in HBM, synchronised per step)"}}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -410,6 +519,8 @@ def main():
                 "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "traffic": (None if traffic is None else round(traffic * 2.0 * samples_per_step, 0)),
+                "traffic_source": "profiles/frontend_traffic.json (ncu --set full dram bytes per algorithmic byte of this kernel) x "
+                                  "this run's algorithmic bytes; not re-measured in this run",
                 "algorithmic_bytes_per_step": int(2 * samples_per_step),
                 "frontend_ms_per_step": round(fe_ms / args.steps, 4),
                 "other_ms_per_step": round(be_ms / args.steps, 4),
@@ -422,7 +533,8 @@ def main():
            "data": "synthetic",
            "config": {"workload": workload_name(args), "streams_per_gpu": S, "bytes_per_stream": nbytes,
                       "l2": "inputs (%.1f GiB per GPU) are far larger than the 126 MB L2" % (S * nbytes / 2**30),
-                      "types": "0x07", "thresh": args.thresh},
+                      "types": "0x%02x" % types_mask, "thresh": args.thresh},
+           "parity_checked_streams": par_total, "parity_checker": par_checker,
            "telegrams_per_s": round(total_decoded / t_dev, 2), "telegrams_decoded": int(total_decoded),
            "telegrams_sent": int(total_sent), "wall_ms_per_step": round(1e3 * t_wall / args.steps, 4),
            "gpu_launches": int(launches), "demod_windows_per_step": int(windows // max(args.steps, 1)),
@@ -432,8 +544,10 @@ def main():
            "clocks": clocks, "roofline": roofline}
     if e2e is not None:
         out["e2e"] = e2e
+    if extra is not None:
+        out["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.sigma, gpu_bufs=bufs)
+        out["cpu_baseline"] = cpu_baseline(args.sigma, gpu_bufs=bufs, types=types_mask)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
