@@ -24,8 +24,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "tfr_dev.h"
-#include "fir_taps.h"
+#include "frontend_common.cuh"
+
 
 namespace tfr {
 
@@ -67,64 +67,10 @@ __host__ __device__ constexpr uint32_t y2_bias(bool wide)
 }
 
 // ------------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------------
-typedef unsigned long long f2;  // packed f32x2: lo = I, hi = Q
-
-__device__ __forceinline__ f2 pack2(float lo, float hi)
-{
-	f2 r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
-}
-__device__ __forceinline__ void unpack2(f2 v, uint32_t &lo, uint32_t &hi)
-{
-	asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 fma2_rm(f2 a, f2 b, f2 c)
-{
-	f2 d;
-	asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-	return d;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra DONE_%=;\n"
-		"bra WAIT_%=;\n"
-		"DONE_%=:\n"
-		"}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-		     "l"(src), "r"(bytes), "r"(bar)
-		     : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------
 // shared memory layout
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 128;
 constexpr int kRowBytes = 512;               // raw bytes per thread
 constexpr int kRowStride = 528;              // +16: 33 x 16 B, odd -> conflict-free LDS.128 across a quarter warp
-constexpr int kOutPerThread = 64;
 constexpr int kRow0 = 128;                   // byte offset of row 0; the 96 halo bytes sit at [16,112)
 constexpr int kHaloOff = 16;
 constexpr int kSmemBytes = kRow0 + kThreads * kRowStride;  // 67,712 B -> 3 CTAs / SM
@@ -162,11 +108,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
-	__shared__ int s_first[kThreads];   // first trigger (0..63) in the thread's 64 outputs, -1 if none
-	__shared__ int s_last[kThreads];
-	__shared__ int s_seg_start[kMaxSeg + 4], s_seg_end[kMaxSeg + 4];
-	__shared__ int s_nseg, s_ntrig;
-	__shared__ int s_warp_cnt[kThreads / 32];
+	__shared__ EpiShared es;
 
 	const int tid = threadIdx.x;
 	const int stream = blockIdx.y;
@@ -262,150 +204,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 		}
 		trig64 |= (unsigned long long)t16 << (16 * it);
 	}
-	const uint32_t trig[2] = { (uint32_t)trig64, (uint32_t)(trig64 >> 32) };
-
-	// ------------------------------------------------------------------ block-level trigger bookkeeping
-	{
-		int f = -1, l = -1;
-		if (trig[0]) f = __ffs(trig[0]) - 1;
-		else if (trig[1]) f = 32 + __ffs(trig[1]) - 1;
-		if (trig[1]) l = 63 - __clz(trig[1]);
-		else if (trig[0]) l = 31 - __clz(trig[0]);
-		s_first[tid] = (f < 0) ? -1 : tid * kOutPerThread + f;
-		s_last[tid] = (l < 0) ? -1 : tid * kOutPerThread + l;
-		const int nt = __popc(trig[0]) + __popc(trig[1]);
-		// ordered event list: exclusive scan of the per-thread trigger counts over the CTA
-		int incl = nt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const int o = __shfl_up_sync(0xffffffffu, incl, d);
-			if ((tid & 31) >= d) incl += o;
-		}
-		if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = incl;
-		__syncthreads();
-		int base = incl - nt;
-		for (int w = 0; w < (tid >> 5); w++) base += s_warp_cnt[w];
-		if (tid == kThreads - 1) s_ntrig = base + nt;
-		if (nt && base < kMaxEvt) {
-			uint32_t *ev = p.events + ((size_t)job.dec_off + tile) * kMaxEvt;
-			unsigned long long msk = trig64;
-			int k = base;
-			while (msk && k < kMaxEvt) {
-				const int b = __ffsll((long long)msk) - 1;
-				msk &= msk - 1;
-				const uint32_t w = outw[b];   // this thread's own output b (I lo16, Q hi16)
-				const int pi = (int)(int16_t)(w & 0xffff), pq = (int)(int16_t)(w >> 16);
-				ev[k++] = ((uint32_t)(tid * kOutPerThread + b) << 16) | (uint32_t)(abs(pi) + abs(pq));
-			}
-		}
-	}
-	__syncthreads();
-
-	// warp 0: merge the per-thread trigger extents into covered segments [start, end)
-	if (tid < 32) {
-		// each lane scans 4 consecutive threads; a segment can only begin at a thread's first trigger
-		// because t_max (>= 356) exceeds the 64 samples a thread owns
-		int lastq = -1;          // last trigger seen before this lane's group (filled by the scan below)
-		int grp_last = -1;
-#pragma unroll
-		for (int k = 0; k < 4; k++) grp_last = max(grp_last, s_last[tid * 4 + k]);
-		// inclusive prefix max over lanes, then shift to exclusive
-		int pm = grp_last;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			int o = __shfl_up_sync(0xffffffffu, pm, d);
-			if (tid >= d) pm = max(pm, o);
-		}
-		lastq = __shfl_up_sync(0xffffffffu, pm, 1);
-		if (tid == 0) lastq = -1;
-		// walk the 4 threads of the group, emitting (start) markers and tracking chain ends
-		int starts[4];
-		int q = lastq;
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			const int f = s_first[tid * 4 + k], l = s_last[tid * 4 + k];
-			starts[k] = -1;
-			if (f >= 0) {
-				if (q < 0 || f - q > p.t_max) starts[k] = f;
-				q = l;
-			}
-		}
-		// number the starts across the warp
-		int cnt = 0;
-#pragma unroll
-		for (int k = 0; k < 4; k++) cnt += (starts[k] >= 0);
-		int incl = cnt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			int o = __shfl_up_sync(0xffffffffu, incl, d);
-			if (tid >= d) incl += o;
-		}
-		int base = incl - cnt;
-		const int total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if (starts[k] >= 0) {
-				if (base < kMaxSeg + 4) s_seg_start[base] = starts[k];
-				base++;
-			}
-		if (tid == 0) s_nseg = min(total, kMaxSeg);
-		__syncwarp();
-		// segment i ends t_max after the last trigger that precedes segment i+1's start
-		const int nseg = min(total, kMaxSeg);
-		const int lastall = __shfl_sync(0xffffffffu, pm, 31);
-		if (tid < nseg) {
-			int endq;
-			if (tid == nseg - 1) {
-				endq = lastall;
-			} else {
-				// last trigger strictly before the next start: scan thread slots backwards from the owner of that start
-				const int nxt = s_seg_start[tid + 1];
-				int t = nxt / kOutPerThread - 1;
-				while (t >= 0 && s_last[t] < 0) t--;
-				endq = (t >= 0) ? s_last[t] : -1;
-			}
-			s_seg_end[tid] = endq + p.t_max;   // exclusive; may exceed the block -> carry_out
-		}
-	}
-	__syncthreads();
-
-	// ------------------------------------------------------------------ sparse store + descriptor
-	const size_t gtile = (size_t)job.dec_off + tile;
-	uint32_t *dst = p.dec + gtile * kBlockDec;
-	const int nseg = s_nseg;
-	auto sample = [&](int m) -> uint32_t {
+	block_epilogue(p, job, tile, [&](int m) -> uint32_t {
 		return *reinterpret_cast<const uint32_t *>(smem + kRow0 + (m >> 6) * kRowStride + (m & 63) * 4);
-	};
-	if (p.keep_all) {
-		for (int m = tid; m < kBlockDec; m += kThreads) dst[m] = sample(m);
-	} else {
-		// head [0, t_max) and the last sample are always kept (needed when the previous block's trigger
-		// reaches into this one, and as the next block's lead-in sample)
-		int covered = min(p.t_max, kBlockDec);
-		for (int m = tid; m < covered; m += kThreads) dst[m] = sample(m);
-		if (tid == 0) dst[kBlockDec - 1] = sample(kBlockDec - 1);
-		for (int sgi = 0; sgi < nseg; sgi++) {
-			const int s0 = max(max(s_seg_start[sgi] - 1, covered), 0);   // one lead-in sample
-			const int e0 = min(s_seg_end[sgi], kBlockDec);
-			for (int m = s0 + tid; m < e0; m += kThreads) dst[m] = sample(m);
-			covered = max(covered, e0);
-		}
-	}
-	if (tid < kMaxSeg) {
-		TileDesc *td = p.tiles + gtile;
-		const bool on = tid < nseg;
-		const int s0 = on ? s_seg_start[tid] : 0;
-		const int e0 = on ? min(s_seg_end[tid], kBlockDec) : 0;
-		td->seg_start[tid] = (uint16_t)s0;
-		td->seg_len[tid] = (uint16_t)(e0 - s0);
-		if (tid == 0) {
-			td->n_seg = (uint16_t)nseg;
-			const int over = nseg ? s_seg_end[nseg - 1] - kBlockDec : 0;
-			td->carry_out = (uint16_t)max(over, 0);
-			td->n_trig = (uint32_t)s_ntrig;
-			td->pad = 0;
-		}
-	}
+	}, es, trig64);
 }
 
 // after the last front-end launch and threshold walk of a call: remember the FIR history for the next call

@@ -16,6 +16,9 @@
 
 namespace tfr {
 cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaStream_t stream);
+cudaError_t launch_frontend_tc(const FrontParams &p, int n_streams, int wide, cudaStream_t stream);
+bool frontend_tc_available();
+int frontend_tc_encode(const void *iq, uint32_t n_blocks, void *out);
 cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream);
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
@@ -88,6 +91,8 @@ struct tfr_handle {
 	// (throughput bound) already use the other slot
 	struct Slot {
 		StreamJob *d_jobs = nullptr;
+		uint8_t *d_tmaps = nullptr;              // [stream][2] CUtensorMap of the call's submits (frontend_tc_kernel)
+		std::vector<uint8_t> h_tmaps;            // host copy (stays until the slot's next call)
 		TileDesc *d_tiles = nullptr;
 		uint32_t *d_dec = nullptr;
 		BlockTrace *d_trace = nullptr;
@@ -106,6 +111,7 @@ struct tfr_handle {
 	cudaStream_t stream_long = nullptr; // winlong_kernel (the long window chains, one warp each) beside win_kernel; high priority
 	cudaEvent_t long_ev[2] = { nullptr, nullptr };
 	bool long_split = true;
+	bool use_tc = true;                // front-end with tensor-core byte->float conversion (frontend_tc.cu); TFR_FE=old: frontend.cu
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
 	cudaStream_t stream_fe2 = nullptr;    // odd front-end chunks: consecutive chunk launches overlap their tails
 	cudaEvent_t chunk_ev[8] = { nullptr };
@@ -209,7 +215,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
 	for (auto &sl : h->slot) {
-		cudaFree(sl.d_jobs); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
+		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt);
 		for (cudaEvent_t e : { sl.front_done, sl.back_done, sl.fe0, sl.fe1 })
 			if (e) cudaEventDestroy(e);
@@ -287,6 +293,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaStreamCreateWithPriority(&h->stream_long, cudaStreamNonBlocking, prio_hi));
 		for (auto &e : h->long_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		if (getenv("TFR_NO_LONG")) h->long_split = false;   // experiments: every chain in the thread-per-chain kernel
+		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=old selects the shared-memory front-end
+		h->use_tc = frontend_tc_available() && !(fe && !strcmp(fe, "old"));
 	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -301,6 +309,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaEventCreate(&sl.fe0));
 		CUH(cudaEventCreate(&sl.fe1));
 		CUH(cudaMalloc(&sl.d_jobs, sizeof(StreamJob) * cfg->n_streams));
+		CUH(cudaMalloc(&sl.d_tmaps, (size_t)256 * cfg->n_streams));
+		sl.h_tmaps.assign((size_t)256 * cfg->n_streams + 64, 0);
 		CUH(cudaMalloc(&sl.d_wincnt, sizeof(WinCount) * cfg->n_streams));
 		CUH(cudaMemset(sl.d_wincnt, 0, sizeof(WinCount) * cfg->n_streams));
 	}
@@ -488,6 +498,14 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	}
 	// h->jobs stays untouched until the copy has run: the next tfr_process first waits for this slot's events
 	CU(cudaMemcpyAsync(sl.d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, sf));
+	if (h->use_tc) {
+		// the call's tensor maps (TMA descriptors of every stream's submit), encoded on the host, 64-byte aligned
+		uint8_t *tm = reinterpret_cast<uint8_t *>(((uintptr_t)sl.h_tmaps.data() + 63) & ~(uintptr_t)63);
+		for (int s = 0; s < ns; s++)
+			if (h->jobs[s].n_blocks && frontend_tc_encode(h->jobs[s].iq, h->jobs[s].n_blocks, tm + (size_t)256 * s))
+				return fail(TFR_E_CUDA, "tfr_process: cuTensorMapEncodeTiled failed");
+		CU(cudaMemcpyAsync(sl.d_tmaps, tm, (size_t)256 * ns, cudaMemcpyHostToDevice, sf));
+	}
 
 	// Auto threshold: the whole call is first run against a speculative lower bound of the threshold (see
 	// spec_margin in tfr_dev.h).  The threshold kernel stops a stream where the bound fails; the rest of such a
@@ -506,6 +524,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	fp.n_tiles = (int)max_blocks;
 	fp.margin = 0;
 	fp.use_progress = 0;
+	fp.tmaps = sl.d_tmaps;
+	auto launch_fe = [&](const FrontParams &q, cudaStream_t st) {
+		return h->use_tc ? launch_frontend_tc(q, ns, h->dcfg.filter, st) : launch_frontend(q, ns, h->dcfg.filter, st);
+	};
 	BackParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.cfg = h->d_cfg;
@@ -560,7 +582,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			// the chunks are independent of each other: alternating two streams lets chunk k+1's first CTAs fill the
 			// SMs that chunk k's last wave leaves idle
 			cudaStream_t sk = (k & 1) ? h->stream_fe2 : sf;
-			CU(launch_frontend(fp, ns, h->dcfg.filter, sk));
+			CU(launch_fe(fp, sk));
 			CU(cudaEventRecord(h->chunk_ev[k], sk));
 			if (k & 1) last_odd = k;
 			CU(cudaStreamWaitEvent(h->stream_walk, h->chunk_ev[k], 0));
@@ -593,7 +615,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			bp.margin = kEpochMargin;
 			CU(cudaEventRecord(h->ev[0], sf));
 			for (int e = 0; e < n_fallback; e++) {
-				CU(launch_frontend(fp, ns, h->dcfg.filter, sf));
+				CU(launch_fe(fp, sf));
 				CU(launch_thresh2(bp, sf));
 				h->stats.kernel_launches += 2;
 			}

@@ -223,6 +223,7 @@ struct FrontParams {
 	                       // the launch, epoch fallback); 0 = the call's frozen speculative bound StreamState::spec_lo
 	int use_progress;      // 1: a stream's first block of this launch is its StreamState::t2_done (epoch fallback)
 	uint32_t *events;      // [gtile][kMaxEvt]
+	const void *tmaps;     // frontend_tc_kernel: [stream][2] CUtensorMap (rows of the submit, and the 32 bytes in front of every row)
 };
 
 struct BackParams {
