@@ -83,6 +83,34 @@ def test_decimator_bit_exact(tb, golden):
             assert sha(d.astype("<i2")) == golden["decimator"][name][key]["sha256"]
 
 
+def test_tensor_core_front_end_variant_bit_exact(tb, golden, hot_fixture, monkeypatch):
+    """frontend_tc.cu (TFR_FE=tc: TMA tensor boxes + tcgen05.mma byte->float conversion + tensor-memory loads) is an
+    opt-in variant of the front-end; it has to produce the reference's samples and records like the default kernel"""
+    monkeypatch.setenv("TFR_FE", "tc")
+    rng = np.random.default_rng(5)
+    fixtures = {
+        "uniform_bytes": rng.integers(0, 256, size=4 * 65536, dtype=np.uint8),
+        "extremes": np.tile(np.array([0, 255, 255, 0, 0, 0, 255, 255], dtype=np.uint8), 65536 // 8 * 2),
+        "single_tfa1": g.fixture_single_tfa1(seed=1),
+    }
+    for name, iq in fixtures.items():
+        for filt, key in ((0, "narrow"), (1, "wide")):
+            d = tb.decimate(iq, filt)
+            assert np.array_equal(d, ol.decimate(iq, filt)), "%s/%s" % (name, key)
+            assert sha(d.astype("<i2")) == golden["decimator"][name][key]["sha256"]
+    # and a whole decode through it, in several submits (history carried between calls)
+    iq = hot_fixture("mixed5")
+    rx = tb.Receiver(types=0x2F, thresh=0)
+    for off in range(0, iq.size, 7 * 65536):
+        rx.submit(0, iq[off:off + 7 * 65536].copy())
+        rx.process()
+    o = ol.Oracle(types=0x2F)
+    o.process(iq)
+    assert [r["exec"] for r in rx.records()] == [r["exec"] for r in o.records()]
+    assert rx.thresh(0) == o.thresh()
+    rx.close()
+
+
 def test_decimator_ragged_length(tb):
     rng = np.random.default_rng(8)
     iq = rng.integers(0, 256, size=65536 + 4096 + 12, dtype=np.uint8)

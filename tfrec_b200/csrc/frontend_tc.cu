@@ -356,34 +356,34 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_tc_kernel(const FrontPar
 #pragma unroll 1
 	for (int q = 0; q < 4; q++) {
 		uint32_t t16 = 0u;
-		uint32_t v[16];
+		uint32_t va[16], vb[16];   // the next step's columns are in flight while the current step computes
 		// ---- phase 2q: buffer 0 (its use number q); outputs into the halo tile (q = 0) or the previous box
 		{
 			uint8_t *orow = (q == 0) ? smem + kOffHalo + tid * 32 : smem + (q - 1) * kBoxBytes + tid * 128;
 			const int xm = (q == 0) ? 0 : (tid & 7), wofs = (q == 0) ? 0 : 8;
 			mbar_wait(bar_full, (uint32_t)(q & 1));
 			tc_fence_after();
-			tmem_ld16(tlane + 0, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 0>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_ld16(tlane + 0, va);
+			tmem_wait_ld(va);
+			tmem_ld16(tlane + 16, vb);
+			tc_step<WIDE, 0>(va, ring, xh, orow, xm, wofs, t16, thresh_lo);
 			if (tid == 0 && q > 0) {   // phase 2q+1 into buffer 1, free once every warp has pulled phase 2q-1
 				mbar_wait(bar_empty + 8, (uint32_t)(q & 1));
 				tc_fence_after();
 				issue_phase(2 * q + 1);
 			}
 			__syncwarp();
-			tmem_ld16(tlane + 16, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 1>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
-			tmem_ld16(tlane + 32, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 2>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
-			tmem_ld16(tlane + 48, v);
-			tmem_wait_ld(v);
+			tmem_wait_ld(vb);
+			tmem_ld16(tlane + 32, va);
+			tc_step<WIDE, 1>(vb, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_wait_ld(va);
+			tmem_ld16(tlane + 48, vb);
+			tc_step<WIDE, 2>(va, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_wait_ld(vb);
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(bar_empty);
-			tc_step<WIDE, 3>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tc_step<WIDE, 3>(vb, ring, xh, orow, xm, wofs, t16, thresh_lo);
 		}
 		// ---- phase 2q+1: buffer 1 (its use number q+1); outputs into the first half of box q's rows
 		{
@@ -391,9 +391,10 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_tc_kernel(const FrontPar
 			const int xm = tid & 7, wofs = 0;
 			mbar_wait(bar_full + 8, (uint32_t)((q + 1) & 1));
 			tc_fence_after();
-			tmem_ld16(tlane + 64, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 4>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_ld16(tlane + 64, va);
+			tmem_wait_ld(va);
+			tmem_ld16(tlane + 80, vb);
+			tc_step<WIDE, 4>(va, ring, xh, orow, xm, wofs, t16, thresh_lo);
 			if (tid == 0 && q < 3) {   // phase 2q+2 into buffer 0, free once every warp has pulled phase 2q
 				mbar_wait(bar_box + 8 * (q + 1), 0);
 				mbar_wait(bar_empty, (uint32_t)(q & 1));
@@ -401,18 +402,17 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_tc_kernel(const FrontPar
 				issue_phase(2 * q + 2);
 			}
 			__syncwarp();
-			tmem_ld16(tlane + 80, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 5>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
-			tmem_ld16(tlane + 96, v);
-			tmem_wait_ld(v);
-			tc_step<WIDE, 6>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
-			tmem_ld16(tlane + 112, v);
-			tmem_wait_ld(v);
+			tmem_wait_ld(vb);
+			tmem_ld16(tlane + 96, va);
+			tc_step<WIDE, 5>(vb, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_wait_ld(va);
+			tmem_ld16(tlane + 112, vb);
+			tc_step<WIDE, 6>(va, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tmem_wait_ld(vb);
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(bar_empty + 8);
-			tc_step<WIDE, 7>(v, ring, xh, orow, xm, wofs, t16, thresh_lo);
+			tc_step<WIDE, 7>(vb, ring, xh, orow, xm, wofs, t16, thresh_lo);
 		}
 		trig64 |= (unsigned long long)t16 << (16 * q);
 	}
@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_tc_kernel(const FrontPar
 	for (int m = 0; m < kSpill; m++) {
 		uint32_t in = __shfl_up_sync(0xffffffffu, sp[m], 1);
 		if (lane == 0) in = s_spill[warp][m];
-		uint32_t *slot = reinterpret_cast<uint32_t *>(smem + tc_out_off(tid, m));
+		// outputs 0..7 are phase 0 (halo tile), output 8 is word 0 of box 0's row
+		uint32_t *slot = reinterpret_cast<uint32_t *>(m < 8 ? smem + kOffHalo + tid * 32 + m * 4 : smem + tid * 128 + ((tid & 7) << 4));
 		const uint32_t own = *slot;
 		const int yi = (int)(int16_t)(own & 0xffff) + (int)(in & 0xffff) - 16384;
 		const int yq = ((int)own >> 16) + (int)(in >> 16) - 16384;

@@ -111,7 +111,8 @@ struct tfr_handle {
 	cudaStream_t stream_long = nullptr; // winlong_kernel (the long window chains, one warp each) beside win_kernel; high priority
 	cudaEvent_t long_ev[2] = { nullptr, nullptr };
 	bool long_split = true;
-	bool use_tc = true;                // front-end with tensor-core byte->float conversion (frontend_tc.cu); TFR_FE=old: frontend.cu
+	bool use_tc = false;               // TFR_FE=tc: the front-end variant with tensor-core byte->float conversion (frontend_tc.cu,
+	                                   // bit-identical, measured 28 % slower on B200: DESIGN.md 4.1b); default frontend.cu
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
 	cudaStream_t stream_fe2 = nullptr;    // odd front-end chunks: consecutive chunk launches overlap their tails
 	cudaEvent_t chunk_ev[8] = { nullptr };
@@ -293,8 +294,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaStreamCreateWithPriority(&h->stream_long, cudaStreamNonBlocking, prio_hi));
 		for (auto &e : h->long_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		if (getenv("TFR_NO_LONG")) h->long_split = false;   // experiments: every chain in the thread-per-chain kernel
-		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=old selects the shared-memory front-end
-		h->use_tc = frontend_tc_available() && !(fe && !strcmp(fe, "old"));
+		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=tc selects the tensor-core front-end variant
+		h->use_tc = fe && !strcmp(fe, "tc") && frontend_tc_available();
 	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
