@@ -227,6 +227,32 @@ def test_streaming_submits_carry_state(tb, hot_fixture):
     rx.close()
 
 
+@pytest.mark.parametrize("parts", [1, 2, 4, 8])
+def test_front_end_chunks_and_back_end_parts(tb, hot_fixture, monkeypatch, parts):
+    """A large call goes through the front-end in up to 8 chunk launches and through the demodulators in parts that
+    start while later chunks are still in the front-end.  TFR_MIN_CHUNK brings that machinery down to
+    the size of the fixtures: whatever the cut, frames, records, block trace and threshold are the oracle's."""
+    monkeypatch.setenv("TFR_MIN_CHUNK", "24")
+    monkeypatch.setenv("TFR_BE_PARTS", str(parts))
+    names = ["mixed5", "cont_noisy", "strong_t7"]
+    iqs = [hot_fixture(n) for n in names]
+    rx = tb.Receiver(types=0x0F, thresh=0, n_streams=len(iqs))
+    nb = min(x.size for x in iqs) // 65536
+    half = (nb // 2) * 65536
+    for lo, hi in ((0, half), (half, nb * 65536)):          # two calls: state carried across them, parts in both
+        for s, iq in enumerate(iqs):
+            rx.submit(s, iq[lo:hi].copy())
+        rx.process()
+    frames, records = rx.frames(), rx.records()
+    for s, iq in enumerate(iqs):
+        o = ol.Oracle(types=0x0F)
+        o.process(iq[:nb * 65536])
+        assert [frame_key(f) for f in frames if f["stream"] == s] == [frame_key(f) for f in o.frames()], names[s]
+        assert [r["exec"] for r in records if r["stream"] == s] == [r["exec"] for r in o.records()], names[s]
+        assert rx.thresh(s) == o.thresh()
+    rx.close()
+
+
 def test_multi_stream_batch(tb, hot_fixture):
     names = ["single_tfa1", "mixed5", "strong_t7", "noise_only"]
     iqs = [hot_fixture(n) for n in names]

@@ -34,6 +34,34 @@ __device__ unsigned long long g_slprof[8];   // of one 2784-sample window: fast 
 #endif
 
 
+#ifndef TFR_CHAIN_MAX
+#define TFR_CHAIN_MAX 8
+#endif
+constexpr int kChainMax = TFR_CHAIN_MAX;
+#ifndef TFR_CHAIN_GROUP
+#define TFR_CHAIN_GROUP 1
+#endif
+constexpr uint32_t kChainGroup = TFR_CHAIN_GROUP;
+#ifdef TFR_WIN_PROFILE
+__device__ unsigned long long g_winprof[16];
+#endif
+__device__ __forceinline__ bool win_near(const WinEntry *wl, uint32_t w, int timeout)
+{
+	return wl[w].start - wl[w - 1].end <= (uint32_t)timeout + 1u;
+}
+// pure function of the window list, so that every thread agrees on where chains begin
+__device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int timeout)
+{
+	uint32_t k = 0;
+	while (w - k > 0 && k < 8u * kChainMax && win_near(wl, w - k, timeout)) k++;
+	if (k) return (k % kChainMax) == 0;
+	// A window that is not near could be speculated on its own, but every speculated window pays a biquad warm-up of
+	// several timeouts (and some of them a repair): only every kChainGroup-th one is a head, the thread carries the
+	// true filter state and last_bit_idx through the windows in between.  (Measured slower for every G > 1.)
+	return (w % kChainGroup) == 0;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // thresh2_kernel: one warp per stream; reproduces fsk_demod::process' per-block bookkeeping
 // (fm_demod.cpp:51-73) from the front-end's event lists and lists every demodulator's windows.
@@ -59,11 +87,18 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 	const int lane = threadIdx.x;
 	if (stream >= p.n_streams) return;
 	const StreamJob job = p.jobs[stream];
-	if (job.n_blocks == 0) return;
+	const DevConfig &cfg = *p.cfg;
+	WinCount *part = (p.part_idx >= 0) ? p.partcnt + (size_t)p.part_idx * p.n_streams + stream : nullptr;
+	if (job.n_blocks == 0) {
+		if (part && lane < cfg.n_demods) part->n[lane] = 0;
+		return;
+	}
 	StreamState *st = p.st + stream;
 	const int b0 = (int)st->t2_done;
-	if (b0 >= (int)job.n_blocks) return;   // this stream finished in an earlier launch of the call
-	const DevConfig &cfg = *p.cfg;
+	if (b0 >= (int)job.n_blocks) {   // this stream finished in an earlier launch of the call: every window is final
+		if (part && lane < cfg.n_demods) part->n[lane] = p.wincnt[stream].n[lane];
+		return;
+	}
 	const int t_max = cfg.t_max;
 	const int nd = cfg.n_demods;
 	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
@@ -354,6 +389,21 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 		st->win_n[lane] = n_win;
 		st->win_cum[lane] = cum;
 		st->win_open[lane] = open;
+		if (part) {
+			// the windows a back-end part may take now: the leading ones that are closed and end before the blocks walked
+			// so far, cut at a chain head.  A window that is still to come starts at or after `bound`; it can only be near
+			// (inside the chain of) the last listed window if that one ended within T_d+1 samples of bound.
+			uint32_t W = n_win;
+			if (!finished) {
+				const uint32_t bound = (uint32_t)t_stop * (uint32_t)kBlockDec;
+				while (W > 0 && wl[W - 1].end >= bound) W--;
+				if (cfg.d[lane].kind != K_TFA1) {
+					if (W == n_win && W > 0 && bound - wl[W - 1].end <= (uint32_t)T_d + 1u) W--;
+					while (W > 0 && W < n_win && !chain_head(wl, W, T_d)) W--;
+				}
+			}
+			part->n[lane] = W;
+		}
 	}
 	for (int o = 16; o; o >>= 1) act_lane += __shfl_xor_sync(0xffffffffu, act_lane, o);
 	if (lane == 0) {
@@ -382,7 +432,7 @@ __global__ void __launch_bounds__(128) devfm_kernel(const BackParams p)
 	// instead of waiting at a barrier for a serially built region list, and strides the kept samples by the CTA width.
 	const int stream = blockIdx.y;
 	const StreamJob job = p.jobs[stream];
-	const int tile = blockIdx.x;
+	const int tile = p.tile0 + blockIdx.x;   // a back-end part covers the blocks [tile0, tile0 + n_tiles)
 	if (tile >= (int)job.n_blocks) return;
 	const size_t gtile = (size_t)job.dec_off + tile;
 	const TileDesc &td = p.tiles[gtile];
@@ -866,31 +916,11 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 // unless last_bit_idx is the 0 sentinel, which verify_kernel catches) and is cut every kChainMax windows to
 // bound the tail latency.  TFA_1 windows carry only the decoder shift register and stay one per thread.
 // ------------------------------------------------------------------------------------------------
-#ifndef TFR_CHAIN_MAX
-#define TFR_CHAIN_MAX 8
-#endif
-constexpr int kChainMax = TFR_CHAIN_MAX;
-#ifndef TFR_CHAIN_GROUP
-#define TFR_CHAIN_GROUP 1
-#endif
-constexpr uint32_t kChainGroup = TFR_CHAIN_GROUP;
-#ifdef TFR_WIN_PROFILE
-__device__ unsigned long long g_winprof[16];
-#endif
-__device__ __forceinline__ bool win_near(const WinEntry *wl, uint32_t w, int timeout)
+// the windows [lo, hi) of (stream, demod) a window-kernel launch works on (BackParams::part_lo / part_hi)
+__device__ __forceinline__ void part_range(const BackParams &p, int stream, int demod, uint32_t &lo, uint32_t &hi)
 {
-	return wl[w].start - wl[w - 1].end <= (uint32_t)timeout + 1u;
-}
-// pure function of the window list, so that every thread agrees on where chains begin
-__device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int timeout)
-{
-	uint32_t k = 0;
-	while (w - k > 0 && k < 8u * kChainMax && win_near(wl, w - k, timeout)) k++;
-	if (k) return (k % kChainMax) == 0;
-	// A window that is not near could be speculated on its own, but every speculated window pays a biquad warm-up of
-	// several timeouts (and some of them a repair): only every kChainGroup-th one is a head, the thread carries the
-	// true filter state and last_bit_idx through the windows in between.  (Measured slower for every G > 1.)
-	return (w % kChainGroup) == 0;
+	lo = (p.part_lo >= 0) ? p.partcnt[(size_t)p.part_lo * p.n_streams + stream].n[demod] : 0u;
+	hi = (p.part_hi >= 0) ? p.partcnt[(size_t)p.part_hi * p.n_streams + stream].n[demod] : p.wincnt[stream].n[demod];
 }
 
 #ifndef TFR_LONG_X
@@ -931,7 +961,8 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + stream;
-	const uint32_t n_win = p.wincnt[stream].n[demod];
+	uint32_t w_lo, n_win;   // this launch's windows: [w_lo, n_win), both chain heads (or the ends of the list)
+	part_range(p, stream, demod, w_lo, n_win);
 	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
 	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
@@ -943,8 +974,8 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 	// thread t looks at the windows [t*G, (t+1)*G): normally the first one is the only head among them and its chain
 	// covers the rest, so consecutive lanes all have work
 	const uint32_t G = chains ? kChainGroup : 1u;
-	for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 * G < n_win; t0 += gridDim.x * blockDim.x)
-	for (uint32_t w0 = t0 * G; w0 < min(n_win, (t0 + 1) * G); w0++) {
+	for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; w_lo + t0 * G < n_win; t0 += gridDim.x * blockDim.x)
+	for (uint32_t w0 = w_lo + t0 * G; w0 < min(n_win, w_lo + (t0 + 1) * G); w0++) {
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
 		if (p.long_split && chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;   // winlong_kernel's
 		DemodState s;
@@ -1440,13 +1471,14 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 	const StreamJob job = p.jobs[stream];
 	if (job.n_blocks == 0) return;
 	StreamState *st = p.st + stream;
-	const uint32_t n_win = p.wincnt[stream].n[demod];
+	uint32_t w_lo, n_win;   // this launch's windows: [w_lo, n_win)
+	part_range(p, stream, demod, w_lo, n_win);
 	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
 	WinRec *rl = p.recs + job.win_off + (size_t)demod * job.win_cap;
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
 	const bool chains = (cfg.kind != K_TFA1);
 	const uint32_t n_warps = gridDim.x * kLongWarps;
-	for (uint32_t w0 = blockIdx.x * kLongWarps + (threadIdx.x >> 5); w0 < n_win; w0 += n_warps) {   // warp-uniform
+	for (uint32_t w0 = w_lo + blockIdx.x * kLongWarps + (threadIdx.x >> 5); w0 < n_win; w0 += n_warps) {   // warp-uniform
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;
 		if (!chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;
 		// the chain loop of win_kernel, every lane the same
@@ -1914,14 +1946,14 @@ cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 }
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)
 {
-	if (p.max_blocks <= 0) return cudaSuccess;
-	devfm_kernel<<<dim3(p.max_blocks, p.n_streams), 128, 0, s>>>(p);
+	if (p.n_tiles <= 0) return cudaSuccess;
+	devfm_kernel<<<dim3(p.n_tiles, p.n_streams), 128, 0, s>>>(p);
 	return cudaGetLastError();
 }
 static dim3 win_grid(const BackParams &p, int n_demods, int threads)
 {
 	// windows per (stream, demod) are at most a few per block
-	int gx = (p.max_blocks * 2 + threads - 1) / threads;
+	int gx = (p.n_tiles * 2 + threads - 1) / threads;   // n_tiles: the blocks this launch's windows come from
 	gx = gx < 1 ? 1 : (gx > 512 ? 512 : gx);
 	return dim3(gx, p.n_streams, n_demods);
 }
@@ -1950,7 +1982,7 @@ cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s)
 cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s)
 {
 	// one warp per window slot; nearly all of them leave at once (not a chain head, or not long)
-	int gx = (p.max_blocks * 2 + kLongWarps - 1) / kLongWarps;
+	int gx = (p.n_tiles * 2 + kLongWarps - 1) / kLongWarps;
 	gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);   // the warps stride over the window list
 	winlong_kernel<<<dim3(gx, p.n_streams, n_demods), 32 * kLongWarps, 0, s>>>(p);
 	return cudaGetLastError();

@@ -101,6 +101,7 @@ struct tfr_handle {
 		WinEntry *d_wins = nullptr;
 		WinRec *d_recs = nullptr;
 		WinCount *d_wincnt = nullptr;
+		WinCount *d_partcnt = nullptr;           // [kMaxParts][stream]: window counts at the back-end part boundaries
 		size_t cap_blocks = 0, cap_wins = 0;
 		cudaEvent_t front_done = nullptr, back_done = nullptr;   // end of the slot's last front / back work
 		cudaEvent_t fe0 = nullptr, fe1 = nullptr;                // around the speculative front-end launch
@@ -111,6 +112,16 @@ struct tfr_handle {
 	cudaStream_t stream_long = nullptr; // winlong_kernel (the long window chains, one warp each) beside win_kernel; high priority
 	cudaEvent_t long_ev[2] = { nullptr, nullptr };
 	bool long_split = true;
+	int be_parts = 1;                  // back-end parts per call (TFR_BE_PARTS): part j runs beside the front-end of the chunks after
+	                                   // it.  Default 1: measured on B200 (profiles/r2_backend_parts.txt) the window kernels and the
+	                                   // front-end slow each other down by more than the overlap buys (4.02 ms per call as one part,
+	                                   // 4.62 / 4.69 / 4.91 ms as 2 / 4 / 8 parts)
+	cudaEvent_t part_ev[kMaxParts] = { nullptr };
+	// a part's window kernels run on streams of their own (a window chain is a long serial walk: parts queued one after
+	// the other on one stream would add their latencies), joined before the verifier
+	cudaStream_t part_stream[kMaxParts] = { nullptr }, part_long[kMaxParts] = { nullptr };
+	cudaEvent_t part_fm[kMaxParts] = { nullptr }, part_done[kMaxParts] = { nullptr }, part_ldone[kMaxParts] = { nullptr };
+	size_t min_chunk = 8192;           // blocks per front-end chunk launch at least (TFR_MIN_CHUNK: tests exercise chunks and parts on small inputs)
 	bool use_tc = false;               // TFR_FE=tc: the front-end variant with tensor-core byte->float conversion (frontend_tc.cu,
 	                                   // bit-identical, measured 28 % slower on B200: DESIGN.md 4.1b); default frontend.cu
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
@@ -212,12 +223,14 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->stream_long) cudaStreamSynchronize(h->stream_long);
+	for (auto st_ : h->part_stream) if (st_) cudaStreamSynchronize(st_);
+	for (auto st_ : h->part_long) if (st_) cudaStreamSynchronize(st_);
 	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
 	for (auto &sl : h->slot) {
 		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
-		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt);
+		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
 		for (cudaEvent_t e : { sl.front_done, sl.back_done, sl.fe0, sl.fe1 })
 			if (e) cudaEventDestroy(e);
 	}
@@ -232,6 +245,10 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
 	if (h->stream_long) cudaStreamDestroy(h->stream_long);
 	for (auto &e : h->long_ev) if (e) cudaEventDestroy(e);
+	for (auto st_ : h->part_stream) if (st_) cudaStreamDestroy(st_);
+	for (auto st_ : h->part_long) if (st_) cudaStreamDestroy(st_);
+	for (auto *arr : { h->part_ev, h->part_fm, h->part_done, h->part_ldone })
+		for (int k = 0; k < kMaxParts; k++) if (arr[k]) cudaEventDestroy(arr[k]);
 	if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
 	if (h->stream_fe2) cudaStreamDestroy(h->stream_fe2);
 	for (auto e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -294,6 +311,16 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaStreamCreateWithPriority(&h->stream_long, cudaStreamNonBlocking, prio_hi));
 		for (auto &e : h->long_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		if (getenv("TFR_NO_LONG")) h->long_split = false;   // experiments: every chain in the thread-per-chain kernel
+		if (const char *bp_env = getenv("TFR_BE_PARTS")) h->be_parts = std::max(1, std::min(atoi(bp_env), (int)kMaxParts));
+		for (auto &e : h->part_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (auto &e : h->part_fm) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (auto &e : h->part_done) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (auto &e : h->part_ldone) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (int k = 0; k < h->be_parts && k < kMaxParts; k++) {
+			CUH(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
+			CUH(cudaStreamCreateWithPriority(&h->part_long[k], cudaStreamNonBlocking, prio_hi));
+		}
+		if (const char *mc = getenv("TFR_MIN_CHUNK")) h->min_chunk = (size_t)std::max(1, atoi(mc));
 		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=tc selects the tensor-core front-end variant
 		h->use_tc = fe && !strcmp(fe, "tc") && frontend_tc_available();
 	}
@@ -314,6 +341,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		sl.h_tmaps.assign((size_t)256 * cfg->n_streams + 64, 0);
 		CUH(cudaMalloc(&sl.d_wincnt, sizeof(WinCount) * cfg->n_streams));
 		CUH(cudaMemset(sl.d_wincnt, 0, sizeof(WinCount) * cfg->n_streams));
+		CUH(cudaMalloc(&sl.d_partcnt, sizeof(WinCount) * kMaxParts * cfg->n_streams));
+		CUH(cudaMemset(sl.d_partcnt, 0, sizeof(WinCount) * kMaxParts * cfg->n_streams));
 	}
 	CUH(cudaEventCreate(&h->ev_h2d0));
 	CUH(cudaEventCreate(&h->ev_h2d1));
@@ -352,6 +381,8 @@ static int sync_all(tfr_handle *h)
 	CU(cudaStreamSynchronize(h->stream_fe2));
 	CU(cudaStreamSynchronize(h->stream_walk));
 	CU(cudaStreamSynchronize(h->stream_long));
+	for (auto st_ : h->part_stream) if (st_) CU(cudaStreamSynchronize(st_));
+	for (auto st_ : h->part_long) if (st_) CU(cudaStreamSynchronize(st_));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
 }
@@ -553,12 +584,51 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.recs = sl.d_recs;
 	bp.devfm = sl.d_devfm;
 	bp.wincnt = sl.d_wincnt;
+	bp.partcnt = sl.d_partcnt;
+	bp.part_idx = -1;
+	bp.part_lo = bp.part_hi = -1;
 	bp.max_blocks = (int)max_blocks;
 	bp.tile0 = 0;
 	bp.n_tiles = (int)max_blocks;
 	bp.margin = 0;
 	bp.progress = h->d_progress;
 	if (h->d_tap_cnt) CU(cudaMemsetAsync(h->d_tap_cnt, 0, (size_t)ns * kMaxDemods * 3 * sizeof(uint32_t), sf));   // taps cover one tfr_process
+
+	// demodulators over the windows of one back-end part (BackParams::part_lo/part_hi, blocks [tile0, tile0+n_tiles))
+	auto launch_demods = [&](BackParams q, int part) -> int {
+		if (!h->dcfg.n_demods) return TFR_OK;
+		// fm_dev on the back stream, part after part (a window's filter warm-up reads the values of earlier parts)
+		if (h->has_fm) { CU(launch_devfm(q, sb)); h->stats.kernel_launches += 1; }
+		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
+		if (has_win) {
+			cudaStream_t sw = h->part_stream[part], sl_ = h->part_long[part];
+			CU(cudaEventRecord(h->part_fm[part], sb));
+			if (h->long_split) {
+				// the long window chains (telegrams, retriggered noise), one warp each, beside the rest
+				q.long_split = 1;
+				CU(cudaStreamWaitEvent(sl_, h->part_fm[part], 0));
+				CU(launch_winlong(q, h->dcfg.n_demods, sl_));
+				CU(cudaEventRecord(h->part_ldone[part], sl_));
+				h->stats.kernel_launches += 1;
+			}
+			CU(cudaStreamWaitEvent(sw, h->part_fm[part], 0));
+			CU(launch_win(q, h->dcfg.n_demods, sw));
+			CU(cudaEventRecord(h->part_done[part], sw));
+			h->stats.kernel_launches += 1;
+		}
+		return TFR_OK;
+	};
+	// everything after the window kernels (WeatherHub walk, verifier, parsers) waits for every part
+	auto join_parts = [&](int n) -> int {
+		const bool has_win = h->dcfg.n_demods && (h->has_fm || (h->dcfg.d[0].kind == K_TFA1));
+		if (!has_win) return TFR_OK;
+		for (int k = 0; k < n; k++) {
+			CU(cudaStreamWaitEvent(sb, h->part_done[k], 0));
+			if (h->long_split) CU(cudaStreamWaitEvent(sb, h->part_ldone[k], 0));
+		}
+		return TFR_OK;
+	};
+	int parts_done = 0, part_tile0 = 0;   // back-end parts already queued, first block of the next one
 
 	// ---- front: decimate + trigger, threshold walk
 	{   // the pair recorded by this slot's previous call has not been read yet if no tfr_sync came in between
@@ -571,7 +641,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	CU(cudaEventRecord(sl.fe0, sf));
 	{
 		// at least 8192 blocks (512 MiB, ~18 waves of CTAs) per launch: smaller launches only add tails
-		const int n_chunks = (int)std::min<size_t>(kFrontChunks, std::max<size_t>(1, total / 8192));
+		const int n_chunks = (int)std::min<size_t>(kFrontChunks, std::max<size_t>(1, total / h->min_chunk));
 		const int per = (int)((max_blocks + n_chunks - 1) / n_chunks);
 		CU(cudaStreamWaitEvent(h->stream_walk, sl.fe0, 0));   // the walk stream starts after everything queued so far
 		CU(cudaStreamWaitEvent(h->stream_fe2, sl.fe0, 0));
@@ -588,8 +658,29 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			if (k & 1) last_odd = k;
 			CU(cudaStreamWaitEvent(h->stream_walk, h->chunk_ev[k], 0));
 			bp.n_tiles = fp.n_tiles;
+			// Back-end part j is queued as soon as the walk has passed its last chunk: it decodes the windows that are
+			// complete by then while the front-end streams on (the window kernels are latency bound and leave the SMs'
+			// issue slots and most of their shared memory to it).  The last part follows the whole front (below).
+			const int n_parts = (h->pipelined && h->dcfg.n_demods) ? std::min(h->be_parts, n_chunks) : 1;
+			const int j = parts_done;
+			const bool part_end = (j + 1 < n_parts) && (k + 1 == (j + 1) * n_chunks / n_parts);
+			bp.part_idx = part_end ? j : -1;
 			CU(launch_thresh2(bp, h->stream_walk));
+			bp.part_idx = -1;
 			h->stats.kernel_launches += 2;
+			if (part_end) {
+				CU(cudaEventRecord(h->part_ev[j], h->stream_walk));
+				CU(cudaStreamWaitEvent(sb, h->part_ev[j], 0));
+				BackParams q = bp;
+				q.tile0 = part_tile0;
+				q.n_tiles = fp.tile0 + fp.n_tiles - part_tile0;
+				q.part_lo = j - 1;
+				q.part_hi = j;
+				rc = launch_demods(q, j);
+				if (rc) return rc;
+				part_tile0 = fp.tile0 + fp.n_tiles;
+				parts_done = j + 1;
+			}
 		}
 		if (last_odd >= 0) CU(cudaStreamWaitEvent(sf, h->chunk_ev[last_odd], 0));
 		CU(cudaEventRecord(sl.fe1, sf));
@@ -626,6 +717,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
 			h->fe_ms_acc += a;
 			h->stats.fallback_epochs += (uint32_t)n_fallback;
+			part_tile0 = 0;   // the redone blocks hold more samples than the parts before saw: the last part's fm_dev pass covers everything
 		}
 	}
 	CU(launch_save_history(sl.d_jobs, h->d_state, ns, sf));
@@ -638,21 +730,16 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.tile0 = 0;
 	bp.n_tiles = (int)max_blocks;
 	if (h->dcfg.n_demods) {
-		if (h->has_fm) { CU(launch_devfm(bp, sb)); h->stats.kernel_launches += 1; }
-		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
-		if (has_win) {
-			if (h->long_split) {
-				// the long window chains (telegrams, retriggered noise), one warp each, first and beside the rest
-				bp.long_split = 1;
-				CU(cudaEventRecord(h->long_ev[0], sb));
-				CU(cudaStreamWaitEvent(h->stream_long, h->long_ev[0], 0));
-				CU(launch_winlong(bp, h->dcfg.n_demods, h->stream_long));
-				CU(cudaEventRecord(h->long_ev[1], h->stream_long));
-				h->stats.kernel_launches += 1;
-			}
-			CU(launch_win(bp, h->dcfg.n_demods, sb));
-			h->stats.kernel_launches += 1;
-			if (h->long_split) CU(cudaStreamWaitEvent(sb, h->long_ev[1], 0));
+		{   // the last part: every window the parts before it did not take
+			BackParams q = bp;
+			q.tile0 = part_tile0;
+			q.n_tiles = (int)max_blocks - part_tile0;
+			q.part_lo = parts_done - 1;
+			q.part_hi = -1;
+			rc = launch_demods(q, parts_done);
+			if (rc) return rc;
+			rc = join_parts(parts_done + 1);
+			if (rc) return rc;
 		}
 		if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, sb)); h->stats.kernel_launches += 1; }
 		CU(launch_verify(bp, h->dcfg.n_demods, sb));

@@ -253,7 +253,15 @@ struct BackParams {
 	int demod;               // kernels that run per registered demod: which one
 	int max_blocks;
 	int long_split;          // 1: win_kernel leaves the long window chains to winlong_kernel
+	// The back-end of a call runs in PARTS, each as soon as the threshold walk has passed a chunk of blocks, beside the
+	// front-end of the following chunks.  partcnt[k][stream].n[d] = number of leading windows of demod d that part k and
+	// the parts before it cover: all closed, ending before the blocks walked so far, and cut at a chain head (so that
+	// no window chain straddles two parts).  Written by thresh2_kernel (part_idx >= 0), read by the window kernels.
+	WinCount *partcnt;       // [kMaxParts][n_streams]
+	int part_idx;            // thresh2_kernel: which row of partcnt this launch fills, -1 none
+	int part_lo, part_hi;    // window kernels: rows of partcnt bounding the windows of this launch (lo -1: from window 0, hi -1: to the end)
 };
+constexpr int kMaxParts = 8;
 
 }  // namespace tfr
 
