@@ -463,6 +463,41 @@ __global__ void __launch_bounds__(128) devfm_kernel(const BackParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// devfm_win_kernel: fm_dev for the samples the demodulators will actually read.
+//
+// devfm_kernel above works from the block descriptors, i.e. on every sample the front-end kept: with the auto
+// threshold that is everything above the call's speculative LOWER bound, about a quarter of all samples, of which the
+// demodulators - which run on the true threshold - read a seventh.  Once the threshold walk has listed the windows the
+// needed samples are known: a demodulator with timeout T is active on the union of [t, t+T-1] over the true triggers
+// t, so the windows of the fm_dev-using demodulator with the LONGEST timeout (BackParams::demod) contain every sample
+// any of them reads, warm-up histories included (those are earlier windows).  One CTA per window.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) devfm_win_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	const int demod = p.demod;
+	const uint32_t n_win = p.wincnt[stream].n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
+	const uint32_t *d = p.dec + (size_t)job.dec_off * kBlockDec;
+	int32_t *o = p.devfm + (size_t)job.dec_off * kBlockDec;
+	const StreamState *st = p.st + stream;
+	const uint32_t prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
+	for (uint32_t w = blockIdx.x; w < n_win; w += gridDim.x) {
+		const WinEntry e = wl[w];
+		if (e.start >= call_len) break;
+		const uint32_t last = min(e.end, call_len - 1);
+		for (uint32_t m = e.start + threadIdx.x; m <= last; m += blockDim.x) {
+			const uint32_t cw = d[m], lw = (m == 0) ? prev_last : d[m - 1];   // the sample before a window's trigger is always stored
+			o[m] = fm_dev_fast((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)(int16_t)(lw & 0xffff),
+					   (int)(int16_t)(lw >> 16));
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // window context shared by the speculative kernels and the verifier's slow path
 // ------------------------------------------------------------------------------------------------
 struct WinCtx {
@@ -1948,6 +1983,14 @@ cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)
 {
 	if (p.n_tiles <= 0) return cudaSuccess;
 	devfm_kernel<<<dim3(p.n_tiles, p.n_streams), 128, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s)
+{
+	if (p.max_blocks <= 0) return cudaSuccess;
+	int gx = p.max_blocks;   // about one window per block and demodulator
+	gx = gx < 1 ? 1 : (gx > 2048 ? 2048 : gx);
+	devfm_win_kernel<<<dim3(gx, p.n_streams), 128, 0, s>>>(p);
 	return cudaGetLastError();
 }
 static dim3 win_grid(const BackParams &p, int n_demods, int threads)

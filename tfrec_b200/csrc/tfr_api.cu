@@ -22,6 +22,7 @@ int frontend_tc_encode(const void *iq, uint32_t n_blocks, void *out);
 cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream);
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
+cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s);
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
@@ -135,6 +136,7 @@ struct tfr_handle {
 	double fe_ms_acc = 0;              // fallback front-end launches (timed synchronously, rare)
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> fe_pending;   // front-end event pairs not yet read
 	bool has_fm = false, has_whb = false;
+	int fm_demod = -1;                 // the fm_dev-using demodulator with the longest timeout: its windows contain the others'
 	// input arena for host submits: normally one chunk; more are added when a later submit does not
 	// fit while earlier ones are still pending, and merged into one the next time the arena is idle
 	struct Chunk { uint8_t *ptr; size_t cap, used; };
@@ -286,7 +288,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	memset(&h->stats, 0, sizeof(h->stats));
 	build_config(*cfg, h->dcfg);
 	for (int k = 0; k < h->dcfg.n_demods; k++) {
-		h->has_fm |= (h->dcfg.d[k].kind == K_TFA2 || h->dcfg.d[k].kind == K_TFA3 || h->dcfg.d[k].kind == K_TX22);
+		if (h->dcfg.d[k].kind == K_TFA2 || h->dcfg.d[k].kind == K_TFA3 || h->dcfg.d[k].kind == K_TX22) {
+			h->has_fm = true;
+			if (h->fm_demod < 0 || h->dcfg.d[k].timeout > h->dcfg.d[h->fm_demod].timeout) h->fm_demod = k;
+		}
 		h->has_whb |= (h->dcfg.d[k].kind == K_WHB);
 	}
 	h->pend.resize(cfg->n_streams);
@@ -597,8 +602,18 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	// demodulators over the windows of one back-end part (BackParams::part_lo/part_hi, blocks [tile0, tile0+n_tiles))
 	auto launch_demods = [&](BackParams q, int part) -> int {
 		if (!h->dcfg.n_demods) return TFR_OK;
-		// fm_dev on the back stream, part after part (a window's filter warm-up reads the values of earlier parts)
-		if (h->has_fm) { CU(launch_devfm(q, sb)); h->stats.kernel_launches += 1; }
+		// fm_dev on the back stream, part after part (a window's filter warm-up reads the values of earlier parts).  A call
+		// that runs as ONE part knows every window by now and computes fm_dev only inside them; parts work from the
+		// blocks' descriptors (the demodulators' part cuts differ, so no single window list bounds a part's samples)
+		if (h->has_fm) {
+			if (q.part_lo < 0 && q.part_hi < 0 && !getenv("TFR_DEVFM_BLOCKS")) {
+				q.demod = h->fm_demod;
+				CU(launch_devfm_win(q, sb));
+			} else {
+				CU(launch_devfm(q, sb));
+			}
+			h->stats.kernel_launches += 1;
+		}
 		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
 		if (has_win) {
 			cudaStream_t sw = h->part_stream[part], sl_ = h->part_long[part];
