@@ -213,6 +213,21 @@ def test_hot_path_against_oracle_and_reference(tb, golden, hot_fixture, name, la
     rx.close()
 
 
+@pytest.mark.parametrize("name", ["mixed5", "cont_noisy"])
+def test_filter_chains_ahead_of_the_slicers(tb, hot_fixture, monkeypatch, name):
+    """TFR_BE=chains: the TFA_2-family low-pass runs ahead of the slicers as chains over four windows (biq_kernel),
+    proven and repaired by biq_verify_kernel; the window kernels then only slice.  An opt-in variant of the back-end
+    (slower on B200) that has to give the reference's results like the default: frames, records, block
+    trace, threshold and every fm_dev / iir2::step value"""
+    monkeypatch.setenv("TFR_BE", "chains")
+    iq = hot_fixture(name)
+    rx = tb.Receiver(types=0x2F, thresh=0, flags=tb.FLAG_TAPS)
+    rx.submit(0, iq)
+    rx.process()
+    compare_with_oracle(rx, iq, 0x2F, 0, 0)
+    rx.close()
+
+
 def test_streaming_submits_carry_state(tb, hot_fixture):
     iq = hot_fixture("mixed5")
     rx = tb.Receiver(types=0x2F, thresh=0)

@@ -505,6 +505,7 @@ struct WinCtx {
 	int stream, demod;
 	const uint32_t *dec;     // this stream's sparse decimated samples, indexed by position in the call
 	const int32_t *devfm;
+	int32_t *ld;             // filter chains: this demodulator's pre-filtered slicer inputs (int)y, indexed like devfm; else null
 	uint32_t call_len;
 	uint32_t prev_last;      // sample before position 0
 	int64_t base_pos;        // blocks_done * 8192
@@ -743,10 +744,13 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	// the slicer levels only move while bitcnt < 10: keep them out of the per-sample chain
 	int noffset = __double2int_rz(__dmul_rn(0.9, (double)offset));
 	int hi = noffset + dmax / 32, lo = noffset + dmin / 32;
-	const int4 *src4 = reinterpret_cast<const int4 *>(c.devfm);
+	// filter chains (biq_kernel) ran ahead: the slicer inputs (int)y are read instead of being filtered here
+	const bool pre = c.ld != nullptr;
+	const int32_t *fsrc = pre ? c.ld : c.devfm;
+	const int4 *src4 = reinterpret_cast<const int4 *>(fsrc);
 	prefetch_l1(c.dec + (e.start & ~31u));        // the first bits' rssi reads I/Q (tfa2.cpp:373)
 	if ((e.start & ~31u) + 32 <= last) {
-		prefetch_l1(c.devfm + (e.start & ~31u) + 32);
+		prefetch_l1(fsrc + (e.start & ~31u) + 32);
 		prefetch_l1(c.dec + (e.start & ~31u) + 32);
 	}
 	// sample m is an edge candidate: (ld > hi || ld < lo) && bit != last_bit  (tfa2.cpp:386-412)
@@ -785,7 +789,7 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	int4 v4 = nxt;
 	if (cb + 4 <= last) nxt = src4[(cb + 4) >> 2];
 	if ((cb & 31u) == 0 && cb + 64 <= last) {   // the line after next: an L2 round trip is ~1 us
-		prefetch_l1(c.devfm + cb + 64);
+		prefetch_l1(fsrc + cb + 64);
 		if (bitcnt < 10) prefetch_l1(c.dec + cb + 64);
 	}
 #ifdef TFR_WIN_PROFILE
@@ -797,11 +801,13 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		// per-sample state machine follows: level tracking while bitcnt < 10 (tfa2.cpp:365-374), then the - rare -
 		// edge candidates, in order.  (A window's first and last partial group take the per-sample loop below.)
 		if ((cb & (kBlockDec - 1)) == 0 && cb != e.start && lbi) lbi -= kIdxPerBlock;   // demodulator::start of a new block
+		int l0 = v4.x, l1 = v4.y, l2 = v4.z, l3 = v4.w;
+		if (!pre) {
 		const double y0 = biquad_step(lp, k, int_to_double(v4.x));
 		const double y1 = biquad_step(lp, k, int_to_double(v4.y));
 		const double y2 = biquad_step(lp, k, int_to_double(v4.z));
 		const double y3 = biquad_step(lp, k, int_to_double(v4.w));
-		const int l0 = trunc_to_int(y0), l1 = trunc_to_int(y1), l2 = trunc_to_int(y2), l3 = trunc_to_int(y3);
+		l0 = trunc_to_int(y0); l1 = trunc_to_int(y1); l2 = trunc_to_int(y2); l3 = trunc_to_int(y3);
 		hash.add(l0);
 		hash.add(l1);
 		hash.add(l2);
@@ -819,6 +825,7 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 				for (int j = 0; j < 4; j++)
 					if (ti + j < c.p->tap_cap) { c.p->tap_i32[0][tbase + ti + j] = dv[j]; c.p->tap_f64[tbase + ti + j] = yv[j]; }
 			}
+		}
 		}
 		auto sample = [&](uint32_t m, int ld) {
 			if (bitcnt < 10) {
@@ -857,16 +864,19 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		if (m < e.start || m > last) continue;
 		const int index = 2 * (int)(m & (kBlockDec - 1));
 		if (index == 0 && m != e.start && lbi) lbi -= kIdxPerBlock;
-		const double y = biquad_step(lp, k, int_to_double(dev0));
-		if (taps) {
-			const uint32_t ti = e.cum + (m - e.start);
-			if (ti < c.p->tap_cap) {
-				c.p->tap_i32[0][tbase + ti] = dev0;
-				c.p->tap_f64[tbase + ti] = y;
+		int ld = dev0;
+		if (!pre) {
+			const double y = biquad_step(lp, k, int_to_double(dev0));
+			if (taps) {
+				const uint32_t ti = e.cum + (m - e.start);
+				if (ti < c.p->tap_cap) {
+					c.p->tap_i32[0][tbase + ti] = dev0;
+					c.p->tap_f64[tbase + ti] = y;
+				}
 			}
+			ld = trunc_to_int(y);
+			hash.add(ld);
 		}
-		const int ld = trunc_to_int(y);
-		hash.add(ld);
 		if (bitcnt < 10) {
 			if (ld > dmax || ld < dmin) {
 				// the levels are pure functions of dmax/dmin (tfa2.cpp:366-368, 380-381): recompute them only when one moved
@@ -933,10 +943,250 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 	c.demod = demod;
 	c.dec = p.dec + (size_t)job.dec_off * kBlockDec;
 	c.devfm = p.devfm ? p.devfm + (size_t)job.dec_off * kBlockDec : nullptr;
+	c.ld = (p.ld && p.fm_slot[demod] >= 0) ? p.ld + (size_t)p.fm_slot[demod] * p.ld_stride + (size_t)job.dec_off * kBlockDec : nullptr;
 	c.call_len = job.n_blocks * (uint32_t)kBlockDec;
 	c.prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
 	c.base_pos = st->blocks_done * (int64_t)kBlockDec;
 	return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Filter chains: biq_kernel + biq_verify_kernel (TFA_2 / TFA_3 / TX22).
+//
+// The biquad is the one part of a TFA_2-family demodulator that never resets (tfa2.cpp:325-334), so a window's first
+// filter state depends on everything before it.  Speculating that state per WINDOW (win_kernel's warm-up over the
+// preceding three timeouts) makes every sample pass the filter four times, inside the slow, divergent slicer threads.
+// Here the filter runs ahead of the slicers and on its own: one thread per CHAIN of kBiqK consecutive windows, a
+// warm-up of TFR_BIQ_WARM_X4 quarter timeouts once per chain, then nothing but the recurrence (four dependent FP64
+// operations per sample), writing the slicer input (int)y of every window sample to `ld`.  biq_verify_kernel then
+// proves the chains link up - a chain's assumed start outputs must be bitwise the outputs its predecessor left - and
+// re-filters the ones that do not, in parallel rounds, exactly like verify_kernel does for whole windows.  After it
+// `ld` holds what the reference's filter would have produced, bit for bit, and the window kernels only slice.
+// ------------------------------------------------------------------------------------------------
+#ifndef TFR_BIQ_WARM_X4
+#define TFR_BIQ_WARM_X4 16   // warm-up length in quarter timeouts (amortised over kBiqK windows)
+#endif
+constexpr int kBiqThreads = 64;
+#ifdef TFR_BIQ_PROFILE
+__device__ unsigned long long g_biqprof[8];   // max chain cycles, its steps; sum of cycles, sum of steps, chains; max steps, its cycles
+#endif
+
+// The recurrence over the samples [a, b] of one window: (int)y into ld (STORE; taps from index tap0 on), filter state
+// in lp_io.  Whole 128-byte lines run as batches of 32 samples with the eight loads of the NEXT batch in flight while
+// the current one is filtered; the partial lines at both ends go sample by sample (a neighbouring window of another
+// chain may share a 16-byte group with this span, so only the span's own elements are written).
+// Measured on B200 (in-kernel clocks, bench workload, ~1 warp per scheduler: the kernel is latency bound): this form
+// 140 cycles per sample; four samples per load 177; one masked loop over lines for all lanes of a warp 250; the same
+// with the lines loaded and stored cooperatively through shared memory 420.  The recurrence itself needs 32.
+template <bool STORE>
+static __device__ __forceinline__ void biq_span(const WinCtx &c, const BiquadCoef &k, Biquad &lp_io, uint32_t a, uint32_t b, uint32_t tap0)
+{
+	Biquad lp = lp_io;   // keep the recurrence in registers
+	const bool taps = STORE && c.p->tap_cap != 0;
+	const size_t tbase = ((size_t)c.stream * kMaxDemods + c.demod) * c.p->tap_cap;
+	auto step = [&](uint32_t m, int dv) -> int {
+		const double y = biquad_step(lp, k, int_to_double(dv));
+		if (taps) {
+			const uint32_t ti = tap0 + (m - a);
+			if (ti < c.p->tap_cap) {
+				c.p->tap_i32[0][tbase + ti] = dv;
+				c.p->tap_f64[tbase + ti] = y;
+			}
+		}
+		return trunc_to_int(y);
+	};
+	uint32_t m = a;
+	const uint32_t first_full = (a + 31u) & ~31u;
+	if (first_full + 31 <= b) prefetch_l1(c.devfm + first_full);   // on its way while the head is walked
+#pragma unroll 1
+	for (; (m & 31u) && m <= b; m++) {
+		const int l = step(m, c.devfm[m]);
+		if (STORE) c.ld[m] = l;
+	}
+	if (m + 31 <= b) {
+		const int4 *src4 = reinterpret_cast<const int4 *>(c.devfm);
+		int4 *dst4 = reinterpret_cast<int4 *>(c.ld);
+		int4 cur[8], nx[8];
+#pragma unroll
+		for (int q = 0; q < 8; q++) cur[q] = src4[(m >> 2) + q];
+		for (; m + 31 <= b; m += 32) {
+			const bool more = m + 63 <= b;
+			if (!more && m + 32 <= b) prefetch_l1(c.devfm + m + 32);   // the tail's line
+#pragma unroll
+			for (int q = 0; q < 8; q++) nx[q] = more ? src4[((m + 32) >> 2) + q] : cur[q];
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				int4 o;
+				o.x = step(m + 4 * q, cur[q].x);
+				o.y = step(m + 4 * q + 1, cur[q].y);
+				o.z = step(m + 4 * q + 2, cur[q].z);
+				o.w = step(m + 4 * q + 3, cur[q].w);
+				if (STORE) dst4[(m >> 2) + q] = o;
+			}
+#pragma unroll
+			for (int q = 0; q < 8; q++) cur[q] = nx[q];
+		}
+	}
+#pragma unroll 1
+	for (; m <= b; m++) {
+		const int l = step(m, c.devfm[m]);
+		if (STORE) c.ld[m] = l;
+	}
+	lp_io = lp;
+}
+// the windows [v, w_end) of one demodulator: window v from sample `from` on, the others whole; windows before w0 are
+// warm-up history, from w0 on (int)y goes to ld.  r: the filter outputs at the first stored sample and after the last.
+static __device__ __forceinline__ void biq_walk(const WinCtx &c, const BiquadCoef &k, const WinEntry *wl, uint32_t v, uint32_t from, uint32_t w0,
+						uint32_t w_end, Biquad &lp, BiqRec &r)
+{
+	for (uint32_t u = v; u < w0; u++) biq_span<false>(c, k, lp, (u == v) ? from : wl[u].start, wl[u].end, 0u);
+	r.u_y0 = lp.y0;
+	r.u_y1 = lp.y1;
+	for (uint32_t u = w0; u < w_end; u++) {
+		const WinEntry e = wl[u];
+		biq_span<true>(c, k, lp, e.start, min(e.end, c.call_len - 1), e.cum);
+	}
+	r.e_y0 = lp.y0;
+	r.e_y1 = lp.y1;
+}
+constexpr unsigned kFullMask = 0xffffffffu;
+// the filter's input history at the end of window v (d1 = last, d2 = the one before), v >= 0
+static __device__ __forceinline__ void biq_inputs_after(const WinCtx &c, const WinEntry *wl, int v, const DemodState &carry0, Biquad &lp)
+{
+	const WinEntry e = wl[v];
+	const uint32_t last = min(e.end, c.call_len - 1);
+	lp.d1 = (double)c.devfm[last];
+	if (last >= e.start + 1) lp.d2 = (double)c.devfm[last - 1];
+	else if (v > 0) lp.d2 = (double)c.devfm[min(wl[v - 1].end, c.call_len - 1)];   // one-sample window
+	else lp.d2 = carry0.lp.d1;
+}
+
+__global__ void __launch_bounds__(kBiqThreads) biq_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y;
+	const int demod = (int)blockIdx.z;
+	if (p.fm_slot[demod] < 0) return;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	const StreamState *st = p.st + stream;
+	uint32_t n_win = p.wincnt[stream].n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	BiqRec *bl = p.biq + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	const BiquadCoef k = cfg.lp;
+	while (n_win && wl[n_win - 1].start >= c.call_len) n_win--;   // windows beyond the data do not filter anything
+	for (uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch * (uint32_t)kBiqK < n_win; ch += gridDim.x * blockDim.x) {
+		const bool on = true;
+		const uint32_t w0 = ch * (uint32_t)kBiqK, w_end = min(n_win, w0 + (uint32_t)kBiqK);
+		Biquad lp = st->d[demod].lp;   // chain 0 starts from the state the previous call left: nothing to speculate
+		BiqRec r;
+		uint32_t v = w0, from = wl[w0].start;
+		if (w0 != 0) {
+			// warm-up over the samples of the preceding windows (the filter's actual history); reaching window 0 means
+			// the true carried state can be used
+			const uint32_t want = ((uint32_t)TFR_BIQ_WARM_X4 * (uint32_t)cfg.timeout) / 4u;
+			uint32_t have = 0;
+			while (v > 0 && have < want) {
+				v--;
+				const uint32_t len = wl[v].end - wl[v].start + 1;
+				if (have + len >= want && v > 0) {
+					from = wl[v].end + 1 - (want - have);
+					have = want;
+				} else {
+					from = wl[v].start;
+					have += len;
+				}
+			}
+			if (!(v == 0 && from == wl[0].start)) lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
+		}
+#ifdef TFR_BIQ_PROFILE
+		const long long bp_t0 = clock64();
+#endif
+		biq_walk(c, k, wl, v, from, w0, w_end, lp, r);
+#ifdef TFR_BIQ_PROFILE
+		if (on) {
+			const unsigned long long cyc = (unsigned long long)(clock64() - bp_t0);
+			unsigned long long steps = wl[v].end - from + 1;
+			for (uint32_t u = v + 1; u < w_end; u++) steps += min(wl[u].end, c.call_len - 1) - wl[u].start + 1;
+			atomicMax(&g_biqprof[0], (cyc << 20) | min(steps, 0xfffffull));
+			atomicAdd(&g_biqprof[2], cyc);
+			atomicAdd(&g_biqprof[3], steps);
+			atomicAdd(&g_biqprof[4], 1ull);
+			atomicMax(&g_biqprof[5], (steps << 32) | min(cyc, 0xffffffffull));
+		}
+#endif
+		if (on) bl[w0] = r;
+	}
+}
+
+// one CTA per (stream, demod): proves that the chains link up, re-filters the ones that do not (rounds: a chain
+// repaired from a predecessor that was itself still wrong is simply flagged again; the first bad chain of a round
+// always starts from a proven state, so every round proves at least one more chain), then leaves the biquad state
+// after the call's last window sample in StreamState::lp_next.
+constexpr int kBiqVerThreads = 128;
+__global__ void __launch_bounds__(kBiqVerThreads) biq_verify_kernel(const BackParams p)
+{
+	const int nd = p.cfg->n_demods;
+	const int stream = blockIdx.x / nd, demod = blockIdx.x % nd;
+	if (stream >= p.n_streams || p.fm_slot[demod] < 0) return;
+	const DemodCfg &cfg = p.cfg->d[demod];
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	StreamState *st = p.st + stream;
+	uint32_t n_win = p.wincnt[stream].n[demod];
+	const WinEntry *wl = p.wins + job.win_off + (size_t)demod * job.win_cap;
+	BiqRec *bl = p.biq + job.win_off + (size_t)demod * job.win_cap;
+	const WinCtx c = make_ctx(p, stream, demod, job, st);
+	const BiquadCoef k = cfg.lp;
+	const DemodState &carry0 = st->d[demod];
+	while (n_win && wl[n_win - 1].start >= c.call_len) n_win--;   // windows beyond the data do not filter anything
+	const uint32_t n_ch = (n_win + (uint32_t)kBiqK - 1) / (uint32_t)kBiqK;
+	__shared__ uint32_t s_bad[kBiqVerThreads];
+	__shared__ uint32_t s_n, s_first;
+	uint32_t n_fix = 0;
+	for (;;) {
+		if (threadIdx.x == 0) {
+			s_n = 0;
+			s_first = 0xffffffffu;
+		}
+		__syncthreads();
+		for (uint32_t ch = 1 + threadIdx.x; ch < n_ch; ch += kBiqVerThreads) {
+			const BiqRec &a = bl[(ch - 1) * kBiqK], &b = bl[ch * kBiqK];
+			if (__double_as_longlong(b.u_y0) != __double_as_longlong(a.e_y0) || __double_as_longlong(b.u_y1) != __double_as_longlong(a.e_y1)) {
+				const uint32_t q = atomicAdd(&s_n, 1u);
+				if (q < (uint32_t)kBiqVerThreads) s_bad[q] = ch;
+				atomicMin(&s_first, ch);
+			}
+		}
+		__syncthreads();
+		const uint32_t nb = min(s_n, (uint32_t)kBiqVerThreads);
+		if (nb == 0) break;
+		if (threadIdx.x == 0 && s_n > (uint32_t)kBiqVerThreads) s_bad[0] = s_first;   // the certain one is in every round
+		__syncthreads();
+		if (threadIdx.x < nb) {
+			const uint32_t ch = s_bad[threadIdx.x], w0 = ch * (uint32_t)kBiqK;
+			Biquad lp;
+			lp.y0 = bl[w0 - kBiqK].e_y0;
+			lp.y1 = bl[w0 - kBiqK].e_y1;
+			biq_inputs_after(c, wl, (int)w0 - 1, carry0, lp);
+			BiqRec r;
+			biq_walk(c, k, wl, w0, wl[w0].start, w0, min(n_win, w0 + (uint32_t)kBiqK), lp, r);
+			bl[w0] = r;
+			n_fix++;
+		}
+		__syncthreads();
+	}
+	if (n_fix) atomicAdd(&p.counters->rerun_biquad, n_fix);
+	if (threadIdx.x == 0) {
+		Biquad lp = carry0.lp;
+		if (n_win) {
+			lp.y0 = bl[(n_ch - 1) * kBiqK].e_y0;
+			lp.y1 = bl[(n_ch - 1) * kBiqK].e_y1;
+			biq_inputs_after(c, wl, (int)n_win - 1, carry0, lp);
+		}
+		st->lp_next[demod] = lp;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1042,6 +1292,8 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 				bool far = true;
 				if (w == 0) {
 					far = false;
+				} else if (w == w0 && c.ld) {
+					// filter chains ran ahead (biq_kernel): the slicer reads their output, there is no filter state here
 				} else if (w == w0) {
 					// biquad warm-up over the samples of the preceding windows of this demod (they are the
 					// filter's actual history); reaching window 0 means the true carried state can be used
@@ -1168,7 +1420,6 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 // ballot mask) are executed by all lanes redundantly.  A sample then costs ~40 cycles instead of ~500.  The
 // arithmetic, its order and every recorded value are those of run_tfa1_window / run_tfa2_window.
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned kFullMask = 0xffffffffu;
 
 // n <= 32 consecutive filter steps; dv = this lane's discriminator value devfm[base+lane] (0 for lane >= n), loaded by
 // the caller one batch ahead (an L2/HBM round trip is about as long as the 32 serial steps).  Returns this lane's
@@ -1292,16 +1543,22 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 			nb += (uint32_t)kBlockDec;
 		}
 	};
-	int dvn = (e.start + lane <= last) ? c.devfm[e.start + lane] : 0;
+	const bool pre = c.ld != nullptr;   // filter chains ran ahead: (int)y is read, not filtered here
+	const int32_t *fsrc = pre ? c.ld : c.devfm;
+	int dvn = (e.start + lane <= last) ? fsrc[e.start + lane] : 0;
 	for (uint32_t base = e.start; base <= last; base += 32) {
 		const uint32_t n = min(32u, last - base + 1);
 		const bool on = (uint32_t)lane < n;
 		const uint32_t m = base + lane;
 		const int dv = dvn;
-		dvn = (m + 32 <= last) ? c.devfm[m + 32] : 0;   // the next batch, in flight during this one
-		const double y = biquad_batch(lp, k, dv, n, lane);
-		const int ld = trunc_to_int(y);
-		if (on) {
+		dvn = (m + 32 <= last) ? fsrc[m + 32] : 0;   // the next batch, in flight during this one
+		double y = 0.0;
+		int ld = dv;
+		if (!pre) {
+			y = biquad_batch(lp, k, dv, n, lane);
+			ld = trunc_to_int(y);
+		}
+		if (on && !pre) {
 			const uint32_t i = m - e.start;
 			ha += (uint32_t)ld * (2u * i + 1u);
 			hb += (uint32_t)ld * (i * i + i + 1u);
@@ -1551,6 +1808,8 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 				bool far = true;
 				if (w == 0) {
 					far = false;
+				} else if (w == w0 && c.ld) {
+					// filter chains ran ahead: nothing to warm up
 				} else if (w == w0) {
 					// the same warm-up history as win_kernel, filtered in batches of 32
 					const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)cfg.timeout) / 4u;
@@ -1762,6 +2021,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 	const WinCtx c = make_ctx(p, stream, demod, job, st);
 	const int last_block = (int)job.n_blocks - 1;
 	const DemodState &carry0 = st->d[demod];   // read in place; overwritten only by the final store below
+	const bool pre = c.ld != nullptr;
 	__shared__ uint32_t s_runs[kVerifyThreads];
 	__shared__ uint32_t s_nruns, s_first;
 	uint32_t n_cheap = 0, n_full = 0, n_sr = 0, rounds = 0;
@@ -1779,8 +2039,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 			return tfa1_sync_same(rec, sr);
 		}
 		const WinRec &pr = rl[w - 1];
-		const bool bq = (__double_as_longlong(rec.u_y0) == __double_as_longlong(pr.e_y0)) &&
-				(__double_as_longlong(rec.u_y1) == __double_as_longlong(pr.e_y1));
+		// (with filter chains the slicer inputs were proven by biq_verify_kernel: only last_bit_idx is left to check)
+		const bool bq = pre || ((__double_as_longlong(rec.u_y0) == __double_as_longlong(pr.e_y0)) &&
+					(__double_as_longlong(rec.u_y1) == __double_as_longlong(pr.e_y1)));
 		edge_bad = !tfa2_edge_same(rec, cfg, lbi_after(rl, (int)w - 1, carry0), wl[w].start);
 		return bq && !edge_bad;
 	};
@@ -1846,14 +2107,16 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 					n_sr++;
 				}
 			} else {
-				Biquad lp = biquad_after(c, wl, rl, (int)w - 1, carry0);
+				Biquad lp;
+				lp.d1 = lp.d2 = lp.y0 = lp.y1 = 0.0;
+				if (!pre) lp = biquad_after(c, wl, rl, (int)w - 1, carry0);
 				for (uint32_t v = w; v < n_win; v++) {
 					WinRec rec = rl[v];
 					if (v != w && !(rec.pad & kPadOk) && (rl[v - 1].pad & kPadOk)) break;   // another thread's run
 					const WinEntry e = wl[v];
 					const Lbi l = lbi_after(rl, (int)v - 1, carry0);
-					const bool bq_ok = (__double_as_longlong(rec.u_y0) == __double_as_longlong(lp.y0)) &&
-							   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp.y1));
+					const bool bq_ok = pre || ((__double_as_longlong(rec.u_y0) == __double_as_longlong(lp.y0)) &&
+								   (__double_as_longlong(rec.u_y1) == __double_as_longlong(lp.y1)));
 					const bool edge_ok = tfa2_edge_same(rec, cfg, l, e.start);
 					if (bq_ok && edge_ok) break;   // consistent from here on
 					bool full = !edge_ok;
@@ -1936,7 +2199,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 		out.sr = sr_end;
 	} else {
 		const Lbi l = lbi_after(rl, (int)n_win - 1, carry0);
-		const Biquad lp_end = biquad_after(c, wl, rl, (int)n_win - 1, carry0);
+		const Biquad lp_end = pre ? st->lp_next[demod] : biquad_after(c, wl, rl, (int)n_win - 1, carry0);
 		const int lbi_end = lbi_at_block(l.v, l.block, last_block);
 		DemodState &out = st->d[demod];
 		if (unfinished) {
@@ -1983,6 +2246,31 @@ cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)
 {
 	if (p.n_tiles <= 0) return cudaSuccess;
 	devfm_kernel<<<dim3(p.n_tiles, p.n_streams), 128, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_biq(const BackParams &p, int n_demods, cudaStream_t s)
+{
+	if (p.max_blocks <= 0) return cudaSuccess;
+	int gx = (p.max_blocks * 2 / kBiqK + kBiqThreads - 1) / kBiqThreads;   // about one window per block and demodulator
+	gx = gx < 1 ? 1 : (gx > 256 ? 256 : gx);
+#ifdef TFR_BIQ_PROFILE
+	{
+		unsigned long long z[8] = { 0 }, r[8];
+		cudaStreamSynchronize(s);
+		cudaMemcpyToSymbol(g_biqprof, z, sizeof(z));
+		biq_kernel<<<dim3(gx, p.n_streams, n_demods), kBiqThreads, 0, s>>>(p);
+		cudaStreamSynchronize(s);
+		cudaMemcpyFromSymbol(r, g_biqprof, sizeof(r));
+		fprintf(stderr, "[biqprof] %llu chains, %.0f steps and %.0f cycles on average (%.1f cycles per step); slowest chain %llu cycles for %llu steps; longest chain %llu steps in %llu cycles\n",
+			r[4], (double)r[3] / (r[4] + 1), (double)r[2] / (r[4] + 1), (double)r[2] / (r[3] + 1), r[0] >> 20, r[0] & 0xfffff, r[5] >> 32, r[5] & 0xffffffffull);
+		biq_verify_kernel<<<p.n_streams * n_demods, kBiqVerThreads, 0, s>>>(p);
+		return cudaGetLastError();
+	}
+#endif
+	biq_kernel<<<dim3(gx, p.n_streams, n_demods), kBiqThreads, 0, s>>>(p);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	biq_verify_kernel<<<p.n_streams * n_demods, kBiqVerThreads, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s)

@@ -23,6 +23,7 @@ cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_st
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s);
+cudaError_t launch_biq(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
@@ -99,6 +100,8 @@ struct tfr_handle {
 		BlockTrace *d_trace = nullptr;
 		uint32_t *d_events = nullptr;
 		int32_t *d_devfm = nullptr;
+		int32_t *d_ld = nullptr;                 // filter chains: (int)y per fm demodulator, direct mapped like d_devfm
+		BiqRec *d_biq = nullptr;                 // filter chain records, indexed like d_wins
 		WinEntry *d_wins = nullptr;
 		WinRec *d_recs = nullptr;
 		WinCount *d_wincnt = nullptr;
@@ -136,6 +139,11 @@ struct tfr_handle {
 	double fe_ms_acc = 0;              // fallback front-end launches (timed synchronously, rare)
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> fe_pending;   // front-end event pairs not yet read
 	bool has_fm = false, has_whb = false;
+	int n_fm = 0;                      // fm_dev-using demodulators (each has a slot of Slot::d_ld)
+	int fm_slot[kMaxDemods] = { -1, -1, -1, -1, -1 };
+	bool biq_chains = false;           // TFR_BE=chains: filter chains ahead of the slicers (biq_kernel + biq_verify_kernel, exact, but on
+	                                   // B200 the two latency-bound filter kernels cost 1.1 ms where they save 0.9: DESIGN.md 4.3b);
+	                                   // default: the window kernels warm up and filter for themselves
 	int fm_demod = -1;                 // the fm_dev-using demodulator with the longest timeout: its windows contain the others'
 	// input arena for host submits: normally one chunk; more are added when a later submit does not
 	// fit while earlier ones are still pending, and merged into one the next time the arena is idle
@@ -233,6 +241,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	for (auto &sl : h->slot) {
 		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
+		cudaFree(sl.d_ld); cudaFree(sl.d_biq);
 		for (cudaEvent_t e : { sl.front_done, sl.back_done, sl.fe0, sl.fe1 })
 			if (e) cudaEventDestroy(e);
 	}
@@ -290,6 +299,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	for (int k = 0; k < h->dcfg.n_demods; k++) {
 		if (h->dcfg.d[k].kind == K_TFA2 || h->dcfg.d[k].kind == K_TFA3 || h->dcfg.d[k].kind == K_TX22) {
 			h->has_fm = true;
+			h->fm_slot[k] = h->n_fm++;
 			if (h->fm_demod < 0 || h->dcfg.d[k].timeout > h->dcfg.d[h->fm_demod].timeout) h->fm_demod = k;
 		}
 		h->has_whb |= (h->dcfg.d[k].kind == K_WHB);
@@ -326,6 +336,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 			CUH(cudaStreamCreateWithPriority(&h->part_long[k], cudaStreamNonBlocking, prio_hi));
 		}
 		if (const char *mc = getenv("TFR_MIN_CHUNK")) h->min_chunk = (size_t)std::max(1, atoi(mc));
+		if (const char *be = getenv("TFR_BE")) h->biq_chains = strcmp(be, "chains") == 0;
 		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=tc selects the tensor-core front-end variant
 		h->use_tc = fe && !strcmp(fe, "tc") && frontend_tc_available();
 	}
@@ -397,25 +408,27 @@ static int ensure_blocks(tfr_handle *h, tfr_handle::Slot &sl, size_t blocks, siz
 	if (blocks > sl.cap_blocks) {
 		int rc = sync_all(h);
 		if (rc) return rc;
-		cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_devfm);
-		sl.d_tiles = nullptr; sl.d_dec = nullptr; sl.d_trace = nullptr; sl.d_events = nullptr; sl.d_devfm = nullptr;
+		cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_devfm); cudaFree(sl.d_ld);
+		sl.d_tiles = nullptr; sl.d_dec = nullptr; sl.d_trace = nullptr; sl.d_events = nullptr; sl.d_devfm = nullptr; sl.d_ld = nullptr;
 		sl.cap_blocks = 0;
 		cudaError_t e = cudaMalloc(&sl.d_tiles, blocks * sizeof(TileDesc));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_trace, blocks * sizeof(BlockTrace));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_events, blocks * (size_t)kMaxEvt * sizeof(uint32_t));
 		if (e == cudaSuccess && h->has_fm) e = cudaMalloc(&sl.d_devfm, blocks * (size_t)kBlockDec * sizeof(int32_t));
+		if (e == cudaSuccess && h->has_fm && h->biq_chains) e = cudaMalloc(&sl.d_ld, (size_t)h->n_fm * blocks * (size_t)kBlockDec * sizeof(int32_t));
 		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("work buffers: ") + cudaGetErrorString(e)); }
 		sl.cap_blocks = blocks;
 	}
 	if (wins > sl.cap_wins) {
 		int rc = sync_all(h);
 		if (rc) return rc;
-		cudaFree(sl.d_wins); cudaFree(sl.d_recs);
-		sl.d_wins = nullptr; sl.d_recs = nullptr;
+		cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_biq);
+		sl.d_wins = nullptr; sl.d_recs = nullptr; sl.d_biq = nullptr;
 		sl.cap_wins = 0;
 		cudaError_t e = cudaMalloc(&sl.d_wins, wins * sizeof(WinEntry));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_recs, wins * sizeof(WinRec));
+		if (e == cudaSuccess && h->has_fm && h->biq_chains) e = cudaMalloc(&sl.d_biq, wins * sizeof(BiqRec));
 		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("window lists: ") + cudaGetErrorString(e)); }
 		sl.cap_wins = wins;
 	}
@@ -589,6 +602,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.recs = sl.d_recs;
 	bp.devfm = sl.d_devfm;
 	bp.wincnt = sl.d_wincnt;
+	bp.ld = nullptr;   // set per launch: filter chains need the call's complete window lists (a call that runs as one part)
+	bp.ld_stride = sl.cap_blocks * (size_t)kBlockDec;
+	bp.biq = sl.d_biq;
+	for (int k = 0; k < kMaxDemods; k++) bp.fm_slot[k] = h->fm_slot[k];
 	bp.partcnt = sl.d_partcnt;
 	bp.part_idx = -1;
 	bp.part_lo = bp.part_hi = -1;
@@ -609,6 +626,11 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			if (q.part_lo < 0 && q.part_hi < 0 && !getenv("TFR_DEVFM_BLOCKS")) {
 				q.demod = h->fm_demod;
 				CU(launch_devfm_win(q, sb));
+				if (q.ld) {
+					// the low-pass of the TFA_2-family demodulators ahead of the slicers, in chains of windows, proven
+					CU(launch_biq(q, h->dcfg.n_demods, sb));
+					h->stats.kernel_launches += 2;
+				}
 			} else {
 				CU(launch_devfm(q, sb));
 			}
@@ -746,6 +768,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.n_tiles = (int)max_blocks;
 	if (h->dcfg.n_demods) {
 		{   // the last part: every window the parts before it did not take
+			// (a call that runs as one part knows all its windows now: filter chains, window-driven fm_dev)
+			if (parts_done == 0 && h->has_fm && h->biq_chains && sl.d_ld && !getenv("TFR_DEVFM_BLOCKS")) bp.ld = sl.d_ld;
 			BackParams q = bp;
 			q.tile0 = part_tile0;
 			q.n_tiles = (int)max_blocks - part_tile0;

@@ -104,6 +104,7 @@ struct alignas(128) StreamState {
 	uint32_t win_cont[kMaxDemods];// 1 if demod d's last window of the previous call runs on into the next call
 	DemodState d[kMaxDemods];
 	DemodState fin[kMaxDemods];   // state left by an unfinished (ran out of data) last window, pending verification
+	Biquad lp_next[kMaxDemods];   // filter chains: the proven biquad state after the call's last window sample
 };
 
 // one entry per (stream, block) of a process() call, written by the front-end
@@ -162,6 +163,13 @@ struct WinRec {
 	int32_t lbi_in;               // edge repair: the predecessor chain's last_bit_idx, relative to the window's first block
 	int32_t pad3;
 };
+// Filter chains (biq_kernel): the TFA_2-family low-pass runs ahead of the slicers, as a chain over kBiqK consecutive
+// windows from ONE speculated start state; a chain's record holds the filter outputs it assumed and the ones it left
+struct BiqRec {
+	double u_y0, u_y1;            // biquad outputs assumed at the chain's first sample (after warm-up)
+	double e_y0, e_y1;            // biquad outputs after the chain's last sample
+};
+constexpr int kBiqK = 4;          // windows per filter chain
 constexpr uint32_t kRecRan = 1u, kRecExact = 2u, kRecEdge = 4u, kRecUnfinished = 8u;
 constexpr uint32_t kRecLbiIn = 16u;   // the run used the explicit last_bit_idx in lbi_in instead of the 'far' assumption
 constexpr int32_t kPadOk = 1, kPadEdgeRepair = 2;   // WinRec::pad bits written by flag_kernel
@@ -257,6 +265,11 @@ struct BackParams {
 	// front-end of the following chunks.  partcnt[k][stream].n[d] = number of leading windows of demod d that part k and
 	// the parts before it cover: all closed, ending before the blocks walked so far, and cut at a chain head (so that
 	// no window chain straddles two parts).  Written by thresh2_kernel (part_idx >= 0), read by the window kernels.
+	// filter chains (null / -1: the window kernels filter for themselves)
+	int32_t *ld;             // [fm slot][direct mapped like dec]: (int)y of the demodulator's low-pass, per window sample
+	size_t ld_stride;        // elements per fm slot
+	BiqRec *biq;             // chain records, indexed like wins/recs by the chain's first window
+	int fm_slot[kMaxDemods]; // demod -> slot of ld, -1 none
 	WinCount *partcnt;       // [kMaxParts][n_streams]
 	int part_idx;            // thresh2_kernel: which row of partcnt this launch fills, -1 none
 	int part_lo, part_hi;    // window kernels: rows of partcnt bounding the windows of this launch (lo -1: from window 0, hi -1: to the end)
