@@ -175,6 +175,17 @@ long tfr_decimate(int device, const uint8_t *iq, size_t nbytes, int filter, int1
  * NULL) receives the CUDA-event time of one cascade. */
 long tfr_downconvert(int device, const uint8_t *iq, size_t nbytes, int passes, int filter, int16_t *out, int mem,
 		     int reps, float *kernel_ms);
+/* downconvert as the streaming class of dsp_stuff.h:46-56 (`downconvert(int p)` + `process_iq`): the history of every
+ * stage is carried from call to call, so feeding a stream block by block gives the same samples as feeding it whole.
+ * passes 1..5.  tfr_dc_process takes raw rtl-sdr bytes (what engine.cpp:77-78 converts) and is the fast path (one fused
+ * kernel, csrc/decim_fused.cu); tfr_dc_process_i16 is process_iq's own signature - int16 I,Q in place on the host,
+ * len = number of int16, returns the new len - for callers that hold converted samples.  The number of IQ pairs of a
+ * call must be a multiple of 2^passes (the reference drops an odd trailing sample of a block for good). */
+typedef struct tfr_dc tfr_dc;
+int tfr_dc_create(int device, int passes, tfr_dc **out);
+void tfr_dc_destroy(tfr_dc *h);
+long tfr_dc_process(tfr_dc *h, const uint8_t *iq, size_t nbytes, int filter, int16_t *out, int mem);
+long tfr_dc_process_i16(tfr_dc *h, int16_t *data_iq, int len, int filter);
 /* decoder::store_bytes + flush(0) (main.cpp:45-50, the -X seam) run through the device parser */
 int tfr_parse_bytes(tfr_handle *h, int type, const uint8_t *bytes, int len, tfr_frame *frame,
 		    tfr_record *recs, int max_recs);

@@ -83,6 +83,40 @@ def test_decimator_bit_exact(tb, golden):
             assert sha(d.astype("<i2")) == golden["decimator"][name][key]["sha256"]
 
 
+@pytest.mark.parametrize("passes", [1, 2, 3, 4, 5])
+def test_downconvert_streaming_object(tb, passes):
+    """dsp_stuff.h:46-56 `downconvert(p)` as an object that is fed block by block: raw bytes through the fused kernel,
+    int16 I,Q in place through process_iq's own signature - both against the oracle run over the whole stream"""
+    rng = np.random.default_rng(70 + passes)
+    iq = rng.integers(0, 256, size=2 * 37 * 4096, dtype=np.uint8)
+    for filt in (0, 1):
+        want = ol.downconvert(iq, passes, filt)
+        cuts = [0, 2 * 32, 2 * 32 + 2 * 4096, 2 * 9 * 4096 + 2 * 64, 2 * 9 * 4096 + 2 * 96, 2 * 30 * 4096, iq.size]   # tiny, tile-sized, long
+        dc = tb.Downconvert(passes)
+        got = np.concatenate([dc.process(iq[a:b], filt) for a, b in zip(cuts[:-1], cuts[1:])])
+        dc.close()
+        assert np.array_equal(got, want), "u8 streaming, passes %d filter %d: %d differ" % (passes, filt, int((got != want).sum()))
+        x = ((iq.astype(np.int16) - 128) << 6).astype(np.int16)            # engine.cpp:77-78
+        dc = tb.Downconvert(passes)
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            buf = x[a:b].copy()
+            n = dc.process_iq(buf, filt)
+            parts.append(buf[:n].copy())
+        dc.close()
+        got = np.concatenate(parts)
+        assert np.array_equal(got, want), "int16 streaming, passes %d filter %d" % (passes, filt)
+
+
+def test_downconvert_cascade_variant(tb, monkeypatch):
+    """TFR_DC=cascade: one launch per stage (decim.cu, what passes 6..8 always use) instead of the fused kernel"""
+    monkeypatch.setenv("TFR_DC", "cascade")
+    rng = np.random.default_rng(9)
+    iq = rng.integers(0, 256, size=3 * 65536 + 4096 + 20, dtype=np.uint8)
+    for passes in (1, 3, 5):
+        assert np.array_equal(tb.downconvert(iq, passes, 0), ol.downconvert(iq, passes, 0))
+
+
 def test_tensor_core_front_end_variant_bit_exact(tb, golden, hot_fixture, monkeypatch):
     """frontend_tc.cu (TFR_FE=tc: TMA tensor boxes + tcgen05.mma byte->float conversion + tensor-memory loads) is an
     opt-in variant of the front-end; it has to produce the reference's samples and records like the default kernel"""

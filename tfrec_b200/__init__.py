@@ -23,8 +23,8 @@ FLAG_TAPS, FLAG_KEEP_DECIM = 1, 2
 
 ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_process", "tfr_sync", "tfr_poll_frames",
                "tfr_poll_records", "tfr_clear_results", "tfr_get_thresh", "tfr_read_block_trace", "tfr_read_taps",
-               "tfr_read_decimated", "tfr_decimate", "tfr_downconvert", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error",
-               "tfr_abi_version"]
+               "tfr_read_decimated", "tfr_decimate", "tfr_downconvert", "tfr_dc_create", "tfr_dc_destroy", "tfr_dc_process",
+               "tfr_dc_process_i16", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error", "tfr_abi_version"]
 
 
 class Config(C.Structure):
@@ -101,6 +101,13 @@ def load():
     L.tfr_downconvert.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.POINTER(C.c_float)]
     L.tfr_downconvert.restype = C.c_long
+    L.tfr_dc_create.argtypes = [C.c_int, C.c_int, C.POINTER(P)]
+    L.tfr_dc_destroy.argtypes = [P]
+    L.tfr_dc_destroy.restype = None
+    L.tfr_dc_process.argtypes = [P, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
+    L.tfr_dc_process.restype = C.c_long
+    L.tfr_dc_process_i16.argtypes = [P, C.c_void_p, C.c_int, C.c_int]
+    L.tfr_dc_process_i16.restype = C.c_long
     L.tfr_parse_bytes.argtypes = [P, C.c_int, C.c_char_p, C.c_int, C.POINTER(Frame), C.POINTER(Record), C.c_int]
     L.tfr_get_stats.argtypes = [P, C.POINTER(Stats)]
     L.tfr_last_error.restype = C.c_char_p
@@ -259,6 +266,38 @@ def downconvert(iq: np.ndarray, passes=2, filter=0, device=0):
     out = np.empty(((iq.size // 2) >> passes) * 2, dtype=np.int16)
     n = _check(load().tfr_downconvert(device, iq.ctypes.data, iq.size, passes, filter, out.ctypes.data, MEM_HOST, 1, None))
     return out[:n]
+
+
+class Downconvert:
+    """`downconvert(int p)` of dsp_stuff.h:46-56 as a streaming object: every stage's history is carried between calls"""
+
+    def __init__(self, passes=2, device=0):
+        self.passes = passes
+        self._h = C.c_void_p()
+        _check(load().tfr_dc_create(device, passes, C.byref(self._h)))
+
+    def process(self, iq: np.ndarray, filter=0):
+        """raw u8 IQ (a multiple of 2^passes pairs) -> int16 I,Q"""
+        iq = np.ascontiguousarray(iq, dtype=np.uint8)
+        out = np.empty(((iq.size // 2) >> self.passes) * 2, dtype=np.int16)
+        n = _check(load().tfr_dc_process(self._h, iq.ctypes.data, iq.size, filter, out.ctypes.data, MEM_HOST))
+        return out[:n]
+
+    def process_iq(self, data_iq: np.ndarray, filter=0):
+        """process_iq(int16_t *buf, int len, int filter) itself: int16 I,Q in place; returns the new len"""
+        assert data_iq.dtype == np.int16 and data_iq.flags.c_contiguous
+        return _check(load().tfr_dc_process_i16(self._h, data_iq.ctypes.data, data_iq.size, filter))
+
+    def close(self):
+        if self._h:
+            load().tfr_dc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def downconvert_device(iq_ptr, nbytes, out_ptr, passes=2, filter=0, device=0, reps=1):

@@ -150,8 +150,9 @@ static cudaError_t launch_stage(const void *in, int16_t *out, long long n_in, lo
 
 // iq: device pointer to n_pairs raw IQ pairs; tmp[0], tmp[1]: device int16 buffers of >= n_pairs/2 and >= n_pairs/4
 // pairs; the result (n_pairs >> passes pairs) is in *result (one of the two).  Stages run back to back on `s`.
-cudaError_t launch_downconvert(const uint8_t *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
-			       cudaStream_t s)
+// in_i16: iq holds int16 I,Q pairs instead of raw bytes (the data fsk_demod::process(int16_t*,int) / process_iq get)
+cudaError_t launch_downconvert(const void *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
+			       cudaStream_t s, bool in_i16)
 {
 	const void *cur = iq;
 	long long n = n_pairs;
@@ -160,7 +161,7 @@ cudaError_t launch_downconvert(const uint8_t *iq, long long n_pairs, int passes,
 	for (int p = 0; p < passes; p++) {
 		dst = bufs[p & 1];
 		const long long no = n / 2;
-		const bool last = (p == passes - 1), first = (p == 0);
+		const bool last = (p == passes - 1), first = (p == 0) && !in_i16;
 		cudaError_t e;
 		if (!last) e = first ? launch_stage<8, false, true>(cur, dst, n, no, s) : launch_stage<8, false, false>(cur, dst, n, no, s);
 		else if (wide) e = first ? launch_stage<20, true, true>(cur, dst, n, no, s) : launch_stage<20, true, false>(cur, dst, n, no, s);

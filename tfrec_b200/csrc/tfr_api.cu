@@ -30,8 +30,10 @@ cudaError_t launch_verify(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_walk(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_submit_epilogue(const BackParams &p, cudaStream_t s);
 cudaError_t launch_parse(const BackParams &p, cudaStream_t s);
-cudaError_t launch_downconvert(const uint8_t *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
-			       cudaStream_t s);
+cudaError_t launch_downconvert_fused(const uint8_t *iq, const uint8_t *hist, long long n_pairs, int passes, int wide, int16_t *out, cudaStream_t s);
+cudaError_t launch_dc_hist(const uint8_t *iq, long long n_pairs, const uint8_t *old_hist, uint8_t *new_hist, cudaStream_t s);
+cudaError_t launch_downconvert(const void *iq, long long n_pairs, int passes, int wide, int16_t *tmp0, int16_t *tmp1, int16_t **result,
+			       cudaStream_t s, bool in_i16);
 }  // namespace tfr
 
 using namespace tfr;
@@ -1107,9 +1109,20 @@ extern "C" __attribute__((visibility("default"))) long tfr_downconvert(int devic
 		if ((e = cudaEventCreate(&ev0)) != cudaSuccess || (e = cudaEventCreate(&ev1)) != cudaSuccess) { ret = cuda_fail("events", e); break; }
 		// reps > 1: timing runs (the sweep tool); the result is the same every time
 		const int n_rep = reps < 1 ? 1 : reps;
-		if ((e = launch_downconvert(src, n_pairs, passes, filter, tmp[0], tmp[1], &res, 0)) != cudaSuccess) { ret = cuda_fail("launch", e); break; }
+		// passes 1..5 run as ONE kernel (decim_fused.cu); TFR_DC=cascade selects the launch-per-stage cascade (decim.cu),
+		// which is also what passes 6..8 use
+		const char *dcsel = getenv("TFR_DC");
+		const bool fused = passes <= 5 && !(dcsel && !strcmp(dcsel, "cascade"));
+		auto run = [&]() -> cudaError_t {
+			if (fused) {
+				res = tmp[0];
+				return launch_downconvert_fused(src, nullptr, n_pairs, passes, filter, tmp[0], 0);
+			}
+			return launch_downconvert(src, n_pairs, passes, filter, tmp[0], tmp[1], &res, 0, false);
+		};
+		if ((e = run()) != cudaSuccess) { ret = cuda_fail("launch", e); break; }
 		cudaEventRecord(ev0, 0);
-		for (int r = 0; r < n_rep && e == cudaSuccess; r++) e = launch_downconvert(src, n_pairs, passes, filter, tmp[0], tmp[1], &res, 0);
+		for (int r = 0; r < n_rep && e == cudaSuccess; r++) e = run();
 		cudaEventRecord(ev1, 0);
 		if (e != cudaSuccess) { ret = cuda_fail("launch", e); break; }
 		if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) { ret = cuda_fail("kernels", e); break; }
@@ -1125,6 +1138,127 @@ extern "C" __attribute__((visibility("default"))) long tfr_downconvert(int devic
 	if (ev1) cudaEventDestroy(ev1);
 	cudaFree(d_in); cudaFree(tmp[0]); cudaFree(tmp[1]);
 	return ret;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// downconvert as a streaming object (dsp_stuff.h:46-56): history carried from call to call
+// ------------------------------------------------------------------------------------------------
+struct tfr_dc {
+	int device = 0, passes = 2;
+	uint8_t *d_hist[2] = { nullptr, nullptr };   // last 384 raw samples (768 B), double buffered
+	int hist_cur = -1;                            // -1: nothing fed yet (zero histories)
+	int16_t *d_hist16 = nullptr;                  // int16 entry: last 384 I,Q pairs
+	bool hist16_valid = false;
+	uint8_t *d_in = nullptr;
+	int16_t *d_tmp[2] = { nullptr, nullptr };
+	size_t cap_in = 0, cap_tmp = 0;
+};
+static constexpr int kDcHistPairs = 384;
+
+extern "C" __attribute__((visibility("default"))) int tfr_dc_create(int device, int passes, tfr_dc **out)
+{
+	if (!out) return fail(TFR_E_INVAL, "tfr_dc_create: null argument");
+	*out = nullptr;
+	if (passes < 1 || passes > 5) return fail(TFR_E_INVAL, "tfr_dc_create: passes must be 1..5");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return fail(TFR_E_NODEVICE, "tfr_dc_create: no such CUDA device (there is no CPU fallback)"); }
+	CU(cudaSetDevice(device));
+	tfr_dc *h = new tfr_dc();
+	h->device = device;
+	h->passes = passes;
+	cudaError_t e = cudaMalloc(&h->d_hist[0], 2 * kDcHistPairs);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_hist[1], 2 * kDcHistPairs);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_hist16, 4 * kDcHistPairs);
+	if (e != cudaSuccess) { cudaGetLastError(); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_hist16); delete h; return fail(TFR_E_NOMEM, "tfr_dc_create: history buffers"); }
+	*out = h;
+	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void tfr_dc_destroy(tfr_dc *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_hist16);
+	cudaFree(h->d_in); cudaFree(h->d_tmp[0]); cudaFree(h->d_tmp[1]);
+	delete h;
+}
+
+static int dc_reserve(tfr_dc *h, size_t in_bytes, size_t tmp_bytes)
+{
+	if (in_bytes > h->cap_in) {
+		cudaFree(h->d_in);
+		h->d_in = nullptr;
+		h->cap_in = 0;
+		if (cudaMalloc(&h->d_in, in_bytes) != cudaSuccess) { cudaGetLastError(); return fail(TFR_E_NOMEM, "tfr_dc: input buffer"); }
+		h->cap_in = in_bytes;
+	}
+	if (tmp_bytes > h->cap_tmp) {
+		cudaFree(h->d_tmp[0]); cudaFree(h->d_tmp[1]);
+		h->d_tmp[0] = h->d_tmp[1] = nullptr;
+		h->cap_tmp = 0;
+		if (cudaMalloc(&h->d_tmp[0], tmp_bytes) != cudaSuccess || cudaMalloc(&h->d_tmp[1], tmp_bytes) != cudaSuccess) { cudaGetLastError(); return fail(TFR_E_NOMEM, "tfr_dc: stage buffers"); }
+		h->cap_tmp = tmp_bytes;
+	}
+	return TFR_OK;
+}
+
+// raw u8 IQ in, int16 I,Q out ((nbytes/2) >> passes pairs); nbytes/2 must be a multiple of 2^passes so that every
+// stage's phase carries over to the next call (the reference drops an odd trailing sample of a block for good)
+extern "C" __attribute__((visibility("default"))) long tfr_dc_process(tfr_dc *h, const uint8_t *iq, size_t nbytes, int filter, int16_t *out, int mem)
+{
+	if (!h || !iq || !out) return fail(TFR_E_INVAL, "tfr_dc_process: null argument");
+	if (mem != TFR_MEM_HOST && mem != TFR_MEM_DEVICE) return fail(TFR_E_INVAL, "tfr_dc_process: mem must be TFR_MEM_HOST or TFR_MEM_DEVICE");
+	const long long n_pairs = (long long)(nbytes / 2);
+	if (nbytes == 0 || (nbytes & 1) || (n_pairs & ((1ll << h->passes) - 1))) return fail(TFR_E_INVAL, "tfr_dc_process: the number of IQ pairs must be a positive multiple of 2^passes");
+	if (mem == TFR_MEM_DEVICE && (((uintptr_t)iq & 3) || ((uintptr_t)out & 15))) return fail(TFR_E_INVAL, "tfr_dc_process: device pointers must be aligned (input 4, output 16 bytes)");
+	CU(cudaSetDevice(h->device));
+	const long long n_res = n_pairs >> h->passes;
+	const uint8_t *src = iq;
+	int16_t *dst = out;
+	if (mem == TFR_MEM_HOST) {
+		int rc = dc_reserve(h, nbytes, (size_t)n_res * 4);
+		if (rc) return rc;
+		CU(cudaMemcpy(h->d_in, iq, nbytes, cudaMemcpyHostToDevice));
+		src = h->d_in;
+		dst = h->d_tmp[0];
+	}
+	const uint8_t *hist = h->hist_cur >= 0 ? h->d_hist[h->hist_cur] : nullptr;
+	const int nxt = h->hist_cur >= 0 ? h->hist_cur ^ 1 : 0;
+	CU(launch_downconvert_fused(src, hist, n_pairs, h->passes, filter, dst, 0));
+	CU(launch_dc_hist(src, n_pairs, hist, h->d_hist[nxt], 0));
+	h->hist_cur = nxt;
+	if (mem == TFR_MEM_HOST) CU(cudaMemcpy(out, dst, (size_t)n_res * 4, cudaMemcpyDeviceToHost));
+	else CU(cudaStreamSynchronize(0));
+	return (long)(n_res * 2);
+}
+
+// downconvert::process_iq(int16_t *buf, int len, int filter) itself (dsp_stuff.cpp:243-264): int16 I,Q in place on the
+// host, len = number of int16 (2 per pair), returns the new len; the pair count must be a multiple of 2^passes.
+// The int16 path runs the stage cascade (decim.cu) over [the last 384 pairs of the previous call | this call's pairs]
+// and returns the outputs that belong to this call (the 384 pairs in front absorb the cascade's zero start).
+extern "C" __attribute__((visibility("default"))) long tfr_dc_process_i16(tfr_dc *h, int16_t *data_iq, int len, int filter)
+{
+	if (!h || !data_iq || len <= 0) return fail(TFR_E_INVAL, "tfr_dc_process_i16: bad argument");
+	const long long n_pairs = len / 2;
+	if ((len & 1) || (n_pairs & ((1ll << h->passes) - 1))) return fail(TFR_E_INVAL, "tfr_dc_process_i16: the number of IQ pairs must be a positive multiple of 2^passes");
+	CU(cudaSetDevice(h->device));
+	const long long tot = n_pairs + kDcHistPairs;
+	int rc = dc_reserve(h, (size_t)tot * 4, (size_t)(tot / 2 + 8) * 4);
+	if (rc) return rc;
+	int16_t *d_all = reinterpret_cast<int16_t *>(h->d_in);
+	if (h->hist16_valid) CU(cudaMemcpy(d_all, h->d_hist16, 4 * kDcHistPairs, cudaMemcpyDeviceToDevice));
+	else CU(cudaMemset(d_all, 0, 4 * kDcHistPairs));
+	CU(cudaMemcpy(d_all + 2 * kDcHistPairs, data_iq, (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
+	int16_t *res = nullptr;
+	CU(launch_downconvert(d_all, tot, h->passes, filter, h->d_tmp[0], h->d_tmp[1], &res, 0, true));
+	// the history for the next call: the last 384 pairs fed so far
+	CU(cudaMemcpy(h->d_hist16, d_all + 2 * (tot - kDcHistPairs), 4 * kDcHistPairs, cudaMemcpyDeviceToDevice));
+	h->hist16_valid = true;
+	const long long n_res = n_pairs >> h->passes;
+	CU(cudaMemcpy(data_iq, res + 2 * (kDcHistPairs >> h->passes), (size_t)n_res * 4, cudaMemcpyDeviceToHost));
+	return (long)(n_res * 2);
 }
 
 extern "C" __attribute__((visibility("default"))) int tfr_parse_bytes(tfr_handle *h, int type, const uint8_t *bytes, int len, tfr_frame *frame,
