@@ -135,6 +135,10 @@ void tfr_destroy(tfr_handle *h);
  * be 16-byte aligned and stay valid until tfr_sync/tfr_poll_* returns.  One submit per stream
  * between two tfr_process calls. */
 int tfr_submit(tfr_handle *h, int stream, const uint8_t *iq, size_t nbytes, int mem);
+/* The same for a caller that keeps its own decimator: int16 I,Q already at 384 kS/s, i.e. exactly what the reference
+ * hands to fsk_demod::process(int16_t *data_iq, int len) (fm_demod.cpp:34; engine.cpp:86).  n_int16 must be a positive
+ * multiple of 16384 (one reference block).  Raw and decimated submits cannot be mixed in one tfr_process call. */
+int tfr_submit_decimated(tfr_handle *h, int stream, const int16_t *iq16, size_t n_int16, int mem);
 
 /* replaces dc.process_iq + fsk->process (engine.cpp:85-86) for everything submitted: enqueues the
  * kernels on the handle's CUDA stream and returns without waiting */

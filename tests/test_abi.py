@@ -75,6 +75,28 @@ def test_downconvert_validates_arguments_without_a_device(lib):
         assert call(2) == -2 and b"no CPU fallback" in lib.tfr_last_error()   # TFR_E_NODEVICE
 
 
+def test_streaming_downconvert_object_without_a_device(lib, tmp_path):
+    """tfr_dc_create validates passes and fails loudly without a device; the host mirror host/dsp_stuff.h (the
+    reference's `downconvert` class, dsp_stuff.h:46-56) compiles against the ABI and throws instead of falling back"""
+    import subprocess
+    import torch
+    h = C.c_void_p()
+    assert lib.tfr_dc_create(0, 0, C.byref(h)) == -1 and lib.tfr_dc_create(0, 6, C.byref(h)) == -1      # TFR_E_INVAL
+    assert lib.tfr_dc_create(0, 2, None) == -1
+    src = tmp_path / "dc.cpp"
+    src.write_text('#include "tfrec_b200/host/dsp_stuff.h"\n'
+                   'int main() { try { downconvert dc(2); int16_t b[64] = {0}; return dc.process_iq(b, 64, 0) == 16 ? 0 : 1; }\n'
+                   '             catch (const std::runtime_error &) { return 2; } }\n')
+    exe = tmp_path / "dc"
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", ROOT, "-o", str(exe), str(src), "-L" + os.path.join(ROOT, "tfrec_b200"),
+                    "-ltfrb200", "-Wl,-rpath," + os.path.join(ROOT, "tfrec_b200")], check=True)
+    rc = subprocess.run([str(exe)]).returncode
+    if torch.cuda.is_available():
+        assert rc == 0
+    else:
+        assert rc == 2 and lib.tfr_dc_create(0, 2, C.byref(h)) == -2                                     # TFR_E_NODEVICE
+
+
 def test_product_does_not_touch_the_oracle():
     # the product path must never import, link or execute anything under oracle/
     for dirpath, _, files in os.walk(os.path.join(ROOT, "tfrec_b200")):

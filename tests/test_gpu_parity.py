@@ -108,6 +108,28 @@ def test_downconvert_streaming_object(tb, passes):
         assert np.array_equal(got, want), "int16 streaming, passes %d filter %d" % (passes, filt)
 
 
+@pytest.mark.parametrize("name,types", [("mixed5", 0x2F), ("strong_t7", 0x07)])
+def test_decimated_int16_entry(tb, hot_fixture, name, types):
+    """tfr_submit_decimated: the samples fsk_demod::process(int16_t *data_iq, int len) gets (fm_demod.cpp:34) - a caller
+    that keeps its own decimator.  Fed with the reference decimator's output, in two calls, the decode is the oracle's"""
+    iq = hot_fixture(name)
+    nb = iq.size // 65536
+    dec = ol.decimate(iq[:nb * 65536], 0)                 # int16 I,Q at 384 kS/s, 16384 int16 per block
+    rx = tb.Receiver(types=types, thresh=0)
+    cut = (nb // 3) * 16384
+    for part in (dec[:cut], dec[cut:]):
+        rx.submit_decimated(0, np.ascontiguousarray(part))
+        rx.process()
+    o = ol.Oracle(types=types, thresh=0)
+    o.process(iq[:nb * 65536])
+    assert [frame_key(f) for f in rx.frames()] == [frame_key(f) for f in o.frames()]
+    assert [r["exec"] for r in rx.records()] == [r["exec"] for r in o.records()]
+    tr = rx.block_trace(0)                                # of the last call
+    assert np.array_equal(tr, o.blocks()[-len(tr):])
+    assert rx.thresh(0) == o.thresh()
+    rx.close()
+
+
 def test_downconvert_cascade_variant(tb, monkeypatch):
     """TFR_DC=cascade: one launch per stage (decim.cu, what passes 6..8 always use) instead of the fused kernel"""
     monkeypatch.setenv("TFR_DC", "cascade")

@@ -21,7 +21,7 @@ BLOCK_BYTES = 65536
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_TAPS, FLAG_KEEP_DECIM = 1, 2
 
-ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_process", "tfr_sync", "tfr_poll_frames",
+ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_submit_decimated", "tfr_process", "tfr_sync", "tfr_poll_frames",
                "tfr_poll_records", "tfr_clear_results", "tfr_get_thresh", "tfr_read_block_trace", "tfr_read_taps",
                "tfr_read_decimated", "tfr_decimate", "tfr_downconvert", "tfr_dc_create", "tfr_dc_destroy", "tfr_dc_process",
                "tfr_dc_process_i16", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error", "tfr_abi_version"]
@@ -101,6 +101,7 @@ def load():
     L.tfr_downconvert.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.POINTER(C.c_float)]
     L.tfr_downconvert.restype = C.c_long
+    L.tfr_submit_decimated.argtypes = [P, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
     L.tfr_dc_create.argtypes = [C.c_int, C.c_int, C.POINTER(P)]
     L.tfr_dc_destroy.argtypes = [P]
     L.tfr_dc_destroy.restype = None
@@ -168,6 +169,12 @@ class Receiver:
             _check(self.L.tfr_submit(self.h, stream, iq.ctypes.data, iq.size if nbytes is None else nbytes, MEM_HOST))
         else:
             _check(self.L.tfr_submit(self.h, stream, C.c_void_p(int(iq)), nbytes, MEM_DEVICE))
+
+    def submit_decimated(self, stream, iq16):
+        """int16 I,Q already at 384 kS/s (what fsk_demod::process(int16_t*, int) takes); numpy int16, a multiple of 16384"""
+        assert isinstance(iq16, np.ndarray) and iq16.dtype == np.int16 and iq16.flags["C_CONTIGUOUS"]
+        self._keep = getattr(self, "_keep", []) + [iq16]
+        _check(self.L.tfr_submit_decimated(self.h, stream, iq16.ctypes.data, iq16.size, MEM_HOST))
 
     def submit_host_ptr(self, stream, ptr, nbytes):
         _check(self.L.tfr_submit(self.h, stream, C.c_void_p(int(ptr)), nbytes, MEM_HOST))

@@ -209,9 +209,43 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	}, es, trig64);
 }
 
+// The same block bookkeeping for input that is ALREADY decimated: int16 I,Q at 384 kS/s, what the reference hands to
+// fsk_demod::process(int16_t *data_iq, int len) (fm_demod.cpp:34-74, len = 16384 per block).  No filter: a thread
+// copies its 64 samples into the row layout above, tests them against the trigger bound and joins the epilogue.
+__global__ void __launch_bounds__(kThreads, 3) frontend_i16_kernel(const FrontParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ EpiShared es;
+	const int tid = threadIdx.x;
+	const int stream = blockIdx.y;
+	const StreamJob job = p.jobs[stream];
+	StreamState *st = p.st + stream;
+	const int tile = (p.use_progress ? (int)st->t2_done : p.tile0) + blockIdx.x;
+	if (tile >= (int)job.n_blocks) return;
+	int thresh_lo = st->thresh;
+	if (st->thresh_mode) thresh_lo = p.margin ? thresh_lo - p.margin : st->spec_lo;
+	const uint4 *src = reinterpret_cast<const uint4 *>(job.iq + (size_t)tile * (kBlockDec * 4)) + tid * 16;
+	uint4 *row = reinterpret_cast<uint4 *>(smem + kRow0 + tid * kRowStride);
+	unsigned long long trig64 = 0ull;
+#pragma unroll 4
+	for (int q = 0; q < 16; q++) {
+		const uint4 v = src[q];
+		row[q] = v;
+		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int yi = (int)(int16_t)(w[j] & 0xffff), yq = (int)(int16_t)(w[j] >> 16);
+			if (abs(yi) + abs(yq) > thresh_lo) trig64 |= 1ull << (4 * q + j);
+		}
+	}
+	block_epilogue(p, job, tile, [&](int m) -> uint32_t {
+		return *reinterpret_cast<const uint32_t *>(smem + kRow0 + (m >> 6) * kRowStride + (m & 63) * 4);
+	}, es, trig64);
+}
+
 // after the last front-end launch and threshold walk of a call: remember the FIR history for the next call
 // (other parity) and rewind the walk cursor
-__global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int n_streams)
+__global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int n_streams, int decimated)
 {
 	const int stream = blockIdx.x;
 	if (stream >= n_streams) return;
@@ -220,7 +254,8 @@ __global__ void save_history_kernel(const StreamJob *jobs, StreamState *st, int 
 	StreamState *s = st + stream;
 	const int par = (s->hist_parity & 1) ^ 1;
 	const uint8_t *src = job.iq + (size_t)job.n_blocks * kBlockBytes - kHistBytes;
-	if (threadIdx.x < kHistBytes) s->hist[par][threadIdx.x] = src[threadIdx.x];
+	// (a call that was fed decimated samples has no raw tail: the filter history restarts from zero signal)
+	if (threadIdx.x < kHistBytes) s->hist[par][threadIdx.x] = decimated ? (uint8_t)128 : src[threadIdx.x];
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		s->hist_parity = par;
@@ -255,9 +290,25 @@ cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaS
 	return cudaGetLastError();
 }
 
-cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream)
+cudaError_t launch_frontend_i16(const FrontParams &p, int n_streams, cudaStream_t stream)
 {
-	save_history_kernel<<<n_streams, 128, 0, stream>>>(jobs, st, n_streams);
+	static bool attr_done[64] = { false };
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 64 && !attr_done[dev]) {
+		e = cudaFuncSetAttribute(frontend_i16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (e != cudaSuccess) return e;
+		attr_done[dev] = true;
+	}
+	if (p.n_tiles <= 0 || n_streams <= 0) return cudaSuccess;
+	frontend_i16_kernel<<<dim3(p.n_tiles, n_streams), kThreads, kSmemBytes, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, int decimated, cudaStream_t stream)
+{
+	save_history_kernel<<<n_streams, 128, 0, stream>>>(jobs, st, n_streams, decimated);
 	return cudaGetLastError();
 }
 

@@ -19,7 +19,8 @@ cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaS
 cudaError_t launch_frontend_tc(const FrontParams &p, int n_streams, int wide, cudaStream_t stream);
 bool frontend_tc_available();
 int frontend_tc_encode(const void *iq, uint32_t n_blocks, void *out);
-cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, cudaStream_t stream);
+cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, int decimated, cudaStream_t stream);
+cudaError_t launch_frontend_i16(const FrontParams &p, int n_streams, cudaStream_t stream);
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s);
@@ -76,6 +77,7 @@ struct PendingSubmit {
 	const uint8_t *dev_ptr = nullptr;
 	size_t nbytes = 0;
 	bool pending = false;
+	bool decimated = false;   // int16 I,Q at 384 kS/s (tfr_submit_decimated) instead of raw bytes
 };
 
 struct tfr_handle {
@@ -437,12 +439,15 @@ static int ensure_blocks(tfr_handle *h, tfr_handle::Slot &sl, size_t blocks, siz
 	return TFR_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int tfr_submit(tfr_handle *h, int stream, const uint8_t *iq, size_t nbytes, int mem)
+static int submit_common(tfr_handle *h, int stream, const uint8_t *iq, size_t nbytes, int mem, bool decimated)
 {
 	if (!h || !iq) return fail(TFR_E_INVAL, "tfr_submit: null argument");
 	if (stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_submit: stream out of range");
-	if (nbytes == 0 || nbytes % TFR_BLOCK_BYTES) return fail(TFR_E_INVAL, "tfr_submit: nbytes must be a positive multiple of 65536");
-	if (nbytes / TFR_BLOCK_BYTES > 262143ull) return fail(TFR_E_INVAL, "tfr_submit: at most 262143 blocks (16 GiB) per stream per call");
+	const size_t blk = decimated ? (size_t)kBlockDec * 4 : (size_t)TFR_BLOCK_BYTES;
+	if (nbytes == 0 || nbytes % blk) return fail(TFR_E_INVAL, decimated ? "tfr_submit_decimated: the int16 count must be a positive multiple of 16384" : "tfr_submit: nbytes must be a positive multiple of 65536");
+	if (nbytes / blk > 262143ull) return fail(TFR_E_INVAL, "tfr_submit: at most 262143 blocks (16 GiB) per stream per call");
+	for (auto &q : h->pend)
+		if (q.pending && q.decimated != decimated) return fail(TFR_E_INVAL, "tfr_submit: raw and decimated submits cannot be mixed in one call");
 	PendingSubmit &ps = h->pend[stream];
 	if (ps.pending) return fail(TFR_E_BUSY, "tfr_submit: stream already has a pending submit");
 	CU(cudaSetDevice(h->device));
@@ -493,7 +498,19 @@ extern "C" __attribute__((visibility("default"))) int tfr_submit(tfr_handle *h, 
 	}
 	ps.nbytes = nbytes;
 	ps.pending = true;
+	ps.decimated = decimated;
 	return TFR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int tfr_submit(tfr_handle *h, int stream, const uint8_t *iq, size_t nbytes, int mem)
+{
+	return submit_common(h, stream, iq, nbytes, mem, false);
+}
+
+// what fsk_demod::process(int16_t *data_iq, int len) takes (fm_demod.cpp:34): int16 I,Q already at 384 kS/s
+extern "C" __attribute__((visibility("default"))) int tfr_submit_decimated(tfr_handle *h, int stream, const int16_t *iq16, size_t n_int16, int mem)
+{
+	return submit_common(h, stream, reinterpret_cast<const uint8_t *>(iq16), n_int16 * sizeof(int16_t), mem, true);
 }
 
 static int ensure_events(tfr_handle *h, size_t n)
@@ -516,12 +533,14 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	size_t total = 0, total_wins = 0;
 	const int ndm = std::max(h->dcfg.n_demods, 1);
 	uint32_t max_blocks = 0;
+	bool decimated = false;   // the call's submits hold int16 I,Q at 384 kS/s (all of them: tfr_submit refuses a mix)
 	for (int s = 0; s < ns; s++) {
 		PendingSubmit &ps = h->pend[s];
 		if (!ps.pending) continue;
 		StreamJob &j = jobs[s];
 		j.iq = ps.dev_ptr;
-		j.n_blocks = (uint32_t)(ps.nbytes / TFR_BLOCK_BYTES);
+		decimated = ps.decimated;
+		j.n_blocks = (uint32_t)(ps.nbytes / (ps.decimated ? (size_t)kBlockDec * 4 : (size_t)TFR_BLOCK_BYTES));
 		j.dec_off = (uint32_t)total;
 		j.win_cap = j.n_blocks * (uint32_t)kWinPerBlock + 4u;
 		j.win_off = (uint32_t)total_wins;
@@ -550,7 +569,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	}
 	// h->jobs stays untouched until the copy has run: the next tfr_process first waits for this slot's events
 	CU(cudaMemcpyAsync(sl.d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, sf));
-	if (h->use_tc) {
+	if (h->use_tc && !decimated) {
 		// the call's tensor maps (TMA descriptors of every stream's submit), encoded on the host, 64-byte aligned
 		uint8_t *tm = reinterpret_cast<uint8_t *>(((uintptr_t)sl.h_tmaps.data() + 63) & ~(uintptr_t)63);
 		for (int s = 0; s < ns; s++)
@@ -578,6 +597,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	fp.use_progress = 0;
 	fp.tmaps = sl.d_tmaps;
 	auto launch_fe = [&](const FrontParams &q, cudaStream_t st) {
+		if (decimated) return launch_frontend_i16(q, ns, st);
 		return h->use_tc ? launch_frontend_tc(q, ns, h->dcfg.filter, st) : launch_frontend(q, ns, h->dcfg.filter, st);
 	};
 	BackParams bp;
@@ -759,7 +779,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			part_tile0 = 0;   // the redone blocks hold more samples than the parts before saw: the last part's fm_dev pass covers everything
 		}
 	}
-	CU(launch_save_history(sl.d_jobs, h->d_state, ns, sf));
+	CU(launch_save_history(sl.d_jobs, h->d_state, ns, decimated ? 1 : 0, sf));
 	h->stats.kernel_launches += 1;
 	CU(cudaEventRecord(sl.front_done, sf));
 

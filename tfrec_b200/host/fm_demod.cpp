@@ -48,10 +48,17 @@ tfr_handle *fsk_demod::handle(int filter_type)
 	return h;
 }
 
-void fsk_demod::process(int16_t *, int)
+// fm_demod.cpp:34-74 with the reference's own arguments: int16 I,Q at 384 kS/s, len = number of int16 (16384 per
+// reference block).  For callers that keep their own decimator (dsp_stuff.h `downconvert`); the fused path from the
+// raw bytes is process_raw().
+void fsk_demod::process(int16_t *data_iq, int len)
 {
-	fprintf(stderr, "fsk_demod::process(int16 IQ): decimation and demodulation are one device path that starts from the raw\n"
-			"u8 samples; call process_raw() (see INTEGRATION.md)\n");
+	tfr_handle *hh = handle(h_filter < 0 ? 0 : h_filter);
+	if (tfr_submit_decimated(hh, 0, data_iq, (size_t)len, TFR_MEM_HOST) || tfr_process(hh)) {
+		fprintf(stderr, "tfr: %s\n", tfr_last_error());
+		return;
+	}
+	deliver(hh);
 }
 
 int fsk_demod::threshold(void)
@@ -68,6 +75,12 @@ int fsk_demod::process_raw(const uint8_t *iq, size_t nbytes, int filter_type)
 		fprintf(stderr, "tfr: %s\n", tfr_last_error());
 		return -1;
 	}
+	return deliver(hh);
+}
+
+// the call's frames and records, in the reference's output order, to the registered decoders
+int fsk_demod::deliver(tfr_handle *hh)
+{
 	long nf = tfr_poll_frames(hh, NULL, 0), nr = tfr_poll_records(hh, NULL, 0);
 	if (nf < 0 || nr < 0) {
 		fprintf(stderr, "tfr: %s\n", tfr_last_error());

@@ -12,8 +12,8 @@ class fsk_demod {
       public:
 	fsk_demod(vector<demodulator *> *_demods, int _thresh, int _dbg);
 	~fsk_demod();
-	// reference signature (decimated int16 IQ): not available - decimation and demodulation are one fused
-	// device path that starts from the raw bytes.  Always returns after printing an error.
+	// reference signature (fm_demod.h:21): int16 I,Q already decimated to 384 kS/s, len = number of int16, a multiple
+	// of 16384 (one reference block) - for callers that keep their own decimator
 	void process(int16_t *data_iq, int len);
 	// the replacement for `dc.process_iq(data,len,filter); fsk->process(data,ld);` (engine.cpp:85-86):
 	// nbytes of raw rtl-sdr u8 IQ, a multiple of 65536; results are delivered to the decoders' store_data()
@@ -21,6 +21,7 @@ class fsk_demod {
 	int types_mask(void) const { return types; }
 	int threshold(void);
 	tfr_handle *handle(int filter_type);
+	int deliver(tfr_handle *hh);
 
       private:
 	vector<demodulator *> *demods;
