@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TFR_ABI_VERSION 1
+#define TFR_ABI_VERSION 2
 #define TFR_BLOCK_BYTES 65536   /* replay block of engine.cpp:68 (RLS); all framing is in these units */
 #define TFR_SAMPLE_RATE 1536000 /* engine.cpp:15 */
 #define TFR_MAX_RDATA 64
@@ -119,6 +119,11 @@ typedef struct {
 	double last_backend_ms;     /* ... of the demod/framer/parser kernels */
 	double last_h2d_ms;
 	double last_total_ms;       /* first H2D copy (or first kernel) to last kernel of the last tfr_process */
+	/* screening front-end (since create; zero when it is off: TFR_FE=dense, TFR_FLAG_KEEP_DECIM, decimated submits) */
+	uint64_t screen_blocks;     /* blocks whose samples the tensor-core screen proved to be no triggers, up to the candidates */
+	uint64_t dense_blocks;      /* blocks the screen handed to the dense exact kernel (bursts) */
+	uint64_t screen_candidates; /* samples of the screened blocks whose exact value had to be computed */
+	uint64_t screen_triggers;   /* ... of which really exceeded the trigger bound */
 } tfr_stats;
 
 typedef struct tfr_handle tfr_handle;
@@ -163,6 +168,11 @@ long tfr_read_block_trace(tfr_handle *h, int stream, tfr_block_trace *out, size_
  * (dsp_stuff.cpp:47-55, double); `demod` is the registration index (main.cpp:173-218 order).
  * Returns the number of elements copied (or available if out==NULL). */
 long tfr_read_taps(tfr_handle *h, int stream, int demod, int kind, void *out, size_t cap_elems);
+
+/* debug (needs TFR_FLAG_TAPS, screening front-end): the screen values of the last tfr_process for a stream, two int32
+ * (I, Q) per 384 kS/s sample: the linear 46-tap filter output times 2^shift minus the centre of the floor losses.  The
+ * true sample obeys |I|+|Q| <= (|vI|+|vQ|) / 2^shift + slack.  Blocks that went to the dense kernel hold zeros. */
+long tfr_read_screen(tfr_handle *h, int stream, int32_t *out, size_t cap_int32, int *shift, int *slack);
 
 /* debug (needs TFR_FLAG_KEEP_DECIM): decimated int16 I,Q of the last tfr_process for a stream,
  * i.e. the buffer process_iq leaves behind in place (dsp_stuff.cpp:197,225) */

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.tfr_abi_version() == 1
+    assert lib.tfr_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -167,6 +167,53 @@ def test_tensor_core_front_end_variant_bit_exact(tb, golden, hot_fixture, monkey
     rx.close()
 
 
+def test_screen_values_are_the_linear_filter(tb, hot_fixture):
+    """Screening front-end (frontend_screen.cu): the tensor-core GEMM of the raw bytes with the 16-bit combined filter is
+    an exact integer computation - every screen value equals the numpy restatement, across submits (carried history) and
+    for both filters; the bound itself is checked against the oracle in tests/test_screen_bound.py"""
+    import screen_ref as sr
+    rng = np.random.default_rng(11)
+    cases = {"mixed5": hot_fixture("mixed5")[:24 * 65536],
+             "uniform": rng.integers(0, 256, size=6 * 65536, dtype=np.uint8),
+             "extremes": np.tile(np.array([0, 255, 255, 0, 0, 0, 255, 255], dtype=np.uint8), 65536 // 8 * 3)}
+    for name, iq in cases.items():
+        for filt in (0, 1):
+            rx = tb.Receiver(types=0x07, thresh=0, filter=filt, flags=tb.FLAG_TAPS)
+            cut = (iq.size // 65536 // 2) * 65536
+            want, c = sr.screen_values(iq, filt)
+            got = []
+            for part in (iq[:cut], iq[cut:]):
+                rx.submit(0, part.copy())
+                rx.process()
+                v, shift, slack = rx.screen(0)
+                assert (shift, slack) == (c["shift"], c["slack"])
+                got.append(v)
+            got = np.concatenate(got)
+            assert got.shape == want.shape
+            bad = np.nonzero((got != want).any(axis=1))[0]
+            assert bad.size == 0, "%s filter %d: %d screen values differ, first at sample %d: got %s want %s" % (
+                name, filt, bad.size, bad[0], got[bad[0]], want[bad[0]])
+            st = rx.stats()
+            assert st["screen_blocks"] + st["dense_blocks"] == iq.size // 65536
+            rx.close()
+
+
+def test_dense_front_end_variant(tb, hot_fixture, monkeypatch):
+    """TFR_FE=dense: every block through the dense exact kernel of frontend.cu (what the screen hands bursts to)"""
+    monkeypatch.setenv("TFR_FE", "dense")
+    iq = hot_fixture("mixed5")
+    rx = tb.Receiver(types=0x2F, thresh=0)
+    for off in range(0, iq.size, 7 * 65536):
+        rx.submit(0, iq[off:off + 7 * 65536].copy())
+        rx.process()
+    o = ol.Oracle(types=0x2F)
+    o.process(iq)
+    assert [r["exec"] for r in rx.records()] == [r["exec"] for r in o.records()]
+    assert rx.thresh(0) == o.thresh()
+    assert rx.stats()["screen_blocks"] == 0
+    rx.close()
+
+
 def test_decimator_ragged_length(tb):
     rng = np.random.default_rng(8)
     iq = rng.integers(0, 256, size=65536 + 4096 + 12, dtype=np.uint8)

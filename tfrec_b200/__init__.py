@@ -23,7 +23,7 @@ FLAG_TAPS, FLAG_KEEP_DECIM = 1, 2
 
 ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_submit_decimated", "tfr_process", "tfr_sync", "tfr_poll_frames",
                "tfr_poll_records", "tfr_clear_results", "tfr_get_thresh", "tfr_read_block_trace", "tfr_read_taps",
-               "tfr_read_decimated", "tfr_decimate", "tfr_downconvert", "tfr_dc_create", "tfr_dc_destroy", "tfr_dc_process",
+               "tfr_read_decimated", "tfr_read_screen", "tfr_decimate", "tfr_downconvert", "tfr_dc_create", "tfr_dc_destroy", "tfr_dc_process",
                "tfr_dc_process_i16", "tfr_parse_bytes", "tfr_get_stats", "tfr_last_error", "tfr_abi_version"]
 
 
@@ -56,7 +56,8 @@ class Stats(C.Structure):
                 ("windows", C.c_uint64), ("reruns", C.c_uint64), ("reruns_sr", C.c_uint32), ("reruns_biquad", C.c_uint32),
                 ("reruns_edge", C.c_uint32), ("fallback_epochs", C.c_uint32),
                 ("last_frontend_ms", C.c_double), ("last_backend_ms", C.c_double), ("last_h2d_ms", C.c_double),
-                ("last_total_ms", C.c_double)]
+                ("last_total_ms", C.c_double), ("screen_blocks", C.c_uint64), ("dense_blocks", C.c_uint64),
+                ("screen_candidates", C.c_uint64), ("screen_triggers", C.c_uint64)]
 
 
 class TfrError(RuntimeError):
@@ -96,6 +97,8 @@ def load():
     L.tfr_read_taps.restype = C.c_long
     L.tfr_read_decimated.argtypes = [P, C.c_int, C.c_void_p, C.c_size_t]
     L.tfr_read_decimated.restype = C.c_long
+    L.tfr_read_screen.argtypes = [P, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tfr_read_screen.restype = C.c_long
     L.tfr_decimate.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
     L.tfr_decimate.restype = C.c_long
     L.tfr_downconvert.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -231,6 +234,15 @@ class Receiver:
         if n:
             _check(self.L.tfr_read_taps(self.h, stream, demod, kind, out.ctypes.data, n))
         return out
+
+    def screen(self, stream=0):
+        """debug (FLAG_TAPS): (values [n, 2] int32, shift, slack) of the screening front-end for the last process()"""
+        sh, sl = C.c_int(0), C.c_int(0)
+        n = _check(self.L.tfr_read_screen(self.h, stream, None, 0, C.byref(sh), C.byref(sl)))
+        out = np.empty(n, dtype=np.int32)
+        if n:
+            _check(self.L.tfr_read_screen(self.h, stream, out.ctypes.data, n, C.byref(sh), C.byref(sl)))
+        return out.reshape(-1, 2), sh.value, sl.value
 
     def decimated(self, stream=0):
         n = _check(self.L.tfr_read_decimated(self.h, stream, None, 0))

@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtfrb200.so")
-SOURCES = ["frontend.cu", "frontend_tc.cu", "backend.cu", "backend2.cu", "decim.cu", "decim_fused.cu", "tfr_api.cu"]
-HEADERS = ["tfr_dev.h", "demod_dev.cuh", "fir_taps.h", "frontend_common.cuh", os.path.join(ROOT, "include", "tfr.h")]
+SOURCES = ["frontend.cu", "frontend_tc.cu", "frontend_screen.cu", "backend.cu", "backend2.cu", "decim.cu", "decim_fused.cu", "tfr_api.cu"]
+HEADERS = ["tfr_dev.h", "demod_dev.cuh", "fir_taps.h", "frontend_common.cuh", "fir_exact.cuh", os.path.join(ROOT, "include", "tfr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared", "-cudart", "static"]
 

@@ -24,47 +24,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "frontend_common.cuh"
+#include "fir_exact.cuh"
 
 
 namespace tfr {
-
-// ------------------------------------------------------------------------------------------------
-// exact-floor accumulator bookkeeping
-// ------------------------------------------------------------------------------------------------
-// byte b -> float z = 33664 + b, built by integer ops in the [32768,65536) binade (ulp 1/256): bits =
-// 0x47038000 + (b << 8).  z = 33*1024 + (b-128), so with c1 = t2/1024 every stage-1 FMA adds
-// floor((b-128)*t2/1024) + 33*t2 : the wanted floor((x*t2)>>16 for x=(b-128)<<6) plus an integer.
-constexpr uint32_t kCvtBase = 0x47038000u;
-constexpr int kCvtMul = 33;
-// stage-1 accumulator: starts at kA1, ends at kM1 + y1 with kM1 a multiple of 65536 so that the
-// offset it injects into stage 2, kM1*t1/65536 = 163*t1, is again an integer.
-constexpr int kM1Mul = 163;
-constexpr int kM1 = kM1Mul * 65536;                       // 10,682,368
-constexpr int kA1 = kM1 - kCvtMul * t2_sum();             //  8,433,616  (>= 2^23 + 8520)
-static_assert(kA1 - 8520 >= (1 << 23) && kM1 + 8520 < (1 << 24), "stage-1 accumulator leaves the integer binade");
-// stage 2 runs as two 10-tap chains (taps 0..9 and 10..19) so that each chain's offset fits the binade
-constexpr int kA2a = (1 << 23) + 1300000;
-constexpr int kA2b = (1 << 23) + 100000;
-
-__host__ __device__ constexpr bool chain_in_range(bool wide, int lo, int hi, int start)
-{
-	int s = start;
-	for (int n = lo; n < hi; n++) {
-		s += kM1Mul * t1_tap(wide, n);
-		if (s - 13000 < (1 << 23) || s + 13000 >= (1 << 24)) return false;
-	}
-	return true;
-}
-static_assert(chain_in_range(false, 0, 10, kA2a) && chain_in_range(false, 10, 20, kA2b), "narrow stage-2 chain range");
-static_assert(chain_in_range(true, 0, 10, kA2a) && chain_in_range(true, 10, 20, kA2b), "wide stage-2 chain range");
-
-// y2 = (bitsA - 0x4B000000 + 2^23 - kA2a - offA) + (same for B) with off = 163*sum(taps of the chain)
-__host__ __device__ constexpr uint32_t y2_bias(bool wide)
-{
-	return 2u * (0x4B000000u - (1u << 23)) + (uint32_t)kA2a + (uint32_t)kA2b +
-	       (uint32_t)(kM1Mul * t1_sum(wide, 0, 10)) + (uint32_t)(kM1Mul * t1_sum(wide, 10, 20));
-}
 
 // ------------------------------------------------------------------------------------------------
 // shared memory layout
@@ -75,52 +38,15 @@ constexpr int kRow0 = 128;                   // byte offset of row 0; the 96 hal
 constexpr int kHaloOff = 16;
 constexpr int kSmemBytes = kRow0 + kThreads * kRowStride;  // 67,712 B -> 3 CTAs / SM
 
-// two bytes (I,Q) of a raw sample -> packed floats 33664+b
-__device__ __forceinline__ f2 cvt_iq(uint32_t w, int half)
-{
-	uint32_t bi = __byte_perm(w, 0, half ? 0x4424 : 0x4404) + kCvtBase;
-	uint32_t bq = __byte_perm(w, 0, half ? 0x4434 : 0x4414) + kCvtBase;
-	return pack2(__uint_as_float(bi), __uint_as_float(bq));
-}
-
+// one block of one stream: everything between the TMA loads and the descriptor.  `phase` is the parity of the mbarrier
+// at smem[0] for this use (a CTA that takes several blocks in turn flips it)
 template <bool WIDE>
-__device__ __forceinline__ f2 c2pair(int n)
+__device__ __forceinline__ void fe_block(const FrontParams &p, const StreamJob &job, StreamState *st, int tile, uint8_t *smem, EpiShared &es,
+					 uint32_t phase)
 {
-	float c = (float)t1_tap(WIDE, n) * (1.0f / 65536.0f);
-	return pack2(c, c);
-}
-__device__ __forceinline__ f2 c1pair(int n)
-{
-	float c = (float)t2_tap(n) * (1.0f / 1024.0f);
-	return pack2(c, c);
-}
-
-// stage 1: one 8-tap output from 8 consecutive converted raw samples
-__device__ __forceinline__ f2 stage1(const f2 *x)
-{
-	f2 acc = pack2((float)kA1, (float)kA1);
-#pragma unroll
-	for (int n = 0; n < 8; n++) acc = fma2_rm(x[n], c1pair(n), acc);
-	return acc;
-}
-
-template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams p)
-{
-	extern __shared__ __align__(128) uint8_t smem[];
-	__shared__ EpiShared es;
-
 	const int tid = threadIdx.x;
-	const int stream = blockIdx.y;
-	const StreamJob job = p.jobs[stream];
-	StreamState *st = p.st + stream;
-	const int tile = (p.use_progress ? (int)st->t2_done : p.tile0) + blockIdx.x;   // block index inside the submit
-	if (tile >= (int)job.n_blocks) return;
-
 	const uint32_t bar = smem_u32(smem);
 	const uint8_t *src = job.iq + (size_t)tile * kBlockBytes;
-	if (tid == 0) mbar_init(bar, 1);
-	__syncthreads();
 	if (tid == 0) {
 		mbar_expect_tx(bar, kBlockBytes + kHistBytes);
 		const uint8_t *hsrc = (tile == 0) ? st->hist[st->hist_parity & 1] : src - kHistBytes;
@@ -131,7 +57,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	int thresh_lo = st->thresh;
 	if (st->thresh_mode) thresh_lo = p.margin ? thresh_lo - p.margin : st->spec_lo;
 
-	mbar_wait(bar, 0);
+	mbar_wait(bar, phase);
 
 	// ------------------------------------------------------------------ per-thread FIR cascade
 	uint8_t *row = smem + kRow0 + tid * kRowStride;
@@ -207,6 +133,44 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	block_epilogue(p, job, tile, [&](int m) -> uint32_t {
 		return *reinterpret_cast<const uint32_t *>(smem + kRow0 + (m >> 6) * kRowStride + (m & 63) * 4);
 	}, es, trig64);
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ EpiShared es;
+	const int stream = blockIdx.y;
+	const StreamJob job = p.jobs[stream];
+	StreamState *st = p.st + stream;
+	const int tile = (p.use_progress ? (int)st->t2_done : p.tile0) + blockIdx.x;   // block index inside the submit
+	if (tile >= (int)job.n_blocks) return;
+	if (threadIdx.x == 0) mbar_init(smem_u32(smem), 1);
+	__syncthreads();
+	fe_block<WIDE>(p, job, st, tile, smem, es, 0u);
+}
+
+// The blocks the screening front-end (frontend_screen.cu) handed back because too many of their samples could be
+// triggers (bursts: telegrams, start-up transients): FrontParams::dense_list holds stream << 20 | block, dense_cnt how
+// many.  The grid is a fixed number of CTAs, each takes every gridDim.x-th entry.
+template <bool WIDE>
+__global__ void __launch_bounds__(kThreads, 3) frontend_list_kernel(const FrontParams p)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ EpiShared es;
+	const uint32_t cnt = *p.dense_cnt;
+	if (blockIdx.x >= cnt) return;
+	if (threadIdx.x == 0) mbar_init(smem_u32(smem), 1);
+	__syncthreads();
+	uint32_t phase = 0;
+	for (uint32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
+		const uint32_t e = p.dense_list[k];
+		const int stream = (int)(e >> 20), tile = (int)(e & 0xfffffu);
+		const StreamJob job = p.jobs[stream];
+		fe_block<WIDE>(p, job, p.st + stream, tile, smem, es, phase);
+		phase ^= 1u;
+		__syncthreads();   // the epilogue has read the block out of shared memory before the next one lands
+	}
 }
 
 // The same block bookkeeping for input that is ALREADY decimated: int16 I,Q at 384 kS/s, what the reference hands to
@@ -287,6 +251,27 @@ cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaS
 		frontend_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
 	else
 		frontend_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_list(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream)
+{
+	static bool attr_done[64] = { false };
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 64 && !attr_done[dev]) {
+		e = cudaFuncSetAttribute(frontend_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(frontend_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (e != cudaSuccess) return e;
+		attr_done[dev] = true;
+	}
+	if (n_ctas <= 0) return cudaSuccess;
+	if (wide)
+		frontend_list_kernel<true><<<n_ctas, kThreads, kSmemBytes, stream>>>(p);
+	else
+		frontend_list_kernel<false><<<n_ctas, kThreads, kSmemBytes, stream>>>(p);
 	return cudaGetLastError();
 }
 

@@ -21,6 +21,11 @@ bool frontend_tc_available();
 int frontend_tc_encode(const void *iq, uint32_t n_blocks, void *out);
 cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, int decimated, cudaStream_t stream);
 cudaError_t launch_frontend_i16(const FrontParams &p, int n_streams, cudaStream_t stream);
+cudaError_t launch_frontend_list(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream);
+cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream);
+cudaError_t launch_decwin(const BackParams &p, int wide, const uint8_t *hist_copy, uint32_t *dec_out, cudaStream_t s);
+void screen_build_consts(int wide, uint8_t *blob, int *shift, int *slack);
+constexpr int kScreenConstBytes = 2048 + 8192 + 256;   // frontend_screen.cu: kScBytes
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s);
@@ -39,7 +44,7 @@ cudaError_t launch_downconvert(const void *iq, long long n_pairs, int passes, in
 
 using namespace tfr;
 
-static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 112,
+static_assert(sizeof(tfr_config) == 40 && sizeof(tfr_frame) == 112 && sizeof(tfr_record) == 72 && sizeof(tfr_stats) == 144,
 	      "public struct layout changed: bump TFR_ABI_VERSION");
 
 static constexpr int kFrontChunks = 8;   // front-end launches per call (each overlaps the previous chunk's threshold walk)
@@ -99,6 +104,11 @@ struct tfr_handle {
 		StreamJob *d_jobs = nullptr;
 		uint8_t *d_tmaps = nullptr;              // [stream][2] CUtensorMap of the call's submits (frontend_tc_kernel)
 		std::vector<uint8_t> h_tmaps;            // host copy (stays until the slot's next call)
+		uint32_t *d_dense_list = nullptr;        // screening front-end: blocks handed to the dense kernel, per chunk launch
+		size_t cap_dense = 0;
+		uint32_t *d_dense_cnt = nullptr;         // [kFrontChunks]
+		uint8_t *d_hist_copy = nullptr;          // [stream][kHistBytes]: the FIR history the call started from
+		cudaEvent_t raw_done = nullptr;          // decwin_kernel has read the call's raw bytes (the input arena may be rewritten)
 		TileDesc *d_tiles = nullptr;
 		uint32_t *d_dec = nullptr;
 		BlockTrace *d_trace = nullptr;
@@ -130,6 +140,16 @@ struct tfr_handle {
 	cudaStream_t part_stream[kMaxParts] = { nullptr }, part_long[kMaxParts] = { nullptr };
 	cudaEvent_t part_fm[kMaxParts] = { nullptr }, part_done[kMaxParts] = { nullptr }, part_ldone[kMaxParts] = { nullptr };
 	size_t min_chunk = 8192;           // blocks per front-end chunk launch at least (TFR_MIN_CHUNK: tests exercise chunks and parts on small inputs)
+	bool use_screen = false;           // screening front-end (frontend_screen.cu): the tensor core proves which samples cannot trigger,
+	                                   // exact FIR only for candidates and inside demodulator windows.  Default; TFR_FE=dense selects
+	                                   // the dense exact kernel of frontend.cu for every block
+	uint8_t *d_screen_consts = nullptr;
+	int screen_shift = 0, screen_slack = 0;
+	uint32_t *d_screen_stat = nullptr; // [4] sparse blocks, dense blocks, candidates, true bound-triggers
+	int32_t *d_screen_dbg = nullptr;   // TFR_FLAG_TAPS: screen values of the last call [block][8192][2]
+	size_t screen_dbg_blocks = 0;
+	int win_demod = -1;                // the demodulator with the longest timeout: its windows contain every sample any demodulator reads
+	int n_sms = 148;
 	bool use_tc = false;               // TFR_FE=tc: the front-end variant with tensor-core byte->float conversion (frontend_tc.cu,
 	                                   // bit-identical, measured 28 % slower on B200: DESIGN.md 4.1b); default frontend.cu
 	cudaStream_t stream_walk = nullptr;   // threshold walk of front-end chunk k, concurrent with the front-end of chunk k+1
@@ -242,7 +262,10 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
+	cudaFree(h->d_screen_consts); cudaFree(h->d_screen_stat); cudaFree(h->d_screen_dbg);
 	for (auto &sl : h->slot) {
+		cudaFree(sl.d_dense_list); cudaFree(sl.d_dense_cnt); cudaFree(sl.d_hist_copy);
+		if (sl.raw_done) cudaEventDestroy(sl.raw_done);
 		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
 		cudaFree(sl.d_ld); cudaFree(sl.d_biq);
@@ -343,6 +366,21 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		if (const char *be = getenv("TFR_BE")) h->biq_chains = strcmp(be, "chains") == 0;
 		const char *fe = getenv("TFR_FE");                  // experiments: TFR_FE=tc selects the tensor-core front-end variant
 		h->use_tc = fe && !strcmp(fe, "tc") && frontend_tc_available();
+		// default: the screening front-end (needs cuTensorMapEncodeTiled; TFR_FE=dense keeps the dense exact kernel everywhere)
+		h->use_screen = !h->use_tc && !(fe && (!strcmp(fe, "dense") || !strcmp(fe, "old"))) && frontend_tc_available();
+		if (fe && !strcmp(fe, "screen") && !h->use_screen) return bail(fail(TFR_E_CUDA, "tfr_create: TFR_FE=screen needs cuTensorMapEncodeTiled"));
+		if (cfg->n_streams > 4095) h->use_screen = false;   // dense list entries: stream << 20 | block
+		CUH(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
+		for (int k = 0; k < h->dcfg.n_demods; k++)
+			if (h->win_demod < 0 || h->dcfg.d[k].timeout > h->dcfg.d[h->win_demod].timeout) h->win_demod = k;
+	}
+	if (h->use_screen) {
+		std::vector<uint8_t> blob(kScreenConstBytes);
+		screen_build_consts(h->dcfg.filter, blob.data(), &h->screen_shift, &h->screen_slack);
+		CUH(cudaMalloc(&h->d_screen_consts, kScreenConstBytes));
+		CUH(cudaMemcpy(h->d_screen_consts, blob.data(), kScreenConstBytes, cudaMemcpyHostToDevice));
+		CUH(cudaMalloc(&h->d_screen_stat, 4 * sizeof(uint32_t)));
+		CUH(cudaMemset(h->d_screen_stat, 0, 4 * sizeof(uint32_t)));
 	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -358,6 +396,11 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaEventCreate(&sl.fe1));
 		CUH(cudaMalloc(&sl.d_jobs, sizeof(StreamJob) * cfg->n_streams));
 		CUH(cudaMalloc(&sl.d_tmaps, (size_t)256 * cfg->n_streams));
+		CUH(cudaEventCreateWithFlags(&sl.raw_done, cudaEventDisableTiming));
+		CUH(cudaMalloc(&sl.d_dense_cnt, sizeof(uint32_t) * kFrontChunks));
+		CUH(cudaMemset(sl.d_dense_cnt, 0, sizeof(uint32_t) * kFrontChunks));
+		CUH(cudaMalloc(&sl.d_hist_copy, (size_t)kHistBytes * cfg->n_streams));
+		CUH(cudaMemset(sl.d_hist_copy, 128, (size_t)kHistBytes * cfg->n_streams));
 		sl.h_tmaps.assign((size_t)256 * cfg->n_streams + 64, 0);
 		CUH(cudaMalloc(&sl.d_wincnt, sizeof(WinCount) * cfg->n_streams));
 		CUH(cudaMemset(sl.d_wincnt, 0, sizeof(WinCount) * cfg->n_streams));
@@ -461,6 +504,7 @@ static int submit_common(tfr_handle *h, int stream, const uint8_t *iq, size_t nb
 			size_t tot = 0;
 			for (auto &c : h->arena) tot += c.cap;
 			CU(cudaStreamSynchronize(h->stream));
+			CU(cudaStreamSynchronize(h->stream_be));
 			for (auto &c : h->arena) cudaFree(c.ptr);
 			h->arena.clear();
 			uint8_t *ptr = nullptr;
@@ -475,6 +519,7 @@ static int submit_common(tfr_handle *h, int stream, const uint8_t *iq, size_t nb
 			if (h->arena.empty()) want *= (size_t)h->cfg.n_streams;
 			if (idle && !h->arena.empty()) {   // nothing points into the old chunk: replace it
 				CU(cudaStreamSynchronize(h->stream));
+				CU(cudaStreamSynchronize(h->stream_be));
 				for (auto &c : h->arena) cudaFree(c.ptr);
 				h->arena.clear();
 			}
@@ -485,6 +530,9 @@ static int submit_common(tfr_handle *h, int stream, const uint8_t *iq, size_t nb
 			ck = &h->arena.back();
 		}
 		uint8_t *dst = ck->ptr + ck->used;
+		// the window kernel of the calls in flight (back-end stream) still reads their raw bytes out of this arena
+		if (h->use_screen)
+			for (auto &sl : h->slot) CU(cudaStreamWaitEvent(h->stream, sl.raw_done, 0));
 		if (!h->h2d_timed) {
 			CU(cudaEventRecord(h->ev_h2d0, h->stream));
 			h->h2d_timed = true;
@@ -569,7 +617,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	}
 	// h->jobs stays untouched until the copy has run: the next tfr_process first waits for this slot's events
 	CU(cudaMemcpyAsync(sl.d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, sf));
-	if (h->use_tc && !decimated) {
+	// screening front-end: raw bytes, nothing that wants every decimated sample, the back-end as one part
+	const bool screen = h->use_screen && !decimated && !(h->cfg.flags & TFR_FLAG_KEEP_DECIM) && h->be_parts == 1 && !getenv("TFR_DEVFM_BLOCKS");
+	if ((h->use_tc || screen) && !decimated) {
 		// the call's tensor maps (TMA descriptors of every stream's submit), encoded on the host, 64-byte aligned
 		uint8_t *tm = reinterpret_cast<uint8_t *>(((uintptr_t)sl.h_tmaps.data() + 63) & ~(uintptr_t)63);
 		for (int s = 0; s < ns; s++)
@@ -584,6 +634,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	const bool auto_mode = (h->dcfg.thresh_cfg == 0);
 
 	FrontParams fp;
+	memset(&fp, 0, sizeof(fp));
 	fp.jobs = sl.d_jobs;
 	fp.st = h->d_state;
 	fp.tiles = sl.d_tiles;
@@ -596,6 +647,47 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	fp.margin = 0;
 	fp.use_progress = 0;
 	fp.tmaps = sl.d_tmaps;
+	fp.n_streams = ns;
+	if (screen) {
+		fp.screen_consts = h->d_screen_consts;
+		fp.screen_shift = h->screen_shift;
+		fp.screen_slack = h->screen_slack;
+		fp.hist_copy = sl.d_hist_copy;
+		fp.screen_stat = h->d_screen_stat;
+		if (h->cfg.flags & TFR_FLAG_TAPS) {   // debug: the screen values of this call
+			if (h->screen_dbg_blocks < total) {
+				CU(cudaStreamSynchronize(sf));
+				cudaFree(h->d_screen_dbg);
+				h->d_screen_dbg = nullptr;
+				h->screen_dbg_blocks = 0;
+				CU(cudaMalloc(&h->d_screen_dbg, total * (size_t)kBlockDec * 2 * sizeof(int32_t)));
+				h->screen_dbg_blocks = total;
+			}
+			CU(cudaMemsetAsync(h->d_screen_dbg, 0, total * (size_t)kBlockDec * 2 * sizeof(int32_t), sf));
+			fp.screen_dbg = h->d_screen_dbg;
+		}
+		CU(cudaMemsetAsync(sl.d_dense_cnt, 0, sizeof(uint32_t) * kFrontChunks, sf));
+		// a chunk launch covers ceil(max_blocks / chunks) blocks of every stream: room for every one of them, per chunk
+		const size_t need = ((size_t)max_blocks + 2 * kFrontChunks) * (size_t)ns;
+		if (need > sl.cap_dense) {
+			rc = sync_all(h);
+			if (rc) return rc;
+			cudaFree(sl.d_dense_list);
+			sl.d_dense_list = nullptr;
+			sl.cap_dense = 0;
+			CU(cudaMalloc(&sl.d_dense_list, need * sizeof(uint32_t)));
+			sl.cap_dense = need;
+		}
+	}
+	// one chunk of blocks through the screen: the screening kernel, then the dense kernel over the blocks it handed back
+	auto launch_screen = [&](FrontParams q, int chunk, cudaStream_t st) -> cudaError_t {
+		q.dense_cnt = sl.d_dense_cnt + chunk;
+		q.dense_list = sl.d_dense_list + (size_t)q.tile0 * ns + (size_t)chunk * ns;
+		cudaError_t e = launch_frontend_screen(q, h->dcfg.filter, 2 * h->n_sms, st);
+		if (e != cudaSuccess) return e;
+		const int items = q.n_tiles * ns;
+		return launch_frontend_list(q, h->dcfg.filter, std::min(items, 3 * h->n_sms), st);
+	};
 	auto launch_fe = [&](const FrontParams &q, cudaStream_t st) {
 		if (decimated) return launch_frontend_i16(q, ns, st);
 		return h->use_tc ? launch_frontend_tc(q, ns, h->dcfg.filter, st) : launch_frontend(q, ns, h->dcfg.filter, st);
@@ -641,6 +733,14 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	// demodulators over the windows of one back-end part (BackParams::part_lo/part_hi, blocks [tile0, tile0+n_tiles))
 	auto launch_demods = [&](BackParams q, int part) -> int {
 		if (!h->dcfg.n_demods) return TFR_OK;
+		if (screen) {
+			// the decimated samples of every window (the screen stored none): exact FIR from the raw bytes
+			BackParams w = q;
+			w.demod = h->win_demod;
+			CU(launch_decwin(w, h->dcfg.filter, sl.d_hist_copy, sl.d_dec, sb));
+			CU(cudaEventRecord(sl.raw_done, sb));
+			h->stats.kernel_launches += 1;
+		}
 		// fm_dev on the back stream, part after part (a window's filter warm-up reads the values of earlier parts).  A call
 		// that runs as ONE part knows every window by now and computes fm_dev only inside them; parts work from the
 		// blocks' descriptors (the demodulators' part cuts differ, so no single window list bounds a part's samples)
@@ -712,7 +812,12 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			// the chunks are independent of each other: alternating two streams lets chunk k+1's first CTAs fill the
 			// SMs that chunk k's last wave leaves idle
 			cudaStream_t sk = (k & 1) ? h->stream_fe2 : sf;
-			CU(launch_fe(fp, sk));
+			if (screen) {
+				CU(launch_screen(fp, k, sk));
+				h->stats.kernel_launches += 1;
+			} else {
+				CU(launch_fe(fp, sk));
+			}
 			CU(cudaEventRecord(h->chunk_ev[k], sk));
 			if (k & 1) last_odd = k;
 			CU(cudaStreamWaitEvent(h->stream_walk, h->chunk_ev[k], 0));
@@ -1061,6 +1166,23 @@ extern "C" __attribute__((visibility("default"))) long tfr_read_decimated(tfr_ha
 	return (long)n;
 }
 
+extern "C" __attribute__((visibility("default"))) long tfr_read_screen(tfr_handle *h, int stream, int32_t *out, size_t cap_int32, int *shift, int *slack)
+{
+	if (!h || stream < 0 || stream >= h->cfg.n_streams) return fail(TFR_E_INVAL, "tfr_read_screen: bad argument");
+	if (!(h->cfg.flags & TFR_FLAG_TAPS) || !h->use_screen) return fail(TFR_E_INVAL, "tfr_read_screen: needs TFR_FLAG_TAPS and the screening front-end");
+	int rc = tfr_sync(h);
+	if (rc) return rc;
+	if (shift) *shift = h->screen_shift;
+	if (slack) *slack = h->screen_slack;
+	if (h->jobs.empty() || !h->d_screen_dbg) return 0;
+	const StreamJob &j = h->jobs[stream];
+	const size_t avail = (size_t)j.n_blocks * kBlockDec * 2;
+	if (!out) return (long)avail;
+	const size_t n = std::min(cap_int32, avail) & ~(size_t)1;
+	if (n) CU(cudaMemcpy(out, h->d_screen_dbg + (size_t)j.dec_off * kBlockDec * 2, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+	return (long)n;
+}
+
 extern "C" __attribute__((visibility("default"))) long tfr_decimate(int device, const uint8_t *iq, size_t nbytes, int filter, int16_t *out, int mem)
 {
 	if (!iq || !out || nbytes < 4) return fail(TFR_E_INVAL, "tfr_decimate: bad argument");
@@ -1382,6 +1504,18 @@ extern "C" __attribute__((visibility("default"))) int tfr_parse_bytes(tfr_handle
 extern "C" __attribute__((visibility("default"))) int tfr_get_stats(tfr_handle *h, tfr_stats *out)
 {
 	if (!h || !out) return fail(TFR_E_INVAL, "tfr_get_stats: null argument");
+	if (h->d_screen_stat) {
+		uint32_t v[4] = { 0, 0, 0, 0 };
+		CU(cudaSetDevice(h->device));
+		int rc = tfr_sync(h);
+		if (rc) return rc;
+		CU(cudaMemcpy(v, h->d_screen_stat, sizeof(v), cudaMemcpyDeviceToHost));
+		CU(cudaMemset(h->d_screen_stat, 0, sizeof(v)));
+		h->stats.screen_blocks += v[0];
+		h->stats.dense_blocks += v[1];
+		h->stats.screen_candidates += v[2];
+		h->stats.screen_triggers += v[3];
+	}
 	*out = h->stats;
 	return TFR_OK;
 }

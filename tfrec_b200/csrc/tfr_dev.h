@@ -231,7 +231,17 @@ struct FrontParams {
 	                       // the launch, epoch fallback); 0 = the call's frozen speculative bound StreamState::spec_lo
 	int use_progress;      // 1: a stream's first block of this launch is its StreamState::t2_done (epoch fallback)
 	uint32_t *events;      // [gtile][kMaxEvt]
-	const void *tmaps;     // frontend_tc_kernel: [stream][2] CUtensorMap (rows of the submit, and the 32 bytes in front of every row)
+	const void *tmaps;     // frontend_tc_kernel / frontend_screen_kernel: [stream][2] CUtensorMap (rows of the submit, and the 32 bytes in front of every row)
+	// screening front-end (frontend_screen.cu)
+	const uint8_t *screen_consts;  // ScreenConsts blob: the band matrix of the combined 46-tap filter, the constant operands
+	int screen_shift;      // q: screen value = linear filter output * 2^q
+	int screen_slack;      // what a sample's true |I|+|Q| can exceed its screen value by, in output units (rounded up)
+	int n_streams;
+	uint32_t *dense_list;  // blocks handed to the dense kernel: stream << 20 | block
+	uint32_t *dense_cnt;
+	uint8_t *hist_copy;    // [stream][kHistBytes]: the FIR history the call started from (the window kernel runs after save_history)
+	int32_t *screen_dbg;   // debug (TFR_FLAG_TAPS): [gtile][8192][2] screen values of I and Q, null otherwise
+	uint32_t *screen_stat; // [0] blocks screened sparse, [1] blocks handed back dense, [2] candidates checked, [3] of them true
 };
 
 struct BackParams {

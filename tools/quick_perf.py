@@ -33,7 +33,8 @@ def main():
         samples = n_streams * nbytes / 2
         print("iter %d wall %.3f ms  frontend %.3f ms (%.1f GS/s, %.1f GB/s)  backend %.3f ms  active %.2f%% frames %d thresh %d" % (
             it, dt * 1e3, st["last_frontend_ms"], samples / st["last_frontend_ms"] / 1e6, 2 * samples / st["last_frontend_ms"] / 1e6,
-            st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)), "windows", rx.stats()["windows"], "reruns", rx.stats()["reruns"], "sr/bq/edge", rx.stats()["reruns_sr"], rx.stats()["reruns_biquad"], rx.stats()["reruns_edge"])
+            st["last_backend_ms"], 100.0 * st["active_samples"] / (st["raw_samples"] / 4), rx.n_records(), rx.thresh(0)), "windows", rx.stats()["windows"], "reruns", rx.stats()["reruns"], "sr/bq/edge", rx.stats()["reruns_sr"], rx.stats()["reruns_biquad"], rx.stats()["reruns_edge"],
+              "screen/dense/cand/true", st["screen_blocks"], st["dense_blocks"], st["screen_candidates"], st["screen_triggers"])
         rx.records(); rx.clear()
     # pipelined: K calls in flight, one sync (front-end of call i+1 overlaps the back-end of call i)
     K = 8
