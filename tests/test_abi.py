@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(tb.Frame) == 112
     assert C.sizeof(tb.Record) == 72
     assert C.sizeof(tb.BlockTrace) == 12
-    assert C.sizeof(tb.Stats) == 112
+    assert C.sizeof(tb.Stats) == 144
 
 
 def test_create_validates_arguments(lib):
