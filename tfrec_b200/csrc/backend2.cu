@@ -721,7 +721,7 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 	const BiquadCoef k = cfg.lp;
 	int bitcnt = s.bitcnt, dmin = s.dmin, dmax = s.dmax, offset = s.offset, last_bit = s.last_bit, rssi = s.rssi_i,
 	    lbi = s.last_bit_idx;
-	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
+	const int td_lo = cfg.td_lo, td_hi = cfg.td_hi;   // tfa2.cpp:391 `tdiff>spb/4 && tdiff<32*spb` for integer tdiff
 	LdHash hash;
 	hash.init();
 	BitRuns br;
@@ -768,9 +768,9 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 			if (index > lbi + 8) {
 				bitcnt++;
 				const int tdiff = index - lbi;
-				if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
+				if (tdiff >= td_lo && tdiff <= td_hi) {
 					const int bit_diff = tdiff / 2;
-					const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
+					const int numbits = cfg.nbits[bit_diff];
 					if (br.n + 2 > kBitRuns) drain();
 					if (numbits < 32 && numbits > 1) br.run[br.n++] = (uint16_t)(((numbits - 1) << 1) | last_bit);
 					br.run[br.n++] = (uint16_t)((1 << 1) | bit);
@@ -847,10 +847,29 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 			}
 			if ((ld > hi || ld < lo) && (int)(ld > hi) != last_bit) edge(m, ld);
 		};
-		sample(cb, l0);
-		sample(cb + 1, l1);
-		sample(cb + 2, l2);
-		sample(cb + 3, l3);
+		if (bitcnt < 10) {
+			sample(cb, l0);
+			sample(cb + 1, l1);
+			sample(cb + 2, l2);
+			sample(cb + 3, l3);
+		} else {
+			// The levels are frozen (tfa2.cpp:365 `if (bitcnt<10)`): which of the four samples is an edge candidate
+			// depends on last_bit alone - (ld > hi || ld < lo) && (ld > hi) != last_bit is `ld > hi` for last_bit 0 and
+			// `ld < lo && !(ld > hi)` for last_bit 1.  The candidates are taken in order, but in ONE loop: every lane of
+			// the warp handles its first candidate in the same pass, whatever sample of the group it sits on (four
+			// per-sample regions ran the edge code up to four times per group, each time for one or two lanes).
+			const unsigned h = (unsigned)(l0 > hi) | ((unsigned)(l1 > hi) << 1) | ((unsigned)(l2 > hi) << 2) | ((unsigned)(l3 > hi) << 3);
+			const unsigned l = (unsigned)(l0 < lo) | ((unsigned)(l1 < lo) << 1) | ((unsigned)(l2 < lo) << 2) | ((unsigned)(l3 < lo) << 3);
+			const unsigned c0 = h, c1 = l & ~h;
+			unsigned todo = 0xfu;
+			for (;;) {
+				const unsigned m = (last_bit ? c1 : c0) & todo;
+				if (!m) break;
+				const int kq = __ffs(m) - 1;
+				edge(cb + kq, kq == 0 ? l0 : kq == 1 ? l1 : kq == 2 ? l2 : l3);
+				todo = (0xfu << (kq + 1)) & 0xfu;
+			}
+		}
 #ifdef TFR_WIN_PROFILE
 		pf_fast++; pf_cfast += clock64() - pg0;
 #endif
@@ -1487,7 +1506,7 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 	const BiquadCoef k = cfg.lp;
 	int bitcnt = s.bitcnt, dmin = s.dmin, dmax = s.dmax, offset = s.offset, last_bit = s.last_bit, rssi = s.rssi_i,
 	    lbi = s.last_bit_idx;
-	const double spb = cfg.spb, spb_lo = __dmul_rn(spb, 0.25), spb_hi = __dmul_rn(32.0, spb), spb_half = __dmul_rn(spb, 0.5);
+	const int td_lo = cfg.td_lo, td_hi = cfg.td_hi;   // tfa2.cpp:391 `tdiff>spb/4 && tdiff<32*spb` for integer tdiff
 	uint32_t ha = 0, hb = 0;   // this lane's share of the LdHash sums
 	BitRuns br;
 	br.n = 0;
@@ -1521,9 +1540,9 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 			if (index > lbi + 8) {
 				bitcnt++;
 				const int tdiff = index - lbi;
-				if ((double)tdiff > spb_lo && (double)tdiff < spb_hi) {
+				if (tdiff >= td_lo && tdiff <= td_hi) {
 					const int bit_diff = tdiff / 2;
-					const int numbits = __double2int_rz(__ddiv_rn(__dadd_rn((double)bit_diff, spb_half), spb));
+					const int numbits = cfg.nbits[bit_diff];
 					if (br.n + 2 > kBitRuns) drain();
 					if (numbits < 32 && numbits > 1) br.run[br.n++] = (uint16_t)(((numbits - 1) << 1) | last_bit);
 					br.run[br.n++] = (uint16_t)((1 << 1) | bit);

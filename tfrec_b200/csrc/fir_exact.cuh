@@ -72,4 +72,62 @@ __device__ __forceinline__ f2 stage1(const f2 *x)
 	return acc;
 }
 
+// The per-thread cascade of frontend.cu as a function: NIT x 16 consecutive outputs from 96 + NIT x 128 consecutive raw
+// bytes.  halo(q), q = 0..5: the q-th 16 bytes of the 96 in front of the thread's first raw byte (raw samples -48..-1);
+// row(q): the q-th 16 bytes of its own; out(m, yi, yq) receives output m = 0 .. 16 NIT - 1 in order.
+template <bool WIDE, int NIT, class Halo, class Row, class Out>
+__device__ __forceinline__ void fir_cascade(const Halo &halo, const Row &row, const Out &out)
+{
+	f2 ring[32];   // stage-1 outputs (kM1 + y1), slot = index mod 32
+	f2 xh[6];      // last 6 converted raw samples
+	{
+		f2 hx[48];
+#pragma unroll
+		for (int q = 0; q < 6; q++) {
+			const uint4 v = halo(q);
+			hx[8 * q + 0] = cvt_iq(v.x, 0); hx[8 * q + 1] = cvt_iq(v.x, 1);
+			hx[8 * q + 2] = cvt_iq(v.y, 0); hx[8 * q + 3] = cvt_iq(v.y, 1);
+			hx[8 * q + 4] = cvt_iq(v.z, 0); hx[8 * q + 5] = cvt_iq(v.z, 1);
+			hx[8 * q + 6] = cvt_iq(v.w, 0); hx[8 * q + 7] = cvt_iq(v.w, 1);
+		}
+		// y1[j] (j = -18..-1) needs x[2j-6 .. 2j+1]; hx[k] = x[k-48]
+#pragma unroll
+		for (int j = -18; j < 0; j++) ring[(j + 32) & 31] = stage1(&hx[2 * j + 42]);
+#pragma unroll
+		for (int k = 0; k < 6; k++) xh[k] = hx[42 + k];
+	}
+#pragma unroll 1
+	for (int it = 0; it < NIT; it++) {
+#pragma unroll
+		for (int s = 0; s < 8; s++) {
+			const uint4 v = row(it * 8 + s);
+			f2 x[14];
+#pragma unroll
+			for (int k = 0; k < 6; k++) x[k] = xh[k];
+			x[6] = cvt_iq(v.x, 0); x[7] = cvt_iq(v.x, 1);
+			x[8] = cvt_iq(v.y, 0); x[9] = cvt_iq(v.y, 1);
+			x[10] = cvt_iq(v.z, 0); x[11] = cvt_iq(v.z, 1);
+			x[12] = cvt_iq(v.w, 0); x[13] = cvt_iq(v.w, 1);
+#pragma unroll
+			for (int jj = 0; jj < 4; jj++) ring[(4 * s + jj) & 31] = stage1(&x[2 * jj]);
+#pragma unroll
+			for (int k = 0; k < 6; k++) xh[k] = x[8 + k];
+#pragma unroll
+			for (int mm = 0; mm < 2; mm++) {
+				const int m = 2 * s + mm;
+				f2 a = pack2((float)kA2a, (float)kA2a), b = pack2((float)kA2b, (float)kA2b);
+#pragma unroll
+				for (int n = 0; n < 10; n++) {
+					a = fma2_rm(ring[(2 * m - 18 + n + 32) & 31], c2pair<WIDE>(n), a);
+					b = fma2_rm(ring[(2 * m - 8 + n + 32) & 31], c2pair<WIDE>(n + 10), b);
+				}
+				uint32_t ai, aq, bi, bq;
+				unpack2(a, ai, aq);
+				unpack2(b, bi, bq);
+				out(it * 16 + m, (int)(ai + bi - y2_bias(WIDE)), (int)(aq + bq - y2_bias(WIDE)));
+			}
+		}
+	}
+}
+
 }  // namespace tfr

@@ -150,29 +150,6 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontParams
 	fe_block<WIDE>(p, job, st, tile, smem, es, 0u);
 }
 
-// The blocks the screening front-end (frontend_screen.cu) handed back because too many of their samples could be
-// triggers (bursts: telegrams, start-up transients): FrontParams::dense_list holds stream << 20 | block, dense_cnt how
-// many.  The grid is a fixed number of CTAs, each takes every gridDim.x-th entry.
-template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, 3) frontend_list_kernel(const FrontParams p)
-{
-	extern __shared__ __align__(128) uint8_t smem[];
-	__shared__ EpiShared es;
-	const uint32_t cnt = *p.dense_cnt;
-	if (blockIdx.x >= cnt) return;
-	if (threadIdx.x == 0) mbar_init(smem_u32(smem), 1);
-	__syncthreads();
-	uint32_t phase = 0;
-	for (uint32_t k = blockIdx.x; k < cnt; k += gridDim.x) {
-		const uint32_t e = p.dense_list[k];
-		const int stream = (int)(e >> 20), tile = (int)(e & 0xfffffu);
-		const StreamJob job = p.jobs[stream];
-		fe_block<WIDE>(p, job, p.st + stream, tile, smem, es, phase);
-		phase ^= 1u;
-		__syncthreads();   // the epilogue has read the block out of shared memory before the next one lands
-	}
-}
-
 // The same block bookkeeping for input that is ALREADY decimated: int16 I,Q at 384 kS/s, what the reference hands to
 // fsk_demod::process(int16_t *data_iq, int len) (fm_demod.cpp:34-74, len = 16384 per block).  No filter: a thread
 // copies its 64 samples into the row layout above, tests them against the trigger bound and joins the epilogue.
@@ -251,27 +228,6 @@ cudaError_t launch_frontend(const FrontParams &p, int n_streams, int wide, cudaS
 		frontend_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(p);
 	else
 		frontend_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(p);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_frontend_list(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream)
-{
-	static bool attr_done[64] = { false };
-	int dev = 0;
-	cudaError_t e = cudaGetDevice(&dev);
-	if (e != cudaSuccess) return e;
-	if (dev < 64 && !attr_done[dev]) {
-		e = cudaFuncSetAttribute(frontend_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-		if (e != cudaSuccess) return e;
-		e = cudaFuncSetAttribute(frontend_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-		if (e != cudaSuccess) return e;
-		attr_done[dev] = true;
-	}
-	if (n_ctas <= 0) return cudaSuccess;
-	if (wide)
-		frontend_list_kernel<true><<<n_ctas, kThreads, kSmemBytes, stream>>>(p);
-	else
-		frontend_list_kernel<false><<<n_ctas, kThreads, kSmemBytes, stream>>>(p);
 	return cudaGetLastError();
 }
 

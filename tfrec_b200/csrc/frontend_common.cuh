@@ -219,7 +219,9 @@ __device__ __forceinline__ void block_epilogue(const FrontParams &p, const Strea
 	uint32_t *dst = p.dec + gtile * kBlockDec;
 	const int nseg = es.nseg;
 	auto sample = [&](int m) -> uint32_t { return smp(m); };
-	if (p.keep_all) {
+	if (p.keep_all == 2) {
+		// the caller has already written every sample of the block to dec (frontend_screen.cu, a burst block done in place)
+	} else if (p.keep_all) {
 		for (int m = tid; m < kBlockDec; m += kThreads) dst[m] = sample(m);
 	} else {
 		// head [0, t_max) and the last sample are always kept (needed when the previous block's trigger

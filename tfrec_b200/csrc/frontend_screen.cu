@@ -17,7 +17,7 @@
 // A sample with |cI| + |cQ| <= (thresh_lo - slack) << q therefore has pwr <= thresh_lo and is provably no trigger.  The
 // rest (a handful per block on noise) are CANDIDATES: their exact values are computed with the reference arithmetic
 // (fir_exact.cuh, one warp per candidate, lane = stage-2 tap) and tested for real.  Blocks with many candidates
-// (telegram bursts, start-up) are handed to the dense kernel of frontend.cu through a list.  The decimated samples
+// (telegram bursts, start-up) run the whole exact cascade in place, like frontend.cu.  The decimated samples
 // the demodulators read are produced after the threshold walk, when the windows are known, by decwin_kernel (below):
 // exact FIR over [window start - 1, window end] only.
 //
@@ -103,6 +103,20 @@ __device__ __forceinline__ void sc_ld16(uint32_t taddr, uint32_t (&v)[16])
 		     : "r"(taddr)
 		     : "memory");
 }
+// 32 consecutive columns (8 outputs) per instruction: a round trip to tensor memory costs ~150 cycles whatever it carries
+__device__ __forceinline__ void sc_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+		       "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+		       "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+		       "=r"(v[31])
+		     : "r"(taddr)
+		     : "memory");
+}
+// the registers of outstanding tcgen05.ld may only be read after this (the asm volatile statements keep their order)
+__device__ __forceinline__ void sc_wait_ld_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sc_wait_ld(uint32_t (&v)[16])
 {
 	asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -112,27 +126,25 @@ __device__ __forceinline__ void sc_wait_ld(uint32_t (&v)[16])
 		     : "memory");
 }
 
-// the 32-bit word at byte offset o (a multiple of 4, -96 <= o < 65536) of the block, from the swizzled boxes: 16-byte
-// chunk c of box row r sits at chunk position c ^ (r & 7); bytes before the block are the tail of the halo box's row 0
-__device__ __forceinline__ uint32_t sc_raw_word(const uint8_t *smem, int o)
-{
-	if (o < 0) return *reinterpret_cast<const uint32_t *>(smem + kOffHaloBox + 128 + o);
-	const int row = o >> 9, col = o & 511, box = col >> 7, cc = col & 127;
-	return *reinterpret_cast<const uint32_t *>(smem + box * kBox + row * 128 + ((((cc >> 4) ^ (row & 7))) << 4) + (cc & 15));
-}
-
 // stage-2 taps by lane (lanes 20..31: 0)
 __device__ const int kT1Narrow[32] = TFR_T1N;
 __device__ const int kT1Wide[32] = TFR_T1W;
 constexpr int kA2One = (1 << 23) + 4000000;   // one stage-2 tap per lane: 163 * t1 + floor part stays inside the integer binade
 static_assert(kA2One - 163 * 3198 - 3000 >= (1 << 23) && kA2One + 163 * 17421 + 3000 < (1 << 24), "single-tap accumulator range");
 
+#ifdef TFR_SCREEN_PROFILE
+__device__ unsigned long long g_scprof[8];   // thread 0: cycles waiting for loads, in the MMAs, readback, candidate list, evaluation, epilogue; blocks
+#define SCPROF(k) do { if (tid == 0) { const long long t_ = clock64(); prof[k] += t_ - pt; pt = t_; } } while (0)
+#else
+#define SCPROF(k) do { } while (0)
+#endif
+
 struct ScreenShared {
 	uint16_t cand[kCandMax + 2];
 	uint32_t res_w[kCandMax + 2];
 	int res_p[kCandMax + 2];
 	int warp_cnt[kWarps];
-	int total;
+	int next[2];   // the CTA's next work item, fetched by thread 0 one block ahead (double buffered)
 };
 
 template <bool WIDE>
@@ -140,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	__shared__ ScreenShared ss;
+	__shared__ EpiShared es;   // burst blocks done in place
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t sbase = smem_u32(smem);
@@ -158,11 +171,6 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemS), "n"(kScreenCols) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
-	sc_fence_before();
-	__syncthreads();
-	sc_fence_after();
-	const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + kOffTmemS);
-	const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
 
 	const uint64_t d_band = sc_desc(sbase + kOffConsts + kScBand, 1024, 128, kScNone);
 	const uint64_t d_bconst = sc_desc(sbase + kOffConsts + kScConst, 4096, 128, kScNone);
@@ -172,30 +180,64 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 	uint32_t phase = 0;
 	uint32_t st_sparse = 0, st_dense = 0, st_cand = 0, st_true = 0;   // thread 0's tallies
 
-	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+	// Work items (stream, block) are handed out by a counter, one block ahead (thread 0): a burst block done in place
+	// holds its CTA ten times as long as a screened one.  Streams may be shorter than the launch's tile range.
+	auto fetch_item = [&]() {
+		for (;;) {
+			const int it = (int)atomicAdd(p.work_ctr, 1u);
+			if (it >= n_items) return n_items;
+			const int s_ = it / p.n_tiles;
+			if (p.tile0 + (it - s_ * p.n_tiles) < (int)p.jobs[s_].n_blocks) return it;
+		}
+	};
+	// the five TMA boxes of a block (thread 0): the loads of block i+1 go out as soon as the MMAs of block i have
+	// consumed shared memory, and fly while the threads screen block i
+	auto issue_loads = [&](int item) {
+		const int s_ = item / p.n_tiles, t_ = p.tile0 + (item - s_ * p.n_tiles);
+		const uint8_t *tm = reinterpret_cast<const uint8_t *>(p.tmaps) + (size_t)s_ * 256;
+		asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+		mbar_expect_tx(bar_box + 32, kBox);
+		sc_tma_2d(sbase + kOffHaloBox, tm, 384, t_ * 128 - 1, bar_box + 32);
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			mbar_expect_tx(bar_box + 8 * q, kBox);
+			sc_tma_2d(sbase + q * kBox, tm, 128 * q, t_ * 128, bar_box + 8 * q);
+		}
+	};
+	if (tid == 0) {
+		const int it = fetch_item();
+		ss.next[0] = it;
+		if (it < n_items) issue_loads(it);
+	}
+	sc_fence_before();
+	__syncthreads();
+	sc_fence_after();
+	const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + kOffTmemS);
+	const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+
+#ifdef TFR_SCREEN_PROFILE
+	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, pt = clock64();
+#endif
+	for (int round = 0;; round++) {
+		const int item = ss.next[round & 1];
+		if (item >= n_items) break;
 		const int stream = item / p.n_tiles;
 		const int tile = p.tile0 + (item - stream * p.n_tiles);
 		const StreamJob job = p.jobs[stream];
-		if (tile >= (int)job.n_blocks) continue;   // uniform over the CTA
 		StreamState *st = p.st + stream;
 		const size_t gtile = (size_t)job.dec_off + tile;
+		const uint8_t *blk = job.iq + (size_t)tile * kBlockBytes;
+		const uint8_t *hist = st->hist[st->hist_parity & 1];
 
-		// ---- loads and MMAs, one thread
+		// ---- MMAs, one thread
 		if (tid == 0) {
-			const uint8_t *tm = reinterpret_cast<const uint8_t *>(p.tmaps) + (size_t)stream * 256;
-			asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
-			mbar_expect_tx(bar_box + 32, kBox);
-			sc_tma_2d(sbase + kOffHaloBox, tm, 384, tile * 128 - 1, bar_box + 32);
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				mbar_expect_tx(bar_box + 8 * q, kBox);
-				sc_tma_2d(sbase + q * kBox, tm, 128 * q, tile * 128, bar_box + 8 * q);
-			}
+			// all 256 columns = -(128 * sum T16 + centre), in planes: needs nothing of the block, goes first
+			sc_mma(tmem, d_ac, d_bconst, screen_idesc(256), 0u);
 			mbar_wait(bar_box + 32, phase);
 			if (tile == 0) {
 				// nothing in front of the submit (TMA filled row -1 with zeros): the carried history, 96 bytes in front of
 				// row 0.  The same bytes go to the slot's copy for decwin_kernel, which runs after save_history_kernel.
-				const uint4 *hs = reinterpret_cast<const uint4 *>(st->hist[st->hist_parity & 1]);
+				const uint4 *hs = reinterpret_cast<const uint4 *>(hist);
 				uint4 *hd = reinterpret_cast<uint4 *>(smem + kOffHaloBox + 32);
 				uint4 *hc = reinterpret_cast<uint4 *>(p.hist_copy + (size_t)stream * kHistBytes);
 #pragma unroll
@@ -208,8 +250,7 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 			}
 			mbar_wait(bar_box, phase);
 			sc_fence_after();
-			// all 256 columns = -(128 * sum T16 + centre), in planes
-			sc_mma(tmem, d_ac, d_bconst, screen_idesc(256), 0u);
+			SCPROF(0);
 			// the row before: byte slices -96.., -64.., -32.. reach outputs 0..2, 0..6, 0..10
 #pragma unroll
 			for (int s = 1; s <= 3; s++) {
@@ -228,6 +269,12 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 				sc_mma(tmem + 16 * s, da, d_band, screen_idesc(n), 1u);
 			}
 			sc_commit(bar_mma);
+			// shared memory is free once the MMAs are done: the next block's boxes
+			const int nx = fetch_item();
+			ss.next[(round + 1) & 1] = nx;
+			mbar_wait(bar_mma, phase);
+			if (nx < n_items) issue_loads(nx);
+			SCPROF(1);
 		}
 		__syncwarp();
 
@@ -242,29 +289,30 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 		unsigned long long cand64 = 0ull;
 		int32_t *dbg = p.screen_dbg ? p.screen_dbg + (gtile * kBlockDec + (size_t)tid * kOutPerThread) * 2 : nullptr;
 		{
-			uint32_t va[16], vb[16];
-			sc_ld16(tlane, va);
+			// two loads of 32 columns (8 outputs) in flight (64 columns each fill the register file: 254 registers, and the
+			// back-end kernels of the previous call no longer fit beside the two screening CTAs of an SM)
+			uint32_t va[32], vb[32];
+			auto screen8 = [&](const uint32_t (&v)[32], int j0) {
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const int ci = (int)(v[4 * k + 1] << 8) + (int)v[4 * k], cq = (int)(v[4 * k + 3] << 8) + (int)v[4 * k + 2];
+					if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (j0 + k);
+					if (dbg) { dbg[2 * (j0 + k)] = ci; dbg[2 * (j0 + k) + 1] = cq; }
+				}
+			};
+			sc_ld32(tlane, va);
+			sc_ld32(tlane + 32, vb);
 #pragma unroll 1
-			for (int g = 0; g < 16; g += 2) {
-				sc_wait_ld(va);
-				sc_ld16(tlane + 16 * (g + 1), vb);
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const int ci = (int)(va[4 * k + 1] << 8) + (int)va[4 * k], cq = (int)(va[4 * k + 3] << 8) + (int)va[4 * k + 2];
-					if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (4 * g + k);
-					if (dbg) { dbg[2 * (4 * g + k)] = ci; dbg[2 * (4 * g + k) + 1] = cq; }
-				}
-				sc_wait_ld(vb);
-				if (g + 2 < 16) sc_ld16(tlane + 16 * (g + 2), va);
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const int ci = (int)(vb[4 * k + 1] << 8) + (int)vb[4 * k], cq = (int)(vb[4 * k + 3] << 8) + (int)vb[4 * k + 2];
-					if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (4 * g + 4 + k);
-					if (dbg) { dbg[2 * (4 * g + 4 + k)] = ci; dbg[2 * (4 * g + 4 + k) + 1] = cq; }
-				}
+			for (int g = 0; g < 4; g++) {
+				sc_wait_ld_all();   // both loads have landed
+				screen8(va, 16 * g);
+				if (g < 3) sc_ld32(tlane + 64 * (g + 1), va);
+				screen8(vb, 16 * g + 8);
+				if (g < 3) sc_ld32(tlane + 64 * (g + 1) + 32, vb);
 			}
 		}
 
+		SCPROF(2);
 		// ---- ordered candidate list
 		const int nt = __popcll(cand64);
 		int incl = nt;
@@ -282,12 +330,26 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 		const bool is_last = (tile == (int)job.n_blocks - 1);
 
 		if (total > kCandMax) {
-			// a burst: the dense kernel redoes this block (descriptor, events, samples)
-			if (tid == 0) {
-				const uint32_t k = atomicAdd(p.dense_cnt, 1u);
-				p.dense_list[k] = ((uint32_t)stream << 20) | (uint32_t)tile;
-				st_dense++;
-			}
+			// ---- a burst (telegram, start-up transient): the whole block with the exact cascade, here.  Shared memory
+			// already belongs to the next block, so a thread reads its 512-byte row (and the 96 bytes in front of it) from
+			// global memory - L2, the block has just been through - and writes its 64 samples straight to dec.
+			const uint4 *row = reinterpret_cast<const uint4 *>(blk + (size_t)tid * 512);
+			const uint4 *halo = (tid == 0 && tile == 0) ? reinterpret_cast<const uint4 *>(hist) : row - 6;
+			uint32_t *dst = p.dec + gtile * kBlockDec + (size_t)tid * kOutPerThread;
+			unsigned long long trig64 = 0ull;
+			uint32_t prev = 0;
+			fir_cascade<WIDE, 4>([&](int q) { return __ldg(halo + q); }, [&](int q) { return __ldg(row + q); },
+					     [&](int m, int yi, int yq) {
+						     if (abs(yi) + abs(yq) > thresh_lo) trig64 |= 1ull << m;
+						     const uint32_t w = pack_iq(yi, yq);
+						     if (m & 1) *reinterpret_cast<uint2 *>(dst + m - 1) = make_uint2(prev, w);
+						     prev = w;
+					     });
+			FrontParams pk = p;
+			pk.keep_all = 2;   // the samples are in dec already
+			const uint32_t *blk_dec = p.dec + gtile * kBlockDec;
+			block_epilogue(pk, job, tile, [&](int m) -> uint32_t { return blk_dec[m]; }, es, trig64);
+			if (tid == 0) st_dense++;
 		} else {
 			if (nt) {
 				unsigned long long msk = cand64;
@@ -300,42 +362,61 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 			}
 			if (tid == 0 && is_last) ss.cand[total] = (uint16_t)(kBlockDec - 1);   // the lead-in sample of the next call
 			__syncthreads();
+			SCPROF(3);
 			// exact values with the reference arithmetic: lane k < 20 = stage-1 output 2m-18+k and stage-2 tap k
 			const int n_eval = total + (is_last ? 1 : 0);
 			const int t1 = WIDE ? kT1Wide[lane] : kT1Narrow[lane];
 			const float c2 = (float)t1 * (1.0f / 65536.0f);
 			const f2 c2p = pack2(c2, c2);
-			for (int i = warp; i < n_eval; i += kWarps) {
-				const int m = ss.cand[i];
-				int fi = 0, fq = 0;
-				if (lane < 20) {
-					const int o = 8 * m - 84 + 4 * lane;
-					const uint32_t w0 = sc_raw_word(smem, o), w1 = sc_raw_word(smem, o + 4), w2 = sc_raw_word(smem, o + 8),
-						       w3 = sc_raw_word(smem, o + 12);
-					f2 x[8];
-					x[0] = cvt_iq(w0, 0); x[1] = cvt_iq(w0, 1);
-					x[2] = cvt_iq(w1, 0); x[3] = cvt_iq(w1, 1);
-					x[4] = cvt_iq(w2, 0); x[5] = cvt_iq(w2, 1);
-					x[6] = cvt_iq(w3, 0); x[7] = cvt_iq(w3, 1);
-					const f2 y1 = stage1(x);
-					const f2 acc = fma2_rm(y1, c2p, pack2((float)kA2One, (float)kA2One));
-					uint32_t ai, aq;
-					unpack2(acc, ai, aq);
-					const int off = (kA2One - (1 << 23)) + kM1Mul * t1;
-					fi = (int)(ai - 0x4B000000u) - off;
-					fq = (int)(aq - 0x4B000000u) - off;
+			for (int i0 = warp; i0 < n_eval; i0 += 4 * kWarps) {
+				// (from global memory - L2 - because shared memory already belongs to the next block; bytes before a submit's
+				// first block are the carried history.)  The loads of four candidates go out together.
+				uint32_t w[4][4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int i = i0 + u * kWarps;
+					if (i < n_eval && lane < 20) {
+						const int o = 8 * (int)ss.cand[i] - 84 + 4 * lane;
+#pragma unroll
+						for (int q = 0; q < 4; q++) {
+							const int oq = o + 4 * q;
+							w[u][q] = (oq >= 0 || tile > 0) ? __ldg(reinterpret_cast<const uint32_t *>(blk + oq))
+										: *reinterpret_cast<const uint32_t *>(hist + kHistBytes + oq);
+						}
+					}
 				}
-				const int yi = __reduce_add_sync(0xffffffffu, fi), yq = __reduce_add_sync(0xffffffffu, fq);
-				if (lane == 0) {
-					ss.res_w[i] = pack_iq(yi, yq);
-					ss.res_p[i] = abs(yi) + abs(yq);
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int i = i0 + u * kWarps;
+					if (i >= n_eval) break;   // warp uniform
+					int fi = 0, fq = 0;
+					if (lane < 20) {
+						f2 x[8];
+						x[0] = cvt_iq(w[u][0], 0); x[1] = cvt_iq(w[u][0], 1);
+						x[2] = cvt_iq(w[u][1], 0); x[3] = cvt_iq(w[u][1], 1);
+						x[4] = cvt_iq(w[u][2], 0); x[5] = cvt_iq(w[u][2], 1);
+						x[6] = cvt_iq(w[u][3], 0); x[7] = cvt_iq(w[u][3], 1);
+						const f2 y1 = stage1(x);
+						const f2 acc = fma2_rm(y1, c2p, pack2((float)kA2One, (float)kA2One));
+						uint32_t ai, aq;
+						unpack2(acc, ai, aq);
+						const int off = (kA2One - (1 << 23)) + kM1Mul * t1;
+						fi = (int)(ai - 0x4B000000u) - off;
+						fq = (int)(aq - 0x4B000000u) - off;
+					}
+					const int yi = __reduce_add_sync(0xffffffffu, fi), yq = __reduce_add_sync(0xffffffffu, fq);
+					if (lane == 0) {
+						ss.res_w[i] = pack_iq(yi, yq);
+						ss.res_p[i] = abs(yi) + abs(yq);
+					}
 				}
 			}
 			__syncthreads();
+			SCPROF(4);
 			// events in order, descriptor
 			if (warp == 0) {
 				uint32_t *ev = p.events + gtile * kMaxEvt;
-				int nev = 0, first = -1, last = -1;
+				int nev = 0, last = -1;
 				for (int b0 = 0; b0 < total; b0 += 32) {
 					const int i = b0 + lane;
 					const bool valid = i < total;
@@ -343,11 +424,7 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 					const bool trig = valid && pw > thresh_lo;
 					const unsigned mask = __ballot_sync(0xffffffffu, trig);
 					if (trig) ev[nev + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)ss.cand[i] << 16) | (uint32_t)pw;
-					if (mask) {
-						const int fpos = ss.cand[b0 + __ffs(mask) - 1], lpos = ss.cand[b0 + 31 - __clz(mask)];
-						if (first < 0) first = fpos;
-						last = lpos;
-					}
+					if (mask) last = ss.cand[b0 + 31 - __clz(mask)];
 					nev += __popc(mask);
 				}
 				if (lane == 0) {
@@ -364,8 +441,18 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 			}
 		}
 		phase ^= 1u;
-		__syncthreads();   // shared memory and tensor memory are free for the next block
+		sc_fence_before();
+		__syncthreads();   // tensor memory is free for the next block's MMAs
+		sc_fence_after();
+		SCPROF(5);
+#ifdef TFR_SCREEN_PROFILE
+		prof[6]++;
+#endif
 	}
+#ifdef TFR_SCREEN_PROFILE
+	if (tid == 0)
+		for (int k = 0; k < 7; k++) atomicAdd(&g_scprof[k], (unsigned long long)prof[k]);
+#endif
 
 	if (tid == 0 && p.screen_stat) {
 		if (st_sparse) atomicAdd(p.screen_stat + 0, st_sparse);
@@ -384,10 +471,12 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 // ------------------------------------------------------------------------------------------------
 // decwin_kernel: the decimated samples the demodulators read - exact FIR (fir_exact.cuh, the arithmetic of frontend.cu)
 // over [start - 1, end] of every window of the demodulator with the longest timeout (its windows contain every other
-// demodulator's: same triggers, longer hold).  One CTA per window, a thread per aligned chunk of 16 outputs: 96 history
-// bytes + 128 bytes from global memory (L2: the block went through the screen a moment ago), 18 + 32 stage-1 outputs,
-// 16 stage-2 outputs, one 64-byte store.  Chunks are computed whole: samples outside the window are exact as well.
+// demodulator's: same triggers, longer hold).  A CTA takes kDwGroup consecutive windows at a time and spreads their
+// aligned chunks of 16 outputs over its threads: per chunk 96 history bytes + 128 bytes from global memory, 18 + 32
+// stage-1 outputs, 16 stage-2 outputs, one 64-byte store.  Chunks are computed whole: samples outside the window are
+// exact as well.
 // ------------------------------------------------------------------------------------------------
+constexpr int kDwGroup = 6;
 template <bool WIDE>
 __global__ void __launch_bounds__(64) decwin_kernel(const BackParams p, const uint8_t *hist_copy, uint32_t *dec_out)
 {
@@ -400,60 +489,38 @@ __global__ void __launch_bounds__(64) decwin_kernel(const BackParams p, const ui
 	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
 	uint32_t *out = dec_out + (size_t)job.dec_off * kBlockDec;
 	const uint8_t *hist = hist_copy + (size_t)stream * kHistBytes;
-	for (uint32_t w = blockIdx.x; w < n_win; w += gridDim.x) {
-		const WinEntry e = wl[w];
-		if (e.start >= call_len) break;
-		const uint32_t first = (e.start ? e.start - 1 : 0u) >> 4, last = min(e.end, call_len - 1) >> 4;
-		for (uint32_t c = first + threadIdx.x; c <= last; c += blockDim.x) {
+	for (uint32_t w0 = blockIdx.x * kDwGroup; w0 < n_win; w0 += gridDim.x * kDwGroup) {
+		// the group's chunk ranges [first, first + cnt), a chunk shared by two windows taken once
+		uint32_t first[kDwGroup], cum[kDwGroup + 1];
+		cum[0] = 0;
+		uint32_t covered = 0;   // first chunk not yet taken
+#pragma unroll
+		for (int k = 0; k < kDwGroup; k++) {
+			uint32_t f = 0, n = 0;
+			if (w0 + k < n_win) {
+				const WinEntry e = wl[w0 + k];
+				if (e.start < call_len) {
+					f = (e.start ? e.start - 1 : 0u) >> 4;
+					const uint32_t l = min(e.end, call_len - 1) >> 4;
+					if (k && f < covered) f = covered;
+					if (l >= f) n = l - f + 1;
+					covered = max(covered, l + 1);
+				}
+			}
+			first[k] = f;
+			cum[k + 1] = cum[k] + n;
+		}
+		for (uint32_t idx = threadIdx.x; idx < cum[kDwGroup]; idx += blockDim.x) {
+			uint32_t c = 0;
+#pragma unroll
+			for (int k = 0; k < kDwGroup; k++)
+				if (idx >= cum[k] && idx < cum[k + 1]) c = first[k] + (idx - cum[k]);
 			// raw bytes 128c-96 .. 128c+127: x[-48..-1] and x[0..63] relative to the chunk
 			const uint4 *row = reinterpret_cast<const uint4 *>(job.iq + (size_t)c * 128);
 			const uint4 *halo = c ? row - 6 : reinterpret_cast<const uint4 *>(hist);
-			f2 ring[32], xh[6];
-			{
-				f2 hx[48];
-#pragma unroll
-				for (int q = 0; q < 6; q++) {
-					const uint4 v = __ldg(halo + q);
-					hx[8 * q + 0] = cvt_iq(v.x, 0); hx[8 * q + 1] = cvt_iq(v.x, 1);
-					hx[8 * q + 2] = cvt_iq(v.y, 0); hx[8 * q + 3] = cvt_iq(v.y, 1);
-					hx[8 * q + 4] = cvt_iq(v.z, 0); hx[8 * q + 5] = cvt_iq(v.z, 1);
-					hx[8 * q + 6] = cvt_iq(v.w, 0); hx[8 * q + 7] = cvt_iq(v.w, 1);
-				}
-#pragma unroll
-				for (int j = -18; j < 0; j++) ring[(j + 32) & 31] = stage1(&hx[2 * j + 42]);
-#pragma unroll
-				for (int k = 0; k < 6; k++) xh[k] = hx[42 + k];
-			}
 			uint32_t o[16];
-#pragma unroll
-			for (int s = 0; s < 8; s++) {
-				const uint4 v = __ldg(row + s);
-				f2 x[14];
-#pragma unroll
-				for (int k = 0; k < 6; k++) x[k] = xh[k];
-				x[6] = cvt_iq(v.x, 0); x[7] = cvt_iq(v.x, 1);
-				x[8] = cvt_iq(v.y, 0); x[9] = cvt_iq(v.y, 1);
-				x[10] = cvt_iq(v.z, 0); x[11] = cvt_iq(v.z, 1);
-				x[12] = cvt_iq(v.w, 0); x[13] = cvt_iq(v.w, 1);
-#pragma unroll
-				for (int jj = 0; jj < 4; jj++) ring[(4 * s + jj) & 31] = stage1(&x[2 * jj]);
-#pragma unroll
-				for (int k = 0; k < 6; k++) xh[k] = x[8 + k];
-#pragma unroll
-				for (int mm = 0; mm < 2; mm++) {
-					const int m = 2 * s + mm;
-					f2 a = pack2((float)kA2a, (float)kA2a), b = pack2((float)kA2b, (float)kA2b);
-#pragma unroll
-					for (int n = 0; n < 10; n++) {
-						a = fma2_rm(ring[(2 * m - 18 + n + 32) & 31], c2pair<WIDE>(n), a);
-						b = fma2_rm(ring[(2 * m - 8 + n + 32) & 31], c2pair<WIDE>(n + 10), b);
-					}
-					uint32_t ai, aq, bi, bq;
-					unpack2(a, ai, aq);
-					unpack2(b, bi, bq);
-					o[m] = pack_iq((int)(ai + bi - y2_bias(WIDE)), (int)(aq + bq - y2_bias(WIDE)));
-				}
-			}
+			fir_cascade<WIDE, 1>([&](int q) { return __ldg(halo + q); }, [&](int q) { return __ldg(row + q); },
+					     [&](int m, int yi, int yq) { o[m] = pack_iq(yi, yq); });
 			uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)c * 16);
 #pragma unroll
 			for (int q = 0; q < 4; q++) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
@@ -556,6 +623,20 @@ cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, c
 	const int items = p.n_tiles * p.n_streams;
 	if (items <= 0) return cudaSuccess;
 	const int grid = items < n_ctas ? items : n_ctas;
+#ifdef TFR_SCREEN_PROFILE
+	{
+		static int calls = 0;
+		if (++calls % 32 == 0) {
+			unsigned long long r[8], z[8] = { 0 };
+			cudaDeviceSynchronize();
+			cudaMemcpyFromSymbol(r, g_scprof, sizeof(r));
+			cudaMemcpyToSymbol(g_scprof, z, sizeof(z));
+			const double n = (double)(r[6] ? r[6] : 1);
+			fprintf(stderr, "[scprof] %llu blocks, cycles per block (thread 0): load wait %.0f, MMAs %.0f, readback %.0f, candidate list %.0f, evaluation %.0f, epilogue+sync %.0f\n",
+				r[6], r[0] / n, r[1] / n, r[2] / n, r[3] / n, r[4] / n, r[5] / n);
+		}
+	}
+#endif
 	if (wide)
 		frontend_screen_kernel<true><<<grid, kThreads, kScreenSmem, stream>>>(p);
 	else
@@ -566,7 +647,7 @@ cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, c
 cudaError_t launch_decwin(const BackParams &p, int wide, const uint8_t *hist_copy, uint32_t *dec_out, cudaStream_t s)
 {
 	if (p.max_blocks <= 0) return cudaSuccess;
-	int gx = p.max_blocks;   // about one window per block
+	int gx = (p.max_blocks + kDwGroup - 1) / kDwGroup;   // about one window per block
 	gx = gx < 1 ? 1 : (gx > 4096 ? 4096 : gx);
 	if (wide)
 		decwin_kernel<true><<<dim3(gx, p.n_streams), 64, 0, s>>>(p, hist_copy, dec_out);

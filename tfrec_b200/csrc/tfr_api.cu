@@ -21,7 +21,6 @@ bool frontend_tc_available();
 int frontend_tc_encode(const void *iq, uint32_t n_blocks, void *out);
 cudaError_t launch_save_history(const StreamJob *jobs, StreamState *st, int n_streams, int decimated, cudaStream_t stream);
 cudaError_t launch_frontend_i16(const FrontParams &p, int n_streams, cudaStream_t stream);
-cudaError_t launch_frontend_list(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream);
 cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, cudaStream_t stream);
 cudaError_t launch_decwin(const BackParams &p, int wide, const uint8_t *hist_copy, uint32_t *dec_out, cudaStream_t s);
 void screen_build_consts(int wide, uint8_t *blob, int *shift, int *slack);
@@ -104,9 +103,7 @@ struct tfr_handle {
 		StreamJob *d_jobs = nullptr;
 		uint8_t *d_tmaps = nullptr;              // [stream][2] CUtensorMap of the call's submits (frontend_tc_kernel)
 		std::vector<uint8_t> h_tmaps;            // host copy (stays until the slot's next call)
-		uint32_t *d_dense_list = nullptr;        // screening front-end: blocks handed to the dense kernel, per chunk launch
-		size_t cap_dense = 0;
-		uint32_t *d_dense_cnt = nullptr;         // [kFrontChunks]
+		uint32_t *d_work_ctr = nullptr;          // [kFrontChunks] screening front-end: work counter of every chunk launch
 		uint8_t *d_hist_copy = nullptr;          // [stream][kHistBytes]: the FIR history the call started from
 		cudaEvent_t raw_done = nullptr;          // decwin_kernel has read the call's raw bytes (the input arena may be rewritten)
 		TileDesc *d_tiles = nullptr;
@@ -216,6 +213,19 @@ static void build_config(const tfr_config &c, DevConfig &d)
 		q.timeout = timeout;
 		if (lp) q.lp = coef_from_bits(lp);
 		if (lp_avg) q.lp_avg = coef_from_bits(lp_avg);
+		{
+			// tfa2.cpp:391-398 in integers: (double)tdiff > spb/4  <=>  tdiff >= floor(spb/4) + 1;  (double)tdiff < 32*spb  <=>
+			// tdiff <= ceil(32*spb) - 1;  numbits by table, computed here with the very operations the device used
+			const volatile double spb_lo = spb * 0.25, spb_hi = 32.0 * spb, spb_half = spb * 0.5;
+			q.td_lo = (int)floor(spb_lo) + 1;
+			q.td_hi = (int)ceil(spb_hi) - 1;
+			for (int bd = 0; bd < kNbitsTab; bd++) {
+				const volatile double a = (double)bd + spb_half;
+				const volatile double r = a / spb;
+				const int nb = (int)r;
+				q.nbits[bd] = (uint8_t)(nb > 255 ? 255 : nb);
+			}
+		}
 		d.t_max = std::max(d.t_max, timeout);
 	};
 	if (c.types & (1 << TFR_TFA_1)) add(K_TFA1, TFR_TFA_1, 10.0, 400, nullptr, nullptr);   // 40*BITPERIOD, tfa1.cpp:34,148
@@ -264,7 +274,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	cudaFree(h->d_frames); cudaFree(h->d_records);
 	cudaFree(h->d_screen_consts); cudaFree(h->d_screen_stat); cudaFree(h->d_screen_dbg);
 	for (auto &sl : h->slot) {
-		cudaFree(sl.d_dense_list); cudaFree(sl.d_dense_cnt); cudaFree(sl.d_hist_copy);
+		cudaFree(sl.d_work_ctr); cudaFree(sl.d_hist_copy);
 		if (sl.raw_done) cudaEventDestroy(sl.raw_done);
 		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
@@ -397,8 +407,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaMalloc(&sl.d_jobs, sizeof(StreamJob) * cfg->n_streams));
 		CUH(cudaMalloc(&sl.d_tmaps, (size_t)256 * cfg->n_streams));
 		CUH(cudaEventCreateWithFlags(&sl.raw_done, cudaEventDisableTiming));
-		CUH(cudaMalloc(&sl.d_dense_cnt, sizeof(uint32_t) * kFrontChunks));
-		CUH(cudaMemset(sl.d_dense_cnt, 0, sizeof(uint32_t) * kFrontChunks));
+		CUH(cudaMalloc(&sl.d_work_ctr, sizeof(uint32_t) * kFrontChunks));
+		CUH(cudaMemset(sl.d_work_ctr, 0, sizeof(uint32_t) * kFrontChunks));
 		CUH(cudaMalloc(&sl.d_hist_copy, (size_t)kHistBytes * cfg->n_streams));
 		CUH(cudaMemset(sl.d_hist_copy, 128, (size_t)kHistBytes * cfg->n_streams));
 		sl.h_tmaps.assign((size_t)256 * cfg->n_streams + 64, 0);
@@ -666,27 +676,12 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			CU(cudaMemsetAsync(h->d_screen_dbg, 0, total * (size_t)kBlockDec * 2 * sizeof(int32_t), sf));
 			fp.screen_dbg = h->d_screen_dbg;
 		}
-		CU(cudaMemsetAsync(sl.d_dense_cnt, 0, sizeof(uint32_t) * kFrontChunks, sf));
-		// a chunk launch covers ceil(max_blocks / chunks) blocks of every stream: room for every one of them, per chunk
-		const size_t need = ((size_t)max_blocks + 2 * kFrontChunks) * (size_t)ns;
-		if (need > sl.cap_dense) {
-			rc = sync_all(h);
-			if (rc) return rc;
-			cudaFree(sl.d_dense_list);
-			sl.d_dense_list = nullptr;
-			sl.cap_dense = 0;
-			CU(cudaMalloc(&sl.d_dense_list, need * sizeof(uint32_t)));
-			sl.cap_dense = need;
-		}
+		CU(cudaMemsetAsync(sl.d_work_ctr, 0, sizeof(uint32_t) * kFrontChunks, sf));
 	}
-	// one chunk of blocks through the screen: the screening kernel, then the dense kernel over the blocks it handed back
+	// one chunk of blocks through the screen: persistent CTAs, two per SM, fetching blocks from the chunk's counter
 	auto launch_screen = [&](FrontParams q, int chunk, cudaStream_t st) -> cudaError_t {
-		q.dense_cnt = sl.d_dense_cnt + chunk;
-		q.dense_list = sl.d_dense_list + (size_t)q.tile0 * ns + (size_t)chunk * ns;
-		cudaError_t e = launch_frontend_screen(q, h->dcfg.filter, 2 * h->n_sms, st);
-		if (e != cudaSuccess) return e;
-		const int items = q.n_tiles * ns;
-		return launch_frontend_list(q, h->dcfg.filter, std::min(items, 3 * h->n_sms), st);
+		q.work_ctr = sl.d_work_ctr + chunk;
+		return launch_frontend_screen(q, h->dcfg.filter, 2 * h->n_sms, st);
 	};
 	auto launch_fe = [&](const FrontParams &q, cudaStream_t st) {
 		if (decimated) return launch_frontend_i16(q, ns, st);

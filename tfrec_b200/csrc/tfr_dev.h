@@ -39,7 +39,13 @@ struct DemodCfg {
 	double spb;          // samples per bit at 384 kS/s (main.cpp:186,194,202,217)
 	BiquadCoef lp;       // tfa2: 0.5/spb (tfa2.cpp:321); whb pulse filter 2.0/spb (whb.cpp:610)
 	BiquadCoef lp_avg;   // whb: 0.0025/spb (whb.cpp:611)
+	// TFA_2 family, the edge arithmetic of tfa2.cpp:391-398 as integers (built on the host with the same IEEE doubles):
+	// `tdiff>spb/4 && tdiff<32*spb` is td_lo <= tdiff <= td_hi, and numbits = (bit_diff + est_spb/2)/est_spb, truncated,
+	// is nbits[bit_diff] (bit_diff = tdiff/2 <= td_hi/2 < kNbitsTab)
+	int32_t td_lo, td_hi;
+	uint8_t nbits[704];
 };
+constexpr int kNbitsTab = 704;
 
 struct DevConfig {
 	int32_t n_demods;
@@ -237,8 +243,7 @@ struct FrontParams {
 	int screen_shift;      // q: screen value = linear filter output * 2^q
 	int screen_slack;      // what a sample's true |I|+|Q| can exceed its screen value by, in output units (rounded up)
 	int n_streams;
-	uint32_t *dense_list;  // blocks handed to the dense kernel: stream << 20 | block
-	uint32_t *dense_cnt;
+	uint32_t *work_ctr;    // the launch's work counter: CTAs fetch (stream, block) items from it
 	uint8_t *hist_copy;    // [stream][kHistBytes]: the FIR history the call started from (the window kernel runs after save_history)
 	int32_t *screen_dbg;   // debug (TFR_FLAG_TAPS): [gtile][8192][2] screen values of I and Q, null otherwise
 	uint32_t *screen_stat; // [0] blocks screened sparse, [1] blocks handed back dense, [2] candidates checked, [3] of them true
