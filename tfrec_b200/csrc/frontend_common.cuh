@@ -71,6 +71,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
 	asm volatile(
@@ -105,9 +109,13 @@ struct EpiShared {
 	int nseg, ntrig;
 	int warp_cnt[kWarps];
 };
-template <class Smp>
+struct CtaSync {
+	__device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// `sync` is the barrier of the kThreads threads that call (the whole CTA, unless the kernel has other warps besides)
+template <class Smp, class Sync = CtaSync>
 __device__ __forceinline__ void block_epilogue(const FrontParams &p, const StreamJob &job, int tile, const Smp &smp, EpiShared &es,
-					       unsigned long long trig64)
+					       unsigned long long trig64, const Sync &sync = Sync())
 {
 	const int tid = threadIdx.x;
 	const uint32_t trig[2] = { (uint32_t)trig64, (uint32_t)(trig64 >> 32) };
@@ -128,7 +136,7 @@ __device__ __forceinline__ void block_epilogue(const FrontParams &p, const Strea
 			if ((tid & 31) >= d) incl += o;
 		}
 		if ((tid & 31) == 31) es.warp_cnt[tid >> 5] = incl;
-		__syncthreads();
+		sync();
 		int base = incl - nt;
 		for (int w = 0; w < (tid >> 5); w++) base += es.warp_cnt[w];
 		if (tid == kThreads - 1) es.ntrig = base + nt;
@@ -212,7 +220,7 @@ __device__ __forceinline__ void block_epilogue(const FrontParams &p, const Strea
 			es.seg_end[tid] = endq + p.t_max;   // exclusive; may exceed the block -> carry_out
 		}
 	}
-	__syncthreads();
+	sync();
 
 	// ------------------------------------------------------------------ sparse store + descriptor
 	const size_t gtile = (size_t)job.dec_off + tile;

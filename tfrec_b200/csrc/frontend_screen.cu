@@ -29,7 +29,9 @@
 // up, column 384) through the same band matrix shifted by 16 / 32 / 48 columns.  The first MMA of a block multiplies a
 // constant A operand with a constant B: it initialises all 256 columns and subtracts the centre.
 //
-// One CTA = 128 threads, persistent over blocks, 256 columns of tensor memory, 2 CTAs per SM.
+// One CTA = four screening warps + one producer warp (work items, TMA, MMAs), persistent over blocks, 256 columns of
+// tensor memory, 2 CTAs per SM.  The producer runs one block ahead: while the screeners evaluate block i's candidates,
+// the MMAs of block i+1 run and the boxes of block i+2 are in flight.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -57,8 +59,8 @@ constexpr int kCandMax = 48;                      // more candidates than this i
 constexpr int kBox = 128 * 128;                   // one TMA box: 128 rows x 128 bytes
 constexpr int kOffHaloBox = 4 * kBox;             // box 4: the last 128 bytes of the row before every row
 constexpr int kOffConsts = 5 * kBox;
-constexpr int kOffBarS = kOffConsts + kScBytes;   // 5 box barriers + 1 MMA barrier
-constexpr int kOffTmemS = kOffBarS + 6 * 8;
+constexpr int kOffBarS = kOffConsts + kScBytes;   // mbarriers: 5 TMA boxes, MMAs done, item published, tensor memory read out
+constexpr int kOffTmemS = kOffBarS + 8 * 8;
 constexpr int kScreenSmem = kOffTmemS + 16;       // 92,480 B -> 2 CTAs / SM
 constexpr uint32_t kScreenCols = 256;
 
@@ -144,11 +146,18 @@ struct ScreenShared {
 	uint32_t res_w[kCandMax + 2];
 	int res_p[kCandMax + 2];
 	int warp_cnt[kWarps];
-	int next[2];   // the CTA's next work item, fetched by thread 0 one block ahead (double buffered)
+	int item[2];   // the work item of round r (slot r & 1), published by the producer; n_items ends the CTA
+};
+
+constexpr int kScreenThreads = kThreads + 32;   // four screening warps (one per tensor-memory lane quadrant) + the producer warp
+// the screening warps' own barrier (the producer warp never joins)
+__device__ __forceinline__ void sc_sync_screeners() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+struct ScreenersSync {
+	__device__ __forceinline__ void operator()() const { sc_sync_screeners(); }
 };
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const FrontParams p)
+__global__ void __launch_bounds__(kScreenThreads, 2) frontend_screen_kernel(const FrontParams p)
 {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	__shared__ ScreenShared ss;
@@ -156,309 +165,329 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_screen_kernel(const Fron
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t sbase = smem_u32(smem);
-	const uint32_t bar_box = sbase + kOffBarS, bar_mma = bar_box + 40;
+	// mbarriers: 5 TMA boxes, MMAs done, item published, tensor memory read out
+	const uint32_t bar_box = sbase + kOffBarS, bar_mma = bar_box + 40, bar_item = bar_box + 48, bar_tfree = bar_box + 56;
 
 	// ---- once per CTA: constants, barriers, tensor memory
 	{
 		const uint4 *src = reinterpret_cast<const uint4 *>(p.screen_consts);
 		uint4 *dst = reinterpret_cast<uint4 *>(smem + kOffConsts);
-		for (int k = tid; k < kScBytes / 16; k += kThreads) dst[k] = src[k];
+		for (int k = tid; k < kScBytes / 16; k += kScreenThreads) dst[k] = src[k];
 	}
-	if (tid == 0)
-		for (int q = 0; q < 6; q++) mbar_init(bar_box + 8 * q, 1);
+	if (tid == 0) {
+		for (int q = 0; q < 7; q++) mbar_init(bar_box + 8 * q, 1);
+		mbar_init(bar_tfree, kWarps);
+	}
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	if (warp == 0) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemS), "n"(kScreenCols) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
-
-	const uint64_t d_band = sc_desc(sbase + kOffConsts + kScBand, 1024, 128, kScNone);
-	const uint64_t d_bconst = sc_desc(sbase + kOffConsts + kScConst, 4096, 128, kScNone);
-	const uint64_t d_ac = sc_desc(sbase + kOffConsts + kScAc, 128, 0, kScNone);
-
-	const int n_items = p.n_tiles * p.n_streams;
-	uint32_t phase = 0;
-	uint32_t st_sparse = 0, st_dense = 0, st_cand = 0, st_true = 0;   // thread 0's tallies
-
-	// Work items (stream, block) are handed out by a counter, one block ahead (thread 0): a burst block done in place
-	// holds its CTA ten times as long as a screened one.  Streams may be shorter than the launch's tile range.
-	auto fetch_item = [&]() {
-		for (;;) {
-			const int it = (int)atomicAdd(p.work_ctr, 1u);
-			if (it >= n_items) return n_items;
-			const int s_ = it / p.n_tiles;
-			if (p.tile0 + (it - s_ * p.n_tiles) < (int)p.jobs[s_].n_blocks) return it;
-		}
-	};
-	// the five TMA boxes of a block (thread 0): the loads of block i+1 go out as soon as the MMAs of block i have
-	// consumed shared memory, and fly while the threads screen block i
-	auto issue_loads = [&](int item) {
-		const int s_ = item / p.n_tiles, t_ = p.tile0 + (item - s_ * p.n_tiles);
-		const uint8_t *tm = reinterpret_cast<const uint8_t *>(p.tmaps) + (size_t)s_ * 256;
-		asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
-		mbar_expect_tx(bar_box + 32, kBox);
-		sc_tma_2d(sbase + kOffHaloBox, tm, 384, t_ * 128 - 1, bar_box + 32);
-#pragma unroll
-		for (int q = 0; q < 4; q++) {
-			mbar_expect_tx(bar_box + 8 * q, kBox);
-			sc_tma_2d(sbase + q * kBox, tm, 128 * q, t_ * 128, bar_box + 8 * q);
-		}
-	};
-	if (tid == 0) {
-		const int it = fetch_item();
-		ss.next[0] = it;
-		if (it < n_items) issue_loads(it);
-	}
 	sc_fence_before();
 	__syncthreads();
 	sc_fence_after();
 	const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + kOffTmemS);
-	const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+	const int n_items = p.n_tiles * p.n_streams;
 
-#ifdef TFR_SCREEN_PROFILE
-	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, pt = clock64();
-#endif
-	for (int round = 0;; round++) {
-		const int item = ss.next[round & 1];
-		if (item >= n_items) break;
-		const int stream = item / p.n_tiles;
-		const int tile = p.tile0 + (item - stream * p.n_tiles);
-		const StreamJob job = p.jobs[stream];
-		StreamState *st = p.st + stream;
-		const size_t gtile = (size_t)job.dec_off + tile;
-		const uint8_t *blk = job.iq + (size_t)tile * kBlockBytes;
-		const uint8_t *hist = st->hist[st->hist_parity & 1];
-
-		// ---- MMAs, one thread
-		if (tid == 0) {
-			// all 256 columns = -(128 * sum T16 + centre), in planes: needs nothing of the block, goes first
-			sc_mma(tmem, d_ac, d_bconst, screen_idesc(256), 0u);
-			mbar_wait(bar_box + 32, phase);
-			if (tile == 0) {
-				// nothing in front of the submit (TMA filled row -1 with zeros): the carried history, 96 bytes in front of
-				// row 0.  The same bytes go to the slot's copy for decwin_kernel, which runs after save_history_kernel.
-				const uint4 *hs = reinterpret_cast<const uint4 *>(hist);
-				uint4 *hd = reinterpret_cast<uint4 *>(smem + kOffHaloBox + 32);
-				uint4 *hc = reinterpret_cast<uint4 *>(p.hist_copy + (size_t)stream * kHistBytes);
-#pragma unroll
-				for (int k = 0; k < 6; k++) {
-					const uint4 v = hs[k];
-					hd[k] = v;
-					hc[k] = v;
+	if (warp == kWarps) {
+		// =====================================================================================================
+		// producer (one thread): work items, TMA loads, MMAs.  Round r: publish the item, wait until the screeners have
+		// read round r-1 out of tensor memory, run the MMAs, and as soon as they have consumed shared memory send the
+		// next block's loads - which fly while the screeners evaluate round r's candidates.
+		// =====================================================================================================
+		if (lane == 0) {
+			const uint64_t d_band = sc_desc(sbase + kOffConsts + kScBand, 1024, 128, kScNone);
+			const uint64_t d_bconst = sc_desc(sbase + kOffConsts + kScConst, 4096, 128, kScNone);
+			const uint64_t d_ac = sc_desc(sbase + kOffConsts + kScAc, 128, 0, kScNone);
+			// Work items (stream, block) are handed out by a counter: a burst block done in place holds its CTA ten
+			// times as long as a screened one.  Streams may be shorter than the launch's tile range.
+			auto valid_item = [&](int it) {
+				if (it >= n_items) return true;
+				const int s_ = it / p.n_tiles;
+				return p.tile0 + (it - s_ * p.n_tiles) < (int)p.jobs[s_].n_blocks;
+			};
+			int fenced_stream = -1;
+			auto issue_loads = [&](int it) {
+				const int s_ = it / p.n_tiles, t_ = p.tile0 + (it - s_ * p.n_tiles);
+				const uint8_t *tm = reinterpret_cast<const uint8_t *>(p.tmaps) + (size_t)s_ * 256;
+				if (s_ != fenced_stream) {
+					asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+					fenced_stream = s_;
 				}
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			}
-			mbar_wait(bar_box, phase);
-			sc_fence_after();
-			SCPROF(0);
-			// the row before: byte slices -96.., -64.., -32.. reach outputs 0..2, 0..6, 0..10
+				mbar_expect_tx(bar_box + 32, kBox);
+				sc_tma_2d(sbase + kOffHaloBox, tm, 384, t_ * 128 - 1, bar_box + 32);
 #pragma unroll
-			for (int s = 1; s <= 3; s++) {
-				const uint64_t da = sc_desc(sbase + kOffHaloBox + 32 * s, 16, 1024, kScSw128);
-				const uint64_t db = sc_desc(sbase + kOffConsts + kScBand + (64 - 16 * s) * 16, 1024, 128, kScNone);
-				sc_mma(tmem, da, db, screen_idesc(16 * s), 1u);
-			}
-#pragma unroll
-			for (int s = 0; s < 16; s++) {
-				if (s && (s & 3) == 0) {
-					mbar_wait(bar_box + 8 * (s >> 2), phase);
-					sc_fence_after();
-				}
-				const uint64_t da = sc_desc(sbase + (s >> 2) * kBox + (s & 3) * 32, 16, 1024, kScSw128);
-				const uint32_t n = (s <= 12) ? 64u : (uint32_t)(256 - 16 * s);
-				sc_mma(tmem + 16 * s, da, d_band, screen_idesc(n), 1u);
-			}
-			sc_commit(bar_mma);
-			// shared memory is free once the MMAs are done: the next block's boxes
-			const int nx = fetch_item();
-			ss.next[(round + 1) & 1] = nx;
-			mbar_wait(bar_mma, phase);
-			if (nx < n_items) issue_loads(nx);
-			SCPROF(1);
-		}
-		__syncwarp();
-
-		int thresh_lo = st->thresh;
-		if (st->thresh_mode) thresh_lo = p.margin ? thresh_lo - p.margin : st->spec_lo;
-		const int lim = thresh_lo - p.screen_slack;
-		const int thr = (lim < 0) ? -1 : (lim << p.screen_shift);
-
-		// ---- screen values out of tensor memory: 16 columns = 4 outputs x (I lo, I hi, Q lo, Q hi)
-		mbar_wait(bar_mma, phase);
-		sc_fence_after();
-		unsigned long long cand64 = 0ull;
-		int32_t *dbg = p.screen_dbg ? p.screen_dbg + (gtile * kBlockDec + (size_t)tid * kOutPerThread) * 2 : nullptr;
-		{
-			// two loads of 32 columns (8 outputs) in flight (64 columns each fill the register file: 254 registers, and the
-			// back-end kernels of the previous call no longer fit beside the two screening CTAs of an SM)
-			uint32_t va[32], vb[32];
-			auto screen8 = [&](const uint32_t (&v)[32], int j0) {
-#pragma unroll
-				for (int k = 0; k < 8; k++) {
-					const int ci = (int)(v[4 * k + 1] << 8) + (int)v[4 * k], cq = (int)(v[4 * k + 3] << 8) + (int)v[4 * k + 2];
-					if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (j0 + k);
-					if (dbg) { dbg[2 * (j0 + k)] = ci; dbg[2 * (j0 + k) + 1] = cq; }
+				for (int q = 0; q < 4; q++) {
+					mbar_expect_tx(bar_box + 8 * q, kBox);
+					sc_tma_2d(sbase + q * kBox, tm, 128 * q, t_ * 128, bar_box + 8 * q);
 				}
 			};
-			sc_ld32(tlane, va);
-			sc_ld32(tlane + 32, vb);
-#pragma unroll 1
-			for (int g = 0; g < 4; g++) {
-				sc_wait_ld_all();   // both loads have landed
-				screen8(va, 16 * g);
-				if (g < 3) sc_ld32(tlane + 64 * (g + 1), va);
-				screen8(vb, 16 * g + 8);
-				if (g < 3) sc_ld32(tlane + 64 * (g + 1) + 32, vb);
+			int item = (int)atomicAdd(p.work_ctr, 1u);
+			while (!valid_item(item)) item = (int)atomicAdd(p.work_ctr, 1u);
+			if (item < n_items) issue_loads(item);
+			for (int round = 0;; round++) {
+				const uint32_t ph = (uint32_t)(round & 1);
+				// the counter's answer for the round after this one is on its way while the MMAs run
+				int nx = (item < n_items) ? (int)atomicAdd(p.work_ctr, 1u) : n_items;
+				if (round) {
+					mbar_wait(bar_tfree, ph ^ 1u);   // round - 1 has been read out of tensor memory
+					sc_fence_after();
+				}
+				// (published only now: the screeners are past round - 1's item, so the barrier never runs two phases ahead of
+				// a waiter - a parity wait cannot tell phase r from phase r + 2)
+				ss.item[round & 1] = item < n_items ? item : n_items;
+				mbar_arrive(bar_item);
+				if (item >= n_items) break;
+				const int stream = item / p.n_tiles;
+				const int tile = p.tile0 + (item - stream * p.n_tiles);
+				// all 256 columns = -(128 * sum T16 + centre), in planes: needs nothing of the block, goes first
+				sc_mma(tmem, d_ac, d_bconst, screen_idesc(256), 0u);
+				mbar_wait(bar_box + 32, ph);
+				if (tile == 0) {
+					// nothing in front of the submit (TMA filled row -1 with zeros): the carried history, 96 bytes in front
+					// of row 0.  The same bytes go to the slot's copy for decwin_kernel, which runs after save_history_kernel.
+					StreamState *st = p.st + stream;
+					const uint4 *hs = reinterpret_cast<const uint4 *>(st->hist[st->hist_parity & 1]);
+					uint4 *hd = reinterpret_cast<uint4 *>(smem + kOffHaloBox + 32);
+					uint4 *hc = reinterpret_cast<uint4 *>(p.hist_copy + (size_t)stream * kHistBytes);
+#pragma unroll
+					for (int k = 0; k < 6; k++) {
+						const uint4 v = hs[k];
+						hd[k] = v;
+						hc[k] = v;
+					}
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				}
+				mbar_wait(bar_box, ph);
+				sc_fence_after();
+				// the row before: byte slices -96.., -64.., -32.. reach outputs 0..2, 0..6, 0..10
+#pragma unroll
+				for (int s = 1; s <= 3; s++) {
+					const uint64_t da = sc_desc(sbase + kOffHaloBox + 32 * s, 16, 1024, kScSw128);
+					const uint64_t db = sc_desc(sbase + kOffConsts + kScBand + (64 - 16 * s) * 16, 1024, 128, kScNone);
+					sc_mma(tmem, da, db, screen_idesc(16 * s), 1u);
+				}
+#pragma unroll
+				for (int s = 0; s < 16; s++) {
+					if (s && (s & 3) == 0) {
+						mbar_wait(bar_box + 8 * (s >> 2), ph);
+						sc_fence_after();
+					}
+					const uint64_t da = sc_desc(sbase + (s >> 2) * kBox + (s & 3) * 32, 16, 1024, kScSw128);
+					const uint32_t n = (s <= 12) ? 64u : (uint32_t)(256 - 16 * s);
+					sc_mma(tmem + 16 * s, da, d_band, screen_idesc(n), 1u);
+				}
+				sc_commit(bar_mma);
+				while (!valid_item(nx)) nx = (int)atomicAdd(p.work_ctr, 1u);
+				// shared memory is free once the MMAs are done: the next block's boxes
+				mbar_wait(bar_mma, ph);
+				if (nx < n_items) issue_loads(nx);
+				item = nx;
 			}
 		}
+	} else {
+		// =====================================================================================================
+		// screeners (four warps, thread t = row t of the block = tensor-memory lane t)
+		// =====================================================================================================
+		const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+		uint32_t st_sparse = 0, st_dense = 0, st_cand = 0, st_true = 0;   // thread 0's tallies
+#ifdef TFR_SCREEN_PROFILE
+		long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, pt = clock64();
+#endif
+		for (int round = 0;; round++) {
+			const uint32_t ph = (uint32_t)(round & 1);
+			mbar_wait(bar_item, ph);
+			const int item = ss.item[round & 1];
+			if (item >= n_items) break;
+			const int stream = item / p.n_tiles;
+			const int tile = p.tile0 + (item - stream * p.n_tiles);
+			const StreamJob job = p.jobs[stream];
+			StreamState *st = p.st + stream;
+			const size_t gtile = (size_t)job.dec_off + tile;
+			const uint8_t *blk = job.iq + (size_t)tile * kBlockBytes;
+			const uint8_t *hist = st->hist[st->hist_parity & 1];
+			int thresh_lo = st->thresh;
+			if (st->thresh_mode) thresh_lo = p.margin ? thresh_lo - p.margin : st->spec_lo;
+			const int lim = thresh_lo - p.screen_slack;
+			const int thr = (lim < 0) ? -1 : (lim << p.screen_shift);
 
-		SCPROF(2);
-		// ---- ordered candidate list
-		const int nt = __popcll(cand64);
-		int incl = nt;
+			// ---- screen values out of tensor memory: 32 columns = 8 outputs x (I lo, I hi, Q lo, Q hi)
+			mbar_wait(bar_mma, ph);
+			sc_fence_after();
+			SCPROF(0);
+			unsigned long long cand64 = 0ull;
+			int32_t *dbg = p.screen_dbg ? p.screen_dbg + (gtile * kBlockDec + (size_t)tid * kOutPerThread) * 2 : nullptr;
+			{
+				// two loads of 32 columns in flight (64 columns each fill the register file: 254 registers, and the back-end
+				// kernels of the previous call no longer fit beside the two screening CTAs of an SM)
+				uint32_t va[32], vb[32];
+				auto screen8 = [&](const uint32_t (&v)[32], int j0) {
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const int o = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= d) incl += o;
-		}
-		if (lane == 31) ss.warp_cnt[warp] = incl;
-		sc_fence_before();
-		__syncthreads();   // (also: every warp has pulled its tensor-memory columns)
-		int base = incl - nt;
-		for (int w = 0; w < warp; w++) base += ss.warp_cnt[w];
-		const int total = ss.warp_cnt[0] + ss.warp_cnt[1] + ss.warp_cnt[2] + ss.warp_cnt[3];
-		const bool is_last = (tile == (int)job.n_blocks - 1);
-
-		if (total > kCandMax) {
-			// ---- a burst (telegram, start-up transient): the whole block with the exact cascade, here.  Shared memory
-			// already belongs to the next block, so a thread reads its 512-byte row (and the 96 bytes in front of it) from
-			// global memory - L2, the block has just been through - and writes its 64 samples straight to dec.
-			const uint4 *row = reinterpret_cast<const uint4 *>(blk + (size_t)tid * 512);
-			const uint4 *halo = (tid == 0 && tile == 0) ? reinterpret_cast<const uint4 *>(hist) : row - 6;
-			uint32_t *dst = p.dec + gtile * kBlockDec + (size_t)tid * kOutPerThread;
-			unsigned long long trig64 = 0ull;
-			uint32_t prev = 0;
-			fir_cascade<WIDE, 4>([&](int q) { return __ldg(halo + q); }, [&](int q) { return __ldg(row + q); },
-					     [&](int m, int yi, int yq) {
-						     if (abs(yi) + abs(yq) > thresh_lo) trig64 |= 1ull << m;
-						     const uint32_t w = pack_iq(yi, yq);
-						     if (m & 1) *reinterpret_cast<uint2 *>(dst + m - 1) = make_uint2(prev, w);
-						     prev = w;
-					     });
-			FrontParams pk = p;
-			pk.keep_all = 2;   // the samples are in dec already
-			const uint32_t *blk_dec = p.dec + gtile * kBlockDec;
-			block_epilogue(pk, job, tile, [&](int m) -> uint32_t { return blk_dec[m]; }, es, trig64);
-			if (tid == 0) st_dense++;
-		} else {
-			if (nt) {
-				unsigned long long msk = cand64;
-				int k = base;
-				while (msk) {
-					const int b = __ffsll((long long)msk) - 1;
-					msk &= msk - 1;
-					ss.cand[k++] = (uint16_t)(tid * kOutPerThread + b);
+					for (int k = 0; k < 8; k++) {
+						const int ci = (int)(v[4 * k + 1] << 8) + (int)v[4 * k], cq = (int)(v[4 * k + 3] << 8) + (int)v[4 * k + 2];
+						if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (j0 + k);
+						if (dbg) { dbg[2 * (j0 + k)] = ci; dbg[2 * (j0 + k) + 1] = cq; }
+					}
+				};
+				sc_ld32(tlane, va);
+				sc_ld32(tlane + 32, vb);
+#pragma unroll 1
+				for (int g = 0; g < 4; g++) {
+					sc_wait_ld_all();   // both loads have landed
+					screen8(va, 16 * g);
+					if (g < 3) sc_ld32(tlane + 64 * (g + 1), va);
+					screen8(vb, 16 * g + 8);
+					if (g < 3) sc_ld32(tlane + 64 * (g + 1) + 32, vb);
 				}
 			}
-			if (tid == 0 && is_last) ss.cand[total] = (uint16_t)(kBlockDec - 1);   // the lead-in sample of the next call
-			__syncthreads();
-			SCPROF(3);
-			// exact values with the reference arithmetic: lane k < 20 = stage-1 output 2m-18+k and stage-2 tap k
-			const int n_eval = total + (is_last ? 1 : 0);
-			const int t1 = WIDE ? kT1Wide[lane] : kT1Narrow[lane];
-			const float c2 = (float)t1 * (1.0f / 65536.0f);
-			const f2 c2p = pack2(c2, c2);
-			for (int i0 = warp; i0 < n_eval; i0 += 4 * kWarps) {
-				// (from global memory - L2 - because shared memory already belongs to the next block; bytes before a submit's
-				// first block are the carried history.)  The loads of four candidates go out together.
-				uint32_t w[4][4];
+			// this warp's quadrant of tensor memory is free for the next block's MMAs
+			sc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_tfree);
+			SCPROF(1);
+
+			// ---- ordered candidate list
+			const int nt = __popcll(cand64);
+			int incl = nt;
 #pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const int i = i0 + u * kWarps;
-					if (i < n_eval && lane < 20) {
-						const int o = 8 * (int)ss.cand[i] - 84 + 4 * lane;
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) incl += o;
+			}
+			if (lane == 31) ss.warp_cnt[warp] = incl;
+			sc_sync_screeners();
+			int base = incl - nt;
+			for (int w = 0; w < warp; w++) base += ss.warp_cnt[w];
+			const int total = ss.warp_cnt[0] + ss.warp_cnt[1] + ss.warp_cnt[2] + ss.warp_cnt[3];
+			const bool is_last = (tile == (int)job.n_blocks - 1);
+
+			if (total > kCandMax) {
+				// ---- a burst (telegram, start-up transient): the whole block with the exact cascade, here.  Shared
+				// memory already belongs to the next block, so a thread reads its 512-byte row (and the 96 bytes in front
+				// of it) from global memory - L2, the block has just been through - and writes its 64 samples straight to dec.
+				const uint4 *row = reinterpret_cast<const uint4 *>(blk + (size_t)tid * 512);
+				const uint4 *halo = (tid == 0 && tile == 0) ? reinterpret_cast<const uint4 *>(hist) : row - 6;
+				uint32_t *dst = p.dec + gtile * kBlockDec + (size_t)tid * kOutPerThread;
+				unsigned long long trig64 = 0ull;
+				uint32_t prev = 0;
+				fir_cascade<WIDE, 4>([&](int q) { return __ldg(halo + q); }, [&](int q) { return __ldg(row + q); },
+						     [&](int m, int yi, int yq) {
+							     if (abs(yi) + abs(yq) > thresh_lo) trig64 |= 1ull << m;
+							     const uint32_t w = pack_iq(yi, yq);
+							     if (m & 1) *reinterpret_cast<uint2 *>(dst + m - 1) = make_uint2(prev, w);
+							     prev = w;
+						     });
+				FrontParams pk = p;
+				pk.keep_all = 2;   // the samples are in dec already
+				const uint32_t *blk_dec = p.dec + gtile * kBlockDec;
+				block_epilogue(pk, job, tile, [&](int m) -> uint32_t { return blk_dec[m]; }, es, trig64, ScreenersSync());
+				if (tid == 0) st_dense++;
+				sc_sync_screeners();   // es is reused by the next burst block
+			} else {
+				if (nt) {
+					unsigned long long msk = cand64;
+					int k = base;
+					while (msk) {
+						const int b = __ffsll((long long)msk) - 1;
+						msk &= msk - 1;
+						ss.cand[k++] = (uint16_t)(tid * kOutPerThread + b);
+					}
+				}
+				if (tid == 0 && is_last) ss.cand[total] = (uint16_t)(kBlockDec - 1);   // the lead-in sample of the next call
+				sc_sync_screeners();
+				SCPROF(2);
+				// exact values with the reference arithmetic: lane k < 20 = stage-1 output 2m-18+k and stage-2 tap k
+				const int n_eval = total + (is_last ? 1 : 0);
+				const int t1 = WIDE ? kT1Wide[lane] : kT1Narrow[lane];
+				const float c2 = (float)t1 * (1.0f / 65536.0f);
+				const f2 c2p = pack2(c2, c2);
+				for (int i0 = warp; i0 < n_eval; i0 += 4 * kWarps) {
+					// (from global memory - L2 - because shared memory already belongs to the next block; bytes before a
+					// submit's first block are the carried history.)  The loads of four candidates go out together.
+					uint32_t w[4][4];
 #pragma unroll
-						for (int q = 0; q < 4; q++) {
-							const int oq = o + 4 * q;
-							w[u][q] = (oq >= 0 || tile > 0) ? __ldg(reinterpret_cast<const uint32_t *>(blk + oq))
-										: *reinterpret_cast<const uint32_t *>(hist + kHistBytes + oq);
+					for (int u = 0; u < 4; u++) {
+						const int i = i0 + u * kWarps;
+						if (i < n_eval && lane < 20) {
+							const int o = 8 * (int)ss.cand[i] - 84 + 4 * lane;
+#pragma unroll
+							for (int q = 0; q < 4; q++) {
+								const int oq = o + 4 * q;
+								w[u][q] = (oq >= 0 || tile > 0) ? __ldg(reinterpret_cast<const uint32_t *>(blk + oq))
+											: *reinterpret_cast<const uint32_t *>(hist + kHistBytes + oq);
+							}
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const int i = i0 + u * kWarps;
+						if (i >= n_eval) break;   // warp uniform
+						int fi = 0, fq = 0;
+						if (lane < 20) {
+							f2 x[8];
+							x[0] = cvt_iq(w[u][0], 0); x[1] = cvt_iq(w[u][0], 1);
+							x[2] = cvt_iq(w[u][1], 0); x[3] = cvt_iq(w[u][1], 1);
+							x[4] = cvt_iq(w[u][2], 0); x[5] = cvt_iq(w[u][2], 1);
+							x[6] = cvt_iq(w[u][3], 0); x[7] = cvt_iq(w[u][3], 1);
+							const f2 y1 = stage1(x);
+							const f2 acc = fma2_rm(y1, c2p, pack2((float)kA2One, (float)kA2One));
+							uint32_t ai, aq;
+							unpack2(acc, ai, aq);
+							const int off = (kA2One - (1 << 23)) + kM1Mul * t1;
+							fi = (int)(ai - 0x4B000000u) - off;
+							fq = (int)(aq - 0x4B000000u) - off;
+						}
+						const int yi = __reduce_add_sync(0xffffffffu, fi), yq = __reduce_add_sync(0xffffffffu, fq);
+						if (lane == 0) {
+							ss.res_w[i] = pack_iq(yi, yq);
+							ss.res_p[i] = abs(yi) + abs(yq);
 						}
 					}
 				}
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const int i = i0 + u * kWarps;
-					if (i >= n_eval) break;   // warp uniform
-					int fi = 0, fq = 0;
-					if (lane < 20) {
-						f2 x[8];
-						x[0] = cvt_iq(w[u][0], 0); x[1] = cvt_iq(w[u][0], 1);
-						x[2] = cvt_iq(w[u][1], 0); x[3] = cvt_iq(w[u][1], 1);
-						x[4] = cvt_iq(w[u][2], 0); x[5] = cvt_iq(w[u][2], 1);
-						x[6] = cvt_iq(w[u][3], 0); x[7] = cvt_iq(w[u][3], 1);
-						const f2 y1 = stage1(x);
-						const f2 acc = fma2_rm(y1, c2p, pack2((float)kA2One, (float)kA2One));
-						uint32_t ai, aq;
-						unpack2(acc, ai, aq);
-						const int off = (kA2One - (1 << 23)) + kM1Mul * t1;
-						fi = (int)(ai - 0x4B000000u) - off;
-						fq = (int)(aq - 0x4B000000u) - off;
+				sc_sync_screeners();
+				SCPROF(3);
+				// events in order, descriptor
+				if (warp == 0) {
+					uint32_t *ev = p.events + gtile * kMaxEvt;
+					int nev = 0, last = -1;
+					for (int b0 = 0; b0 < total; b0 += 32) {
+						const int i = b0 + lane;
+						const bool valid = i < total;
+						const int pw = valid ? ss.res_p[i] : 0;
+						const bool trig = valid && pw > thresh_lo;
+						const unsigned mask = __ballot_sync(0xffffffffu, trig);
+						if (trig) ev[nev + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)ss.cand[i] << 16) | (uint32_t)pw;
+						if (mask) last = ss.cand[b0 + 31 - __clz(mask)];
+						nev += __popc(mask);
 					}
-					const int yi = __reduce_add_sync(0xffffffffu, fi), yq = __reduce_add_sync(0xffffffffu, fq);
 					if (lane == 0) {
-						ss.res_w[i] = pack_iq(yi, yq);
-						ss.res_p[i] = abs(yi) + abs(yq);
+						TileDesc *td = p.tiles + gtile;
+						td->n_seg = 0;
+						td->carry_out = (uint16_t)((last >= 0) ? max(last + p.t_max - kBlockDec, 0) : 0);
+						td->n_trig = (uint32_t)nev;
+						td->pad = 0;
+						if (is_last) p.dec[gtile * kBlockDec + kBlockDec - 1] = ss.res_w[total];
+						st_sparse++;
+						st_cand += (uint32_t)total;
+						st_true += (uint32_t)nev;
 					}
 				}
+				SCPROF(4);
 			}
-			__syncthreads();
-			SCPROF(4);
-			// events in order, descriptor
-			if (warp == 0) {
-				uint32_t *ev = p.events + gtile * kMaxEvt;
-				int nev = 0, last = -1;
-				for (int b0 = 0; b0 < total; b0 += 32) {
-					const int i = b0 + lane;
-					const bool valid = i < total;
-					const int pw = valid ? ss.res_p[i] : 0;
-					const bool trig = valid && pw > thresh_lo;
-					const unsigned mask = __ballot_sync(0xffffffffu, trig);
-					if (trig) ev[nev + __popc(mask & ((1u << lane) - 1u))] = ((uint32_t)ss.cand[i] << 16) | (uint32_t)pw;
-					if (mask) last = ss.cand[b0 + 31 - __clz(mask)];
-					nev += __popc(mask);
-				}
-				if (lane == 0) {
-					TileDesc *td = p.tiles + gtile;
-					td->n_seg = 0;
-					td->carry_out = (uint16_t)((last >= 0) ? max(last + p.t_max - kBlockDec, 0) : 0);
-					td->n_trig = (uint32_t)nev;
-					td->pad = 0;
-					if (is_last) p.dec[gtile * kBlockDec + kBlockDec - 1] = ss.res_w[total];
-					st_sparse++;
-					st_cand += (uint32_t)total;
-					st_true += (uint32_t)nev;
-				}
-			}
+#ifdef TFR_SCREEN_PROFILE
+			prof[6]++;
+#endif
 		}
-		phase ^= 1u;
-		sc_fence_before();
-		__syncthreads();   // tensor memory is free for the next block's MMAs
-		sc_fence_after();
-		SCPROF(5);
 #ifdef TFR_SCREEN_PROFILE
-		prof[6]++;
+		if (tid == 0)
+			for (int k = 0; k < 7; k++) atomicAdd(&g_scprof[k], (unsigned long long)prof[k]);
 #endif
-	}
-#ifdef TFR_SCREEN_PROFILE
-	if (tid == 0)
-		for (int k = 0; k < 7; k++) atomicAdd(&g_scprof[k], (unsigned long long)prof[k]);
-#endif
-
-	if (tid == 0 && p.screen_stat) {
-		if (st_sparse) atomicAdd(p.screen_stat + 0, st_sparse);
-		if (st_dense) atomicAdd(p.screen_stat + 1, st_dense);
-		if (st_cand) atomicAdd(p.screen_stat + 2, st_cand);
-		if (st_true) atomicAdd(p.screen_stat + 3, st_true);
+		if (tid == 0 && p.screen_stat) {
+			if (st_sparse) atomicAdd(p.screen_stat + 0, st_sparse);
+			if (st_dense) atomicAdd(p.screen_stat + 1, st_dense);
+			if (st_cand) atomicAdd(p.screen_stat + 2, st_cand);
+			if (st_true) atomicAdd(p.screen_stat + 3, st_true);
+		}
 	}
 	sc_fence_before();
 	__syncthreads();
@@ -615,7 +644,7 @@ cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, c
 		if (e != cudaSuccess) return e;
 		if (getenv("TFR_DEBUG")) {
 			int nb = 0;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frontend_screen_kernel<false>, kThreads, kScreenSmem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frontend_screen_kernel<false>, kScreenThreads, kScreenSmem);
 			fprintf(stderr, "[tfr] frontend_screen: %d CTAs per SM, %d B dynamic shared memory\n", nb, kScreenSmem);
 		}
 		attr_done[dev] = true;
@@ -632,15 +661,15 @@ cudaError_t launch_frontend_screen(const FrontParams &p, int wide, int n_ctas, c
 			cudaMemcpyFromSymbol(r, g_scprof, sizeof(r));
 			cudaMemcpyToSymbol(g_scprof, z, sizeof(z));
 			const double n = (double)(r[6] ? r[6] : 1);
-			fprintf(stderr, "[scprof] %llu blocks, cycles per block (thread 0): load wait %.0f, MMAs %.0f, readback %.0f, candidate list %.0f, evaluation %.0f, epilogue+sync %.0f\n",
-				r[6], r[0] / n, r[1] / n, r[2] / n, r[3] / n, r[4] / n, r[5] / n);
+			fprintf(stderr, "[scprof] %llu blocks, cycles per block (screener thread 0): waiting for the MMAs %.0f, readback %.0f, candidate list %.0f, evaluation %.0f, events %.0f\n",
+				r[6], r[0] / n, r[1] / n, r[2] / n, r[3] / n, r[4] / n);
 		}
 	}
 #endif
 	if (wide)
-		frontend_screen_kernel<true><<<grid, kThreads, kScreenSmem, stream>>>(p);
+		frontend_screen_kernel<true><<<grid, kScreenThreads, kScreenSmem, stream>>>(p);
 	else
-		frontend_screen_kernel<false><<<grid, kThreads, kScreenSmem, stream>>>(p);
+		frontend_screen_kernel<false><<<grid, kScreenThreads, kScreenSmem, stream>>>(p);
 	return cudaGetLastError();
 }
 

@@ -70,10 +70,6 @@ __device__ __forceinline__ void tma_tensor_2d(uint32_t dst, const void *tmap, in
 		     "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
 		     : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start [0,14), leading byte offset [16,30), stride byte
 // offset [32,46) - all in 16-byte units -, version 1 at [46,48), swizzle mode at [61,64)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout)
