@@ -424,7 +424,6 @@ def main():
     # (CUDA-event span of the step's front-end launches, on the streams they run on), which is what the roofline of
     # the front-end kernel is computed from; reported beside the headline as `synchronised`
     dev_ms = fe_ms = be_ms = 0.0
-    w0 = rx.stats()["windows"]
     for _ in range(args.steps):
         step_device()
         rx.sync()
@@ -433,7 +432,7 @@ def main():
         fe_ms += st["last_frontend_ms"]
         be_ms += st["last_backend_ms"]
     st_end = rx.stats()
-    windows = st_end["windows"] - w0
+    windows = st_end["windows"] * args.steps          # (tfr_stats.windows counts the last call)
     rx.clear()
     barrier()
     m1 = sampler.mark() + 1
