@@ -70,7 +70,9 @@ typedef struct {
 typedef struct {
 	int32_t stream;
 	int32_t type;       /* sensor_e of the decoder that flushed */
-	int32_t status;     /* 0 ok, 1 bad CRC, 2 failed sanity checks */
+	int32_t status;     /* 0 ok, 1 bad CRC, 2 failed sanity checks; 3: not a flush but a notice - the TFA_2-family window
+	                     * that ended at pos saw byte_cnt inverted sync words, for each of which the reference prints
+	                     * "Inverted SYNC" (tfa2.cpp:294-300); rdata is empty */
 	int32_t byte_cnt;
 	int64_t pos;        /* 384 kS/s sample index (per stream) at which flush() ran */
 	int32_t rssi;       /* the int the reference passes to flush(): (int)(10*log10(.)) */

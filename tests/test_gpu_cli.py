@@ -33,6 +33,7 @@ def test_cli_replay_matches_reference(cli, golden, hot_fixture, tmp_path, name, 
     hot_fixture(name).tofile(str(path))
     out = run([cli, *c["argv"], "-L", str(path)])
     assert make_golden.decode_lines(out) == c["lines"]
+    assert out.count("Inverted SYNC\n") == c["inverted_syncs"]      # tfa2.cpp:294-300, printed whatever -D / -q say
     assert "done reading dump" in out
     out = run([cli, *c["argv"], "-q", "-e", "/bin/echo", "-L", str(path)])
     assert make_golden.exec_lines(out) == c["exec"]

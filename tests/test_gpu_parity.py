@@ -44,6 +44,7 @@ def compare_with_oracle(rx, iq, types, filt, thresh, stream=0, check_taps=True):
     assert [frame_key(f) for f in gf] == [frame_key(f) for f in of]
     assert [record_key(r) for r in gr] == [record_key(r) for r in orr]
     assert [r["exec"] for r in gr] == [r["exec"] for r in orr]
+    assert rx.inverted_syncs(stream) == o.inverted_syncs(), "'Inverted SYNC' lines (tfa2.cpp:294-300)"
     tr = rx.block_trace(stream)
     assert np.array_equal(tr, o.blocks()), "per-block threshold/trigger trace differs"
     assert rx.thresh(stream) == o.thresh()

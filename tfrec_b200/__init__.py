@@ -20,6 +20,7 @@ TFA_1, TFA_2, TFA_3, TX22, TFA_WHB = 0, 1, 2, 3, 5
 BLOCK_BYTES = 65536
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_TAPS, FLAG_KEEP_DECIM = 1, 2
+STATUS_NOTICE = 3          # tfr_frame.status of an "Inverted SYNC" notice (not a flush)
 
 ABI_SYMBOLS = ["tfr_create", "tfr_destroy", "tfr_submit", "tfr_submit_decimated", "tfr_process", "tfr_sync", "tfr_poll_frames",
                "tfr_poll_records", "tfr_clear_results", "tfr_get_thresh", "tfr_read_block_trace", "tfr_read_taps",
@@ -189,14 +190,21 @@ class Receiver:
         _check(self.L.tfr_sync(self.h))
         self._keep = []
 
-    def frames(self):
+    def frames(self, notices=False):
+        """the flushes of the calls since the last clear(); notices=True also returns the "Inverted SYNC" entries
+        (status STATUS_NOTICE, byte_cnt = how many the window saw) in their place in the output order"""
         n = _check(self.L.tfr_poll_frames(self.h, None, 0))
         buf = (Frame * max(n, 1))()
         n = _check(self.L.tfr_poll_frames(self.h, buf, n))
         self._keep = []
         return [{"stream": f.stream, "type": f.type, "status": f.status, "byte_cnt": f.byte_cnt, "pos": f.pos,
                  "rssi": f.rssi, "offset": f.offset, "rssi_raw": f.rssi_raw, "n_records": f.n_records,
-                 "rdata": bytes(f.rdata[:min(f.byte_cnt, 64)]).hex()} for f in buf[:n]]
+                 "rdata": bytes(f.rdata[:min(f.byte_cnt, 64)]).hex()} for f in buf[:n] if notices or f.status != STATUS_NOTICE]
+
+    def inverted_syncs(self, stream=None):
+        """how many "Inverted SYNC" lines the reference prints for what was decoded since the last clear() (tfa2.cpp:294-300)"""
+        return sum(f["byte_cnt"] for f in self.frames(notices=True)
+                   if f["status"] == STATUS_NOTICE and (stream is None or f["stream"] == stream))
 
     def records(self):
         n = _check(self.L.tfr_poll_records(self.h, None, 0))

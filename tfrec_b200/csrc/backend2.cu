@@ -541,6 +541,45 @@ static __device__ void drop_frame(const WinCtx &c, int idx)
 	if (idx >= 0) c.p->frames[idx].status = -2;
 }
 
+// tfa2_decoder::store_bit prints "Inverted SYNC" whenever the inverted sync word passes the shift register
+// (tfa2.cpp:294-300), noise windows included.  A window that saw some leaves ONE notice in the frame list: status 3,
+// byte_cnt = how many, pos = the window's end (where its frame, if any, follows).  Slot handling as for frames.
+static __device__ int put_notice(const WinCtx &c, int reuse, int count, uint32_t pos)
+{
+	uint32_t k = (uint32_t)reuse;
+	if (reuse < 0) {
+		k = atomicAdd(&c.p->counters->n_frames, 1u);
+		if (k >= c.p->max_frames) {
+			c.p->counters->overflow = 1;
+			return -1;
+		}
+	}
+	DevFrame &f = c.p->frames[k];
+	f.stream = c.stream;
+	f.demod = c.demod;
+	f.type = c.p->cfg->d[c.demod].type;
+	f.status = 3;
+	f.byte_cnt = count;
+	f.offset = 0;
+	f.n_records = 0;
+	f.first_record = 0;
+	f.pos = c.base_pos + pos;
+	f.rssi_raw = 1.0;
+	for (int n = 0; n < kMaxRdata; n++) f.rdata[n] = 0;
+	return (int)k;
+}
+static __device__ int window_notice(const WinCtx &c, int pad3, int count, uint32_t end)
+{
+	int ni = pad3 - 1;
+	if (count) {
+		ni = put_notice(c, ni, count, end);
+	} else {
+		drop_frame(c, ni);
+		ni = -1;
+	}
+	return ni + 1;   // the record's new pad3
+}
+
 // last_bit_idx bookkeeping: the reference keeps it relative to the current block and subtracts len at every
 // block start unless it is 0 (demodulator::start, decoder.cpp:118-122) - so 0 stays 0 forever
 __device__ __forceinline__ int lbi_at_block(int v, int vblock, int block)
@@ -942,6 +981,7 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		if (gate) fi = put_frame(c, rec.frame_idx, s, e.end, (double)s.rssi_i, s.offset);
 		else drop_frame(c, rec.frame_idx);
 		rec.frame_idx = fi;
+		rec.pad3 = window_notice(c, rec.pad3, s.inv_cnt, e.end);
 		s.sr_cnt = -1;
 		s.sr = 0;
 		s.byte_cnt = 0;
@@ -949,6 +989,9 @@ static __device__ void run_tfa2_window(const WinCtx &c, const DemodCfg &cfg, con
 		s.timeout_cnt = 0;
 		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan;
 	} else {
+		// the data ended inside the window: what it has seen so far is reported now (the reference printed it long ago)
+		rec.pad3 = window_notice(c, rec.pad3, s.inv_cnt, last);
+		s.inv_cnt = 0;   // reported: the continuation in the next call starts counting afresh
 		s.timeout_cnt = (int)(e.end - last);
 		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan | kRecUnfinished;
 	}
@@ -1294,6 +1337,7 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 			rec.first_edge = rec.first_edge_block = 0;
 			rec.pad = 0;
 			rec.lbi_in = 0;
+			rec.pad3 = 0;
 			const bool cont = (e.flags & kWinCont) != 0;
 			if (w == 0) {
 				// the first window of a call starts from the true carried state: nothing to speculate
@@ -1656,6 +1700,11 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 		}
 		fi = __shfl_sync(kFullMask, fi, 0);
 		rec.frame_idx = fi;
+		{   // every lane holds the same state; lane 0 owns the slot
+			int np = rec.pad3;
+			if (lane == 0) np = window_notice(c, rec.pad3, s.inv_cnt, e.end);
+			rec.pad3 = __shfl_sync(kFullMask, np, 0);
+		}
 		s.sr_cnt = -1;
 		s.sr = 0;
 		s.byte_cnt = 0;
@@ -1663,6 +1712,10 @@ static __device__ void run_tfa2_window_w(const WinCtx &c, const DemodCfg &cfg, c
 		s.timeout_cnt = 0;
 		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan;
 	} else {
+		int np = rec.pad3;
+		if (lane == 0) np = window_notice(c, rec.pad3, s.inv_cnt, last);
+		rec.pad3 = __shfl_sync(kFullMask, np, 0);
+		s.inv_cnt = 0;
 		s.timeout_cnt = (int)(e.end - last);
 		rec.flags = (rec.flags & (kRecExact | kRecEdge | kRecLbiIn)) | kRecRan | kRecUnfinished;
 	}
@@ -1805,6 +1858,7 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 			rec.first_edge = rec.first_edge_block = 0;
 			rec.pad = 0;
 			rec.lbi_in = 0;
+			rec.pad3 = 0;
 			rec.head31 = rec.sr_final = 0;
 			rec.nbits = 0;
 			rec.lbi_end = rec.lbi_end_block = 0;

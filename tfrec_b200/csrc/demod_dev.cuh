@@ -228,6 +228,7 @@ __device__ __forceinline__ void tfa2_bit(DemodState &s, int bit)
 		s.rdata[0] = (uint8_t)~((s.sr >> 8) & 0xff);
 		s.byte_cnt = 1;
 		s.invert = 1;
+		s.inv_cnt++;   // the reference prints "Inverted SYNC" here
 	}
 	if (s.sr_cnt == 0) {
 		if (s.byte_cnt < kRdataBytes)
@@ -244,6 +245,7 @@ __device__ __forceinline__ void tfa2_reset(DemodState &s)
 	s.dmax = -32767;
 	s.last_bit = 0;
 	s.rssi_i = 0;
+	s.inv_cnt = 0;
 }
 // ---- WeatherHub ---------------------------------------------------------------------------------
 __device__ __forceinline__ void whb_bit(DemodState &s, int bit)

@@ -996,7 +996,8 @@ static int fetch_results(tfr_handle *h)
 		const DevFrame &x = df[a], &y = df[b];
 		if (x.stream != y.stream) return x.stream < y.stream;
 		if (x.pos != y.pos) return x.pos < y.pos;
-		return x.demod < y.demod;
+		if (x.demod != y.demod) return x.demod < y.demod;
+		return (x.status == 3) > (y.status == 3);   // a window's "Inverted SYNC" notice comes before its frame
 	});
 	h->frames.clear();
 	h->records.clear();

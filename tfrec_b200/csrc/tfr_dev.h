@@ -79,6 +79,7 @@ struct DemodState {
 	int32_t byte_cnt;
 	int32_t synced;
 	int32_t invert;
+	int32_t inv_cnt;     // tfa2 family: inverted sync words seen in the current window (tfa2.cpp:294-300 prints a line for each)
 	int32_t w_last_bit, w_psk, w_last_psk, w_nrzs;
 	uint32_t w_lfsr;
 	uint8_t rdata[kRdataBytes];
@@ -167,7 +168,7 @@ struct WinRec {
 	double e_y0, e_y1;            // biquad outputs at window end
 	unsigned long long ld_hash;   // hash of the slicer input sequence (int)y over the window
 	int32_t lbi_in;               // edge repair: the predecessor chain's last_bit_idx, relative to the window's first block
-	int32_t pad3;
+	int32_t pad3;                 // 1 + frame slot of the window's "Inverted SYNC" notice (status 3), 0 = none
 };
 // Filter chains (biq_kernel): the TFA_2-family low-pass runs ahead of the slicers, as a chain over kBiqK consecutive
 // windows from ONE speculated start state; a chain's record holds the filter outputs it assumed and the ones it left

@@ -249,6 +249,10 @@ void decoder::flush(int rssi, int offset)
 void decoder::deliver_frame(const tfr_frame &f, sensordata_t *recs, int n_recs)
 {
 	const uint8_t *r = f.rdata;
+	if (f.status == 3) {   // tfa2.cpp:294-300: printed unconditionally, once per inverted sync word
+		for (int k = 0; k < f.byte_cnt; k++) printf("Inverted SYNC\n");
+		return;
+	}
 	if (dbg) {
 		int n = f.byte_cnt;
 		if (type == TFA_1) n = 11;
@@ -319,6 +323,49 @@ void decoder::store_data(sensordata_t &d)
 	if (mode == 0 && !repeat) execute_handler(d);
 }
 
+// Opt-in sink for high telegram rates (TFREC_EXEC=async in the environment): the reference forks the whole process and
+// a shell for every telegram and waits for the handler (decoder.cpp:95 `system(cmd)`), which caps it at a few hundred
+// telegrams per second.  Here ONE /bin/sh is started at the first telegram and every command line is written to its
+// standard input: same commands, same order, executed one after the other by that shell, but the decoder does not
+// wait for them.  The pipe is flushed after every delivered batch and closed (waited for) at exit.  Default: system().
+namespace {
+FILE *g_exec_sh = NULL;
+int g_exec_mode = -1;   // -1 not looked up yet, 0 system() per telegram, 1 one shell fed through a pipe
+void exec_close()
+{
+	if (g_exec_sh) {
+		pclose(g_exec_sh);
+		g_exec_sh = NULL;
+	}
+}
+bool exec_async(const char *cmd)
+{
+	if (g_exec_mode < 0) {
+		const char *e = getenv("TFREC_EXEC");
+		g_exec_mode = (e && !strcmp(e, "async")) ? 1 : 0;
+	}
+	if (!g_exec_mode) return false;
+	if (!g_exec_sh) {
+		fflush(stdout);   // what has been printed so far stays in front of the handlers' output
+		g_exec_sh = popen("/bin/sh", "w");
+		if (!g_exec_sh) {
+			perror("popen /bin/sh");
+			g_exec_mode = 0;
+			return false;
+		}
+		atexit(exec_close);
+	}
+	fputs(cmd, g_exec_sh);
+	fputc('\n', g_exec_sh);
+	return true;
+}
+}  // namespace
+
+void decoder::flush_exec(void)
+{
+	if (g_exec_sh) fflush(g_exec_sh);
+}
+
 // "<handler> id temp hum seq alarm rssi flags ts" through system() (decoder.cpp:67-96)
 void decoder::execute_handler(sensordata_t &d)
 {
@@ -333,6 +380,7 @@ void decoder::execute_handler(sensordata_t &d)
 			 d.alarm, d.rssi, d.flags, (long)d.ts);
 	}
 	if (dbg >= 1) printf("EXEC %s\n", cmd);
+	if (exec_async(cmd)) return;
 	if (system(cmd) == -1) perror("system");
 }
 

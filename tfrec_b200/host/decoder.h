@@ -56,6 +56,9 @@ class decoder {
 	virtual void store_data(sensordata_t &d);
 	virtual void execute_handler(sensordata_t &d);
 	virtual void flush_storage(void);
+	// TFREC_EXEC=async (opt-in): pushes the commands queued so far to the handler shell; a no-op with the default
+	// per-telegram system()
+	static void flush_exec(void);
 	virtual int has_sync(void) { return synced; }
 	int count(void) { return (int)data.size(); }
 	sensor_e get_type(void) { return type; }

@@ -124,6 +124,7 @@ int fsk_demod::deliver(tfr_handle *hh)
 		}
 		dec->deliver_frame(f, sd, n);
 	}
+	decoder::flush_exec();
 	tfr_clear_results(hh);
 	return (int)nf;
 }
