@@ -372,6 +372,29 @@ def test_front_end_chunks_and_back_end_parts(tb, hot_fixture, monkeypatch, parts
     rx.close()
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_split_back_end_across_calls(tb, hot_fixture, monkeypatch, mode):
+    """TFR_BE_SPLIT=2: every call's decwin, fm_dev and the windows that do not need the previous call's final state run on
+    the early stream beside the previous call's verifier; only window 0 and the windows whose warm-up reaches it wait
+    (one warp each).  =0: the whole back-end call after call.  Several small calls in flight, all five decoders."""
+    monkeypatch.setenv("TFR_BE_SPLIT", mode)
+    monkeypatch.setenv("TFR_MIN_CHUNK", "4")
+    for name, types in (("mixed5", 0x2F), ("cont_noisy", 0x07), ("strong_t7", 0x07)):
+        iq = hot_fixture(name)
+        rx = tb.Receiver(types=types, thresh=0)
+        step = 5 * 65536
+        for off in range(0, iq.size - iq.size % 65536, step):
+            rx.submit(0, iq[off:off + step].copy())
+            rx.process()                                   # no sync in between: calls in flight
+        o = ol.Oracle(types=types, thresh=0)
+        o.process(iq)
+        assert [frame_key(f) for f in rx.frames()] == [frame_key(f) for f in o.frames()], (name, mode)
+        assert [r["exec"] for r in rx.records()] == [r["exec"] for r in o.records()], (name, mode)
+        assert rx.inverted_syncs() == o.inverted_syncs()
+        assert rx.thresh(0) == o.thresh()
+        rx.close()
+
+
 def test_multi_stream_batch(tb, hot_fixture):
     names = ["single_tfa1", "mixed5", "strong_t7", "noise_only"]
     iqs = [hot_fixture(n) for n in names]

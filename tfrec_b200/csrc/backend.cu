@@ -624,6 +624,8 @@ __global__ void parse_kernel(const BackParams p)
 	for (uint32_t fi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; fi < n_frames; fi += n_warps) {
 	if (p.frames[fi].status != -1) continue;   // >= 0: parsed by an earlier tfr_process; -2: retired by the verifier (dead)
 	DevFrame *f = p.frames + fi;
+	// a frame of the NEXT call (its early windows run beside this call's verifier and parsers) is left to that call's parse
+	if (*reinterpret_cast<volatile int32_t *>(&f->first_record) != p.slot_tag) continue;
 	__syncwarp();
 	for (int k = lane; k < kMaxRdata; k += 32) r[k] = f->rdata[k];
 	__syncwarp();

@@ -37,6 +37,9 @@ __device__ unsigned long long g_slprof[8];   // of one 2784-sample window: fast 
 #ifndef TFR_CHAIN_MAX
 #define TFR_CHAIN_MAX 8
 #endif
+#ifndef TFR_WARM_X4
+#define TFR_WARM_X4 12   // biquad warm-up length of a speculated window in quarter timeouts
+#endif
 constexpr int kChainMax = TFR_CHAIN_MAX;
 #ifndef TFR_CHAIN_GROUP
 #define TFR_CHAIN_GROUP 1
@@ -384,6 +387,19 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 		st->win_cont[lane] = cont;
 		p.wincnt[stream].n[lane] = n_win;
 		p.wincnt[stream].cum[lane] = cum;
+		// the leading windows that need the previous call's final state (kLateRow): window 0, and for the filtered
+		// demodulators every window whose warm-up history (TFR_WARM_X4 quarter timeouts of earlier windows' samples) would
+		// reach window 0, up to the next chain head
+		uint32_t W = 0;
+		if (n_win) {
+			W = 1;
+			if (cfg.d[lane].kind != K_TFA1) {
+				const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)T_d) / 4u;
+				const uint32_t c1 = (n_win > 1) ? wl[1].cum : 0u;   // samples of window 0
+				while (W < n_win && !(wl[W].cum - c1 >= want && chain_head(wl, W, T_d))) W++;
+			}
+		}
+		p.partcnt[(size_t)kLateRow * p.n_streams + stream].n[lane] = W;
 	}
 	if (lane < nd) {
 		st->win_n[lane] = n_win;
@@ -497,6 +513,19 @@ __global__ void __launch_bounds__(128) devfm_win_kernel(const BackParams p)
 	}
 }
 
+// fm_dev of sample 0 once the previous call's last sample is known (devfm_win_kernel of a call may run beside the previous
+// call's verifier, before submit_epilogue_kernel has rolled StreamState::last_i/q forward)
+__global__ void devfm_first_kernel(const BackParams p)
+{
+	const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+	if (stream >= p.n_streams) return;
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	const StreamState *st = p.st + stream;
+	const uint32_t cw = p.dec[(size_t)job.dec_off * kBlockDec];
+	p.devfm[(size_t)job.dec_off * kBlockDec] = fm_dev_fast((int)(int16_t)(cw & 0xffff), (int)(int16_t)(cw >> 16), (int)st->last_i, (int)st->last_q);
+}
+
 // ------------------------------------------------------------------------------------------------
 // window context shared by the speculative kernels and the verifier's slow path
 // ------------------------------------------------------------------------------------------------
@@ -522,17 +551,19 @@ static __device__ int put_frame(const WinCtx &c, int reuse, const DemodState &s,
 		}
 	}
 	DevFrame &f = c.p->frames[k];
+	f.status = -2;   // not a frame until everything below is in place (parse_kernel of the previous call may be looking)
 	f.stream = c.stream;
 	f.demod = c.demod;
 	f.type = c.p->cfg->d[c.demod].type;
-	f.status = -1;
 	f.byte_cnt = s.byte_cnt;
 	f.offset = offset;
 	f.n_records = 0;
-	f.first_record = 0;
+	f.first_record = c.p->slot_tag;   // until parsed: whose parse_kernel this frame is for
 	f.pos = c.base_pos + pos;
 	f.rssi_raw = rssi_raw;
 	for (int n = 0; n < kMaxRdata; n++) f.rdata[n] = s.rdata[n];
+	__threadfence();
+	f.status = -1;
 	return (int)k;
 }
 // a re-run that no longer yields a frame retires the slot its first run claimed
@@ -1008,7 +1039,7 @@ __device__ __forceinline__ WinCtx make_ctx(const BackParams &p, int stream, int 
 	c.ld = (p.ld && p.fm_slot[demod] >= 0) ? p.ld + (size_t)p.fm_slot[demod] * p.ld_stride + (size_t)job.dec_off * kBlockDec : nullptr;
 	c.call_len = job.n_blocks * (uint32_t)kBlockDec;
 	c.prev_last = ((uint32_t)(uint16_t)st->last_i) | ((uint32_t)(uint16_t)st->last_q << 16);
-	c.base_pos = st->blocks_done * (int64_t)kBlockDec;
+	c.base_pos = job.base_blocks * (int64_t)kBlockDec;
 	return c;
 }
 
@@ -1324,7 +1355,7 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 	for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; w_lo + t0 * G < n_win; t0 += gridDim.x * blockDim.x)
 	for (uint32_t w0 = w_lo + t0 * G; w0 < min(n_win, w_lo + (t0 + 1) * G); w0++) {
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;   // an earlier thread carries on into this window
-		if (p.long_split && chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;   // winlong_kernel's
+		if (p.long_split && (p.long_all || chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout))) continue;   // winlong_kernel's
 		DemodState s;
 		bool have_lbi = false;   // s.last_bit_idx is the value the reference would hold (given the chain head's start state)
 		for (uint32_t w = w0; w < n_win; w++) {
@@ -1364,9 +1395,6 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 					// radius 0.905 .. 0.946 - but the two trajectories then sit in a +-1 ulp dead band and only merge by
 					// chance; measured on B200, windows that need the verifier's biquad-only repair / back-end time of a
 					// 32 x 128 MiB call: 2 timeouts 21 % 2.04 ms, 2.5: 13 % 1.90, 3: 8 % 1.90, 3.5: 5 % 1.85, 4: 3.3 % 1.84)
-#ifndef TFR_WARM_X4
-#define TFR_WARM_X4 12   // warm-up length in quarter timeouts
-#endif
 					const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)cfg.timeout) / 4u;
 					uint32_t have = 0;
 					int v = (int)w;
@@ -1457,7 +1485,7 @@ __global__ void __launch_bounds__(kWinThreads, TFR_WIN_MINBLOCKS) win_kernel(con
 #endif
 				if (rec.flags & kRecEdge) have_lbi = true;
 			}
-			if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+			if (rec.flags & kRecUnfinished) c.p->fin[(size_t)c.stream * kMaxDemods + demod] = s;
 			rl[w] = rec;
 			if (rec.flags & kRecUnfinished) break;
 		}
@@ -1844,7 +1872,7 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 	const uint32_t n_warps = gridDim.x * kLongWarps;
 	for (uint32_t w0 = w_lo + blockIdx.x * kLongWarps + (threadIdx.x >> 5); w0 < n_win; w0 += n_warps) {   // warp-uniform
 		if (chains && !chain_head(wl, w0, cfg.timeout)) continue;
-		if (!chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;
+		if (!p.long_all && !chain_is_long(wl, w0, n_win, c.call_len, chains, cfg.timeout)) continue;
 		// the chain loop of win_kernel, every lane the same
 		DemodState s;
 		bool have_lbi = false;
@@ -1929,7 +1957,7 @@ __global__ void __launch_bounds__(32 * kLongWarps) winlong_kernel(const BackPara
 				if (rec.flags & kRecEdge) have_lbi = true;
 			}
 			if (lane == 0) {
-				if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+				if (rec.flags & kRecUnfinished) c.p->fin[(size_t)c.stream * kMaxDemods + demod] = s;
 				rl[w] = rec;
 			}
 			if (rec.flags & kRecUnfinished) break;
@@ -2175,7 +2203,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 					run_tfa1_window(c, wl[v], s, rec, false);
 					rec.flags |= kRecLbiIn;
 					rec.lbi_in = (int32_t)sr;
-					if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+					if (rec.flags & kRecUnfinished) c.p->fin[(size_t)c.stream * kMaxDemods + demod] = s;
 					rl[v] = rec;
 					n_sr++;
 				}
@@ -2200,7 +2228,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 							rec.u_y1 = lp.y1;
 							rec.e_y0 = t.y0;
 							rec.e_y1 = t.y1;
-							if (rec.flags & kRecUnfinished) st->fin[demod].lp = t;
+							if (rec.flags & kRecUnfinished) c.p->fin[(size_t)c.stream * kMaxDemods + demod].lp = t;
 							lp = t;
 							n_cheap++;
 						} else {
@@ -2218,7 +2246,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 						rec.flags &= ~kRecEdge;
 						rec.flags |= kRecLbiIn;
 						run_tfa2_window(c, cfg, e, s, rec, false, false);
-						if (rec.flags & kRecUnfinished) st->fin[demod] = s;
+						if (rec.flags & kRecUnfinished) c.p->fin[(size_t)c.stream * kMaxDemods + demod] = s;
 						lp = s.lp;
 						n_full++;
 					}
@@ -2261,7 +2289,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 		const uint32_t sr_end = sr_before(rl, (int)n_win, carry0);
 		DemodState &out = st->d[demod];
 		if (unfinished) {
-			out = st->fin[demod];
+			out = c.p->fin[(size_t)c.stream * kMaxDemods + demod];
 		} else {
 			// tfa1.cpp:179-184 + :115-117: everything but the shift register is reset by the flush
 			out.mark_lvl = out.rssi_i = out.last_bit_idx = out.timeout_cnt = 0;
@@ -2276,7 +2304,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 		const int lbi_end = lbi_at_block(l.v, l.block, last_block);
 		DemodState &out = st->d[demod];
 		if (unfinished) {
-			out = st->fin[demod];
+			out = c.p->fin[(size_t)c.stream * kMaxDemods + demod];
 			out.lp = lp_end;
 		} else {
 			tfa2_reset(out);
@@ -2344,6 +2372,11 @@ cudaError_t launch_biq(const BackParams &p, int n_demods, cudaStream_t s)
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
 	biq_verify_kernel<<<p.n_streams * n_demods, kBiqVerThreads, 0, s>>>(p);
+	return cudaGetLastError();
+}
+cudaError_t launch_devfm_first(const BackParams &p, cudaStream_t s)
+{
+	devfm_first_kernel<<<(p.n_streams + 63) / 64, 64, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s)

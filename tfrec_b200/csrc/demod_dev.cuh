@@ -186,17 +186,19 @@ static __device__ void emit_frame(Walk &w, double rssi_raw, int offset)
 		return;
 	}
 	DevFrame &f = w.p->frames[k];
+	f.status = -2;   // not a frame until everything below is in place
 	f.stream = w.stream;
 	f.demod = w.demod;
 	f.type = w.p->cfg->d[w.demod].type;
-	f.status = -1;
 	f.byte_cnt = w.s.byte_cnt;
 	f.offset = offset;
 	f.n_records = 0;
-	f.first_record = 0;
+	f.first_record = w.p->slot_tag;   // until parsed: whose parse_kernel this frame is for
 	f.pos = w.pos;
 	f.rssi_raw = rssi_raw;
 	for (int n = 0; n < kMaxRdata; n++) f.rdata[n] = w.s.rdata[n];
+	__threadfence();
+	f.status = -1;
 }
 
 // ---- TFA_1 ----------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ constexpr int kScreenConstBytes = 2048 + 8192 + 256;   // frontend_screen.cu: kS
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s);
 cudaError_t launch_devfm_win(const BackParams &p, cudaStream_t s);
+cudaError_t launch_devfm_first(const BackParams &p, cudaStream_t s);
 cudaError_t launch_biq(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_win(const BackParams &p, int n_demods, cudaStream_t s);
 cudaError_t launch_winlong(const BackParams &p, int n_demods, cudaStream_t s);
@@ -104,6 +105,8 @@ struct tfr_handle {
 		uint8_t *d_tmaps = nullptr;              // [stream][2] CUtensorMap of the call's submits (frontend_tc_kernel)
 		std::vector<uint8_t> h_tmaps;            // host copy (stays until the slot's next call)
 		uint32_t *d_work_ctr = nullptr;          // [kFrontChunks] screening front-end: work counter of every chunk launch
+		DemodState *d_fin = nullptr;             // [stream][kMaxDemods]: state left by a window the call's data ended in
+		cudaEvent_t early_done = nullptr;        // decwin + fm_dev of the call's early back-end part are done
 		uint8_t *d_hist_copy = nullptr;          // [stream][kHistBytes]: the FIR history the call started from
 		cudaEvent_t raw_done = nullptr;          // decwin_kernel has read the call's raw bytes (the input arena may be rewritten)
 		TileDesc *d_tiles = nullptr;
@@ -123,6 +126,11 @@ struct tfr_handle {
 	};
 	Slot slot[2];
 	int cur = 0;                       // slot of the most recent tfr_process
+	cudaStream_t stream_early = nullptr;   // early back-end part of a call (decwin, fm_dev, the windows that do not need the previous
+	                                       // call's final state): runs beside the previous call's verifier on the back stream
+	int be_split = 1;                  // TFR_BE_SPLIT: 0 = the whole back-end of a call after the previous call's, 1 = split when the
+	                                   // previous call is still in flight (default), 2 = always split (tests)
+	std::vector<int64_t> stream_blocks;   // per stream: blocks decoded by the calls issued so far (StreamJob::base_blocks)
 	cudaStream_t stream_be = nullptr;  // back-end stream
 	cudaStream_t stream_long = nullptr; // winlong_kernel (the long window chains, one warp each) beside win_kernel; high priority
 	cudaEvent_t long_ev[2] = { nullptr, nullptr };
@@ -269,12 +277,14 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->stream_long) cudaStreamSynchronize(h->stream_long);
 	for (auto st_ : h->part_stream) if (st_) cudaStreamSynchronize(st_);
 	for (auto st_ : h->part_long) if (st_) cudaStreamSynchronize(st_);
+	if (h->stream_early) cudaStreamSynchronize(h->stream_early);
 	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
 	cudaFree(h->d_screen_consts); cudaFree(h->d_screen_stat); cudaFree(h->d_screen_dbg);
 	for (auto &sl : h->slot) {
-		cudaFree(sl.d_work_ctr); cudaFree(sl.d_hist_copy);
+		cudaFree(sl.d_work_ctr); cudaFree(sl.d_hist_copy); cudaFree(sl.d_fin);
+		if (sl.early_done) cudaEventDestroy(sl.early_done);
 		if (sl.raw_done) cudaEventDestroy(sl.raw_done);
 		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
@@ -291,6 +301,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->span0) cudaEventDestroy(h->span0);
 	if (h->span1) cudaEventDestroy(h->span1);
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
+	if (h->stream_early) cudaStreamDestroy(h->stream_early);
 	if (h->stream_long) cudaStreamDestroy(h->stream_long);
 	for (auto &e : h->long_ev) if (e) cudaEventDestroy(e);
 	for (auto st_ : h->part_stream) if (st_) cudaStreamDestroy(st_);
@@ -356,6 +367,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	// same priority as the front stream: measured on B200, a high-priority back-end stream shortens a pipelined
 	// call from 4.35 to 4.0 ms but stretches the issue-bound front-end kernel from 1.9 to 3.15 ms
 	CUH(cudaStreamCreateWithFlags(&h->stream_be, cudaStreamNonBlocking));
+	CUH(cudaStreamCreateWithFlags(&h->stream_early, cudaStreamNonBlocking));
+	h->stream_blocks.assign(cfg->n_streams, 0);
+	if (const char *sp = getenv("TFR_BE_SPLIT")) h->be_split = atoi(sp);
 	{   // the walk is 1 warp per stream on the call's critical path: its CTAs go first when an SM has room
 		int prio_lo = 0, prio_hi = 0;
 		CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -407,6 +421,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaMalloc(&sl.d_jobs, sizeof(StreamJob) * cfg->n_streams));
 		CUH(cudaMalloc(&sl.d_tmaps, (size_t)256 * cfg->n_streams));
 		CUH(cudaEventCreateWithFlags(&sl.raw_done, cudaEventDisableTiming));
+		CUH(cudaEventCreateWithFlags(&sl.early_done, cudaEventDisableTiming));
+		CUH(cudaMalloc(&sl.d_fin, sizeof(DemodState) * kMaxDemods * cfg->n_streams));
+		CUH(cudaMemset(sl.d_fin, 0, sizeof(DemodState) * kMaxDemods * cfg->n_streams));
 		CUH(cudaMalloc(&sl.d_work_ctr, sizeof(uint32_t) * kFrontChunks));
 		CUH(cudaMemset(sl.d_work_ctr, 0, sizeof(uint32_t) * kFrontChunks));
 		CUH(cudaMalloc(&sl.d_hist_copy, (size_t)kHistBytes * cfg->n_streams));
@@ -456,6 +473,7 @@ static int sync_all(tfr_handle *h)
 	CU(cudaStreamSynchronize(h->stream_long));
 	for (auto st_ : h->part_stream) if (st_) CU(cudaStreamSynchronize(st_));
 	for (auto st_ : h->part_long) if (st_) CU(cudaStreamSynchronize(st_));
+	CU(cudaStreamSynchronize(h->stream_early));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
 }
@@ -602,6 +620,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		j.dec_off = (uint32_t)total;
 		j.win_cap = j.n_blocks * (uint32_t)kWinPerBlock + 4u;
 		j.win_off = (uint32_t)total_wins;
+		j.base_blocks = h->stream_blocks[s];
+		h->stream_blocks[s] += j.n_blocks;
 		total_wins += (size_t)j.win_cap * ndm;
 		total += j.n_blocks;
 		max_blocks = std::max(max_blocks, j.n_blocks);
@@ -715,6 +735,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	bp.ld_stride = sl.cap_blocks * (size_t)kBlockDec;
 	bp.biq = sl.d_biq;
 	for (int k = 0; k < kMaxDemods; k++) bp.fm_slot[k] = h->fm_slot[k];
+	bp.fin = sl.d_fin;
+	bp.slot_tag = si + 1;
+	bp.long_all = 0;
 	bp.partcnt = sl.d_partcnt;
 	bp.part_idx = -1;
 	bp.part_lo = bp.part_hi = -1;
@@ -888,7 +911,75 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	CU(cudaEventRecord(h->dbg_ev[1], sb));
 	bp.tile0 = 0;
 	bp.n_tiles = (int)max_blocks;
-	if (h->dcfg.n_demods) {
+	// Split back-end: only the first window of every (stream, demodulator) - true carried state, the sample before position 0 -
+	// and the windows whose filter warm-up reaches back to it need what the previous call's verifier leaves (thresh2_kernel
+	// lists how many: partcnt row kLateRow).  Everything else of this call - decwin, fm_dev, the other windows - goes to the
+	// early stream and runs beside the previous call's verifier and parsers; the back stream, call after call, then only
+	// takes the late windows (a warp each), WeatherHub, the verifier and the parsers.
+	bool split = screen && h->be_split && h->pipelined && h->long_split && h->dcfg.n_demods && parts_done == 0 && h->be_parts == 1 &&
+		     !h->biq_chains;
+	if (split && h->be_split == 1) {
+		// nothing to run beside when the previous call's back-end is already done (a caller that synchronises per call): the
+		// split only adds launches then
+		const cudaError_t q = cudaEventQuery(h->slot[si ^ 1].back_done);
+		if (q == cudaSuccess) split = false;
+		else if (q != cudaErrorNotReady) CU(q);
+		else cudaGetLastError();
+	}
+	if (h->dcfg.n_demods && split) {
+		cudaStream_t se = h->stream_early;
+		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
+		CU(cudaStreamWaitEvent(se, sl.front_done, 0));
+		{
+			BackParams w = bp;
+			w.demod = h->win_demod;
+			CU(launch_decwin(w, h->dcfg.filter, sl.d_hist_copy, sl.d_dec, se));
+			CU(cudaEventRecord(sl.raw_done, se));
+			h->stats.kernel_launches += 1;
+		}
+		if (h->has_fm) {
+			BackParams w = bp;
+			w.demod = h->fm_demod;
+			CU(launch_devfm_win(w, se));
+			h->stats.kernel_launches += 1;
+		}
+		CU(cudaEventRecord(sl.early_done, se));
+		if (has_win) {
+			BackParams q = bp;
+			q.part_lo = kLateRow;
+			q.part_hi = -1;
+			q.long_split = 1;
+			CU(cudaStreamWaitEvent(h->part_long[0], sl.early_done, 0));
+			CU(launch_winlong(q, h->dcfg.n_demods, h->part_long[0]));
+			CU(cudaEventRecord(h->part_ldone[0], h->part_long[0]));
+			CU(cudaStreamWaitEvent(h->part_stream[0], sl.early_done, 0));
+			CU(launch_win(q, h->dcfg.n_demods, h->part_stream[0]));
+			CU(cudaEventRecord(h->part_done[0], h->part_stream[0]));
+			h->stats.kernel_launches += 2;
+		}
+		// late: after the previous call's back-end (stream order)
+		CU(cudaStreamWaitEvent(sb, sl.early_done, 0));
+		if (h->has_fm) {
+			BackParams w = bp;
+			w.demod = h->fm_demod;
+			CU(launch_devfm_first(w, sb));
+			h->stats.kernel_launches += 1;
+		}
+		if (has_win) {
+			BackParams q = bp;
+			q.part_lo = -1;
+			q.part_hi = kLateRow;
+			q.long_split = 1;
+			q.long_all = 1;
+			CU(launch_winlong(q, h->dcfg.n_demods, sb));
+			h->stats.kernel_launches += 1;
+			CU(cudaStreamWaitEvent(sb, h->part_done[0], 0));
+			CU(cudaStreamWaitEvent(sb, h->part_ldone[0], 0));
+		}
+		if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, sb)); h->stats.kernel_launches += 1; }
+		CU(launch_verify(bp, h->dcfg.n_demods, sb));
+		h->stats.kernel_launches += 1;
+	} else if (h->dcfg.n_demods) {
 		{   // the last part: every window the parts before it did not take
 			// (a call that runs as one part knows all its windows now: filter chains, window-driven fm_dev)
 			if (parts_done == 0 && h->has_fm && h->biq_chains && sl.d_ld && !getenv("TFR_DEVFM_BLOCKS")) bp.ld = sl.d_ld;

@@ -131,6 +131,8 @@ struct StreamJob {
 	uint32_t dec_off;             // offset (in blocks) of this stream inside the sparse decimated buffer
 	uint32_t win_off;             // first window-list entry of this stream (demod d starts at win_off + d*win_cap)
 	uint32_t win_cap;             // window-list capacity per demod = n_blocks*kWinPerBlock + 4
+	int64_t base_blocks;          // blocks of this stream decoded by earlier calls (position base = base_blocks * 8192); from the
+	                              // host, so that kernels of call i+1 that run beside call i's verifier need not read StreamState
 };
 
 // windows listed for one stream by the threshold kernel of ONE call (per work-buffer slot: the back-end of call
@@ -286,11 +288,19 @@ struct BackParams {
 	size_t ld_stride;        // elements per fm slot
 	BiqRec *biq;             // chain records, indexed like wins/recs by the chain's first window
 	int fm_slot[kMaxDemods]; // demod -> slot of ld, -1 none
+	DemodState *fin;         // [stream][kMaxDemods], per work-buffer slot: state left by a window the data ended in
+	int slot_tag;            // 1 + work-buffer slot: frames are tagged with it until they are parsed (parse_kernel of call i
+	                         // leaves the frames that call i+1's early windows are appending alone)
+	int long_all;            // 1: winlong_kernel takes every chain of its window range (the few windows of a call that need
+	                         // the previous call's final state run after its verifier: a warp each, not a thread)
 	WinCount *partcnt;       // [kMaxParts][n_streams]
 	int part_idx;            // thresh2_kernel: which row of partcnt this launch fills, -1 none
 	int part_lo, part_hi;    // window kernels: rows of partcnt bounding the windows of this launch (lo -1: from window 0, hi -1: to the end)
 };
 constexpr int kMaxParts = 8;
+// partcnt row kLateRow: the leading windows of every (stream, demodulator) that depend on the previous call's final state -
+// window 0 (true carried state, the sample before position 0) and the windows whose filter warm-up reaches back to it
+constexpr int kLateRow = kMaxParts - 1;
 
 }  // namespace tfr
 
