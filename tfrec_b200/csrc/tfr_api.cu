@@ -126,6 +126,7 @@ struct tfr_handle {
 	};
 	Slot slot[2];
 	int cur = 0;                       // slot of the most recent tfr_process
+	cudaStream_t stream_early2 = nullptr;  // ... of the calls in the other work-buffer slot: two calls' early parts may overlap
 	cudaStream_t stream_early = nullptr;   // early back-end part of a call (decwin, fm_dev, the windows that do not need the previous
 	                                       // call's final state): runs beside the previous call's verifier on the back stream
 	int be_split = 1;                  // TFR_BE_SPLIT: 0 = the whole back-end of a call after the previous call's, 1 = split when the
@@ -278,6 +279,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	for (auto st_ : h->part_stream) if (st_) cudaStreamSynchronize(st_);
 	for (auto st_ : h->part_long) if (st_) cudaStreamSynchronize(st_);
 	if (h->stream_early) cudaStreamSynchronize(h->stream_early);
+	if (h->stream_early2) cudaStreamSynchronize(h->stream_early2);
 	if (h->stream_be) cudaStreamSynchronize(h->stream_be);
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
@@ -302,6 +304,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	if (h->span1) cudaEventDestroy(h->span1);
 	if (h->stream_be) cudaStreamDestroy(h->stream_be);
 	if (h->stream_early) cudaStreamDestroy(h->stream_early);
+	if (h->stream_early2) cudaStreamDestroy(h->stream_early2);
 	if (h->stream_long) cudaStreamDestroy(h->stream_long);
 	for (auto &e : h->long_ev) if (e) cudaEventDestroy(e);
 	for (auto st_ : h->part_stream) if (st_) cudaStreamDestroy(st_);
@@ -368,6 +371,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 	// call from 4.35 to 4.0 ms but stretches the issue-bound front-end kernel from 1.9 to 3.15 ms
 	CUH(cudaStreamCreateWithFlags(&h->stream_be, cudaStreamNonBlocking));
 	CUH(cudaStreamCreateWithFlags(&h->stream_early, cudaStreamNonBlocking));
+	CUH(cudaStreamCreateWithFlags(&h->stream_early2, cudaStreamNonBlocking));
 	h->stream_blocks.assign(cfg->n_streams, 0);
 	if (const char *sp = getenv("TFR_BE_SPLIT")) h->be_split = atoi(sp);
 	{   // the walk is 1 warp per stream on the call's critical path: its CTAs go first when an SM has room
@@ -382,7 +386,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		for (auto &e : h->part_fm) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		for (auto &e : h->part_done) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		for (auto &e : h->part_ldone) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-		for (int k = 0; k < h->be_parts && k < kMaxParts; k++) {
+		for (int k = 0; k < std::max(h->be_parts, 2) && k < kMaxParts; k++) {   // (two at least: the split back-end uses one pair per slot)
 			CUH(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
 			CUH(cudaStreamCreateWithPriority(&h->part_long[k], cudaStreamNonBlocking, prio_hi));
 		}
@@ -474,6 +478,7 @@ static int sync_all(tfr_handle *h)
 	for (auto st_ : h->part_stream) if (st_) CU(cudaStreamSynchronize(st_));
 	for (auto st_ : h->part_long) if (st_) CU(cudaStreamSynchronize(st_));
 	CU(cudaStreamSynchronize(h->stream_early));
+	CU(cudaStreamSynchronize(h->stream_early2));
 	CU(cudaStreamSynchronize(h->stream_be));
 	return TFR_OK;
 }
@@ -927,7 +932,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		else cudaGetLastError();
 	}
 	if (h->dcfg.n_demods && split) {
-		cudaStream_t se = h->stream_early;
+		cudaStream_t se = si ? h->stream_early2 : h->stream_early;
+		cudaStream_t s_win = h->part_stream[si], s_long = h->part_long[si];
 		const bool has_win = h->has_fm || (h->dcfg.d[0].kind == K_TFA1);
 		CU(cudaStreamWaitEvent(se, sl.front_done, 0));
 		{
@@ -949,12 +955,12 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			q.part_lo = kLateRow;
 			q.part_hi = -1;
 			q.long_split = 1;
-			CU(cudaStreamWaitEvent(h->part_long[0], sl.early_done, 0));
-			CU(launch_winlong(q, h->dcfg.n_demods, h->part_long[0]));
-			CU(cudaEventRecord(h->part_ldone[0], h->part_long[0]));
-			CU(cudaStreamWaitEvent(h->part_stream[0], sl.early_done, 0));
-			CU(launch_win(q, h->dcfg.n_demods, h->part_stream[0]));
-			CU(cudaEventRecord(h->part_done[0], h->part_stream[0]));
+			CU(cudaStreamWaitEvent(s_long, sl.early_done, 0));
+			CU(launch_winlong(q, h->dcfg.n_demods, s_long));
+			CU(cudaEventRecord(h->part_ldone[si], s_long));
+			CU(cudaStreamWaitEvent(s_win, sl.early_done, 0));
+			CU(launch_win(q, h->dcfg.n_demods, s_win));
+			CU(cudaEventRecord(h->part_done[si], s_win));
 			h->stats.kernel_launches += 2;
 		}
 		// late: after the previous call's back-end (stream order)
@@ -973,8 +979,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			q.long_all = 1;
 			CU(launch_winlong(q, h->dcfg.n_demods, sb));
 			h->stats.kernel_launches += 1;
-			CU(cudaStreamWaitEvent(sb, h->part_done[0], 0));
-			CU(cudaStreamWaitEvent(sb, h->part_ldone[0], 0));
+			CU(cudaStreamWaitEvent(sb, h->part_done[si], 0));
+			CU(cudaStreamWaitEvent(sb, h->part_ldone[si], 0));
 		}
 		if (h->has_whb) { CU(launch_walk(bp, h->dcfg.n_demods, sb)); h->stats.kernel_launches += 1; }
 		CU(launch_verify(bp, h->dcfg.n_demods, sb));
