@@ -322,12 +322,14 @@ __global__ void __launch_bounds__(kScreenThreads, 2) frontend_screen_kernel(cons
 				// kernels of the previous call no longer fit beside the two screening CTAs of an SM)
 				uint32_t va[32], vb[32];
 				auto screen8 = [&](const uint32_t (&v)[32], int j0) {
+					unsigned m8 = 0u;   // (constant bit positions: a predicated OR per output instead of a 64-bit variable shift)
 #pragma unroll
 					for (int k = 0; k < 8; k++) {
 						const int ci = (int)(v[4 * k + 1] << 8) + (int)v[4 * k], cq = (int)(v[4 * k + 3] << 8) + (int)v[4 * k + 2];
-						if (abs(ci) + abs(cq) > thr) cand64 |= 1ull << (j0 + k);
+						if (abs(ci) + abs(cq) > thr) m8 |= 1u << k;
 						if (dbg) { dbg[2 * (j0 + k)] = ci; dbg[2 * (j0 + k) + 1] = cq; }
 					}
+					cand64 |= (unsigned long long)m8 << j0;
 				};
 				sc_ld32(tlane, va);
 				sc_ld32(tlane + 32, vb);
