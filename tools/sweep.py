@@ -33,6 +33,73 @@ def decim_sweep(peak):
         del buf, out
 
 
+def synth_bytes(lo, hi, dev):
+    """deterministic byte stream by index (every rank can make any slice of the same stream): a hashed counter"""
+    idx = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+    return (((idx * 2654435761) >> 13) ^ (idx >> 7)).bitwise_and_(0xff).to(torch.uint8)
+
+
+def mgpu_sweep(peak):
+    """BASELINE configs[4] across GPUs: ONE IQ buffer of 2^20 .. 2^30 raw samples, decimation /2 .. /32, time-sharded over
+    the ranks of a torchrun launch.  A FIR has finite support (410 raw samples for /32), so rank r decimates its slice
+    plus a lead-in of 64 outputs' worth of raw samples and drops those 64 outputs: what remains is bit-identical to the
+    single-GPU result (checked here against rank 0 decimating the whole buffer, up to 2^26 samples).  No collective on
+    the data path; time = max over ranks of the CUDA-event time of the cascade, GB/s = 2 B per raw sample of the WHOLE
+    buffer / that time.   torchrun --nproc-per-node N tools/sweep.py mgpu"""
+    import hashlib
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        print("# time-sharded tfr_downconvert over %d GPU(s), narrow filter; aggregate algorithmic GB/s (2 B per raw sample) and %% of N x the measured HBM peak" % world)
+        print("%12s %8s | %s" % ("raw samples", "MiB", " | ".join("/%-2d %8s %8s %6s" % (1 << p, "ms", "GB/s", "%peak") for p in range(1, 6))))
+    for lg in (20, 22, 24, 26, 28, 30):
+        n = 1 << lg                                       # raw IQ samples in the whole buffer
+        cells = []
+        for p in range(1, 6):
+            lead = 64 << p                                # raw samples of lead-in (64 outputs)
+            lo, hi = rank * n // world, (rank + 1) * n // world
+            lo_in = lo - lead if rank else lo
+            buf = synth_bytes(2 * lo_in, 2 * hi, dev)
+            out = torch.empty(2 * ((hi - lo_in) >> p) + 16, device=dev, dtype=torch.int16)
+            best = 1e9
+            for it in range(3):
+                if world > 1:
+                    dist.barrier()
+                cnt, ms = tb.downconvert_device(buf.data_ptr(), buf.numel(), out.data_ptr(), passes=p, filter=0, device=local, reps=5)
+                best = min(best, ms)
+            mine = out[: cnt][(2 * 64 if rank else 0):]    # drop the lead-in's outputs
+            t = torch.tensor([best], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ok = ""
+            if n <= (1 << 26):                            # parity: the slices, concatenated, are the single-GPU result
+                parts = [mine.cpu()]
+                if world > 1:
+                    gathered = [None] * world
+                    dist.all_gather_object(gathered, mine.cpu().numpy().tobytes())
+                    parts = gathered
+                if rank == 0:
+                    whole_in = synth_bytes(0, 2 * n, dev)
+                    whole = torch.empty(2 * (n >> p) + 16, device=dev, dtype=torch.int16)
+                    c2, _ = tb.downconvert_device(whole_in.data_ptr(), whole_in.numel(), whole.data_ptr(), passes=p, filter=0, device=local)
+                    want = hashlib.sha256(whole[:c2].cpu().numpy().tobytes()).hexdigest()
+                    got = hashlib.sha256(b"".join(parts) if world > 1 else parts[0].numpy().tobytes()).hexdigest()
+                    ok = "=" if got == want else "MISMATCH"
+                    assert got == want, "time-sharded result differs from the single-GPU result (n=2^%d, /%d)" % (lg, 1 << p)
+                    del whole_in, whole
+            tt = float(t.item())
+            cells.append("/%-2d %8.4f %8.1f %5.1f%%%s" % (1 << p, tt, 2.0 * n / tt / 1e6, 100 * 2.0 * n / tt / 1e6 / (peak * world), ok))
+            del buf, out
+        if rank == 0:
+            print("%12d %8.1f | %s" % (n, 2.0 * n / 2**20, " | ".join(cells)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     peak = 6544.7
     try:
@@ -41,6 +108,8 @@ def main():
         pass
     if len(sys.argv) > 1 and sys.argv[1] == "decim":
         return decim_sweep(peak)
+    if len(sys.argv) > 1 and sys.argv[1] == "mgpu":
+        return mgpu_sweep(peak)
     g = torch.Generator(device="cuda"); g.manual_seed(5)
     print("%12s %10s %12s %10s %8s | %12s %10s" % ("raw samples", "MiB", "front ms", "GB/s", "%peak", "T7 auto ms", "GS/s"))
     for lg in range(20, 31):
