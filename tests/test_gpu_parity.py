@@ -168,11 +168,12 @@ def test_tensor_core_front_end_variant_bit_exact(tb, golden, hot_fixture, monkey
     rx.close()
 
 
-def test_screen_values_are_the_linear_filter(tb, hot_fixture):
+def test_screen_values_are_the_linear_filter(tb, hot_fixture, monkeypatch):
     """Screening front-end (frontend_screen.cu): the tensor-core GEMM of the raw bytes with the 16-bit combined filter is
     an exact integer computation - every screen value equals the numpy restatement, across submits (carried history) and
     for both filters; the bound itself is checked against the oracle in tests/test_screen_bound.py"""
     import screen_ref as sr
+    monkeypatch.setenv("TFR_NO_DENSE_MODE", "1")          # random bytes are all bursts: keep them going through the screen
     rng = np.random.default_rng(11)
     cases = {"mixed5": hot_fixture("mixed5")[:24 * 65536],
              "uniform": rng.integers(0, 256, size=6 * 65536, dtype=np.uint8),
@@ -393,6 +394,29 @@ def test_split_back_end_across_calls(tb, hot_fixture, monkeypatch, mode):
         assert rx.inverted_syncs() == o.inverted_syncs()
         assert rx.thresh(0) == o.thresh()
         rx.close()
+
+
+def test_bursty_input_switches_to_the_dense_front_end(tb):
+    """A fixed threshold inside the noise makes every block a burst: the screening front-end runs them in place (exact),
+    reports it, and the following calls take the dense kernel (every 16th probes the screen again).  Results stay the
+    oracle's across the switches."""
+    rng = np.random.default_rng(23)
+    iq = np.clip(np.rint(rng.normal(127.5, 6.0, 40 * 65536)), 0, 255).astype(np.uint8)
+    rx = tb.Receiver(types=0x07, thresh=120)
+    o = ol.Oracle(types=0x07, thresh=120)
+    step = 2 * 65536
+    for off in range(0, iq.size, step):
+        rx.submit(0, iq[off:off + step].copy())
+        rx.process()
+        rx.sync()
+    o.process(iq)
+    assert [frame_key(f) for f in rx.frames()] == [frame_key(f) for f in o.frames()]
+    assert [r["exec"] for r in rx.records()] == [r["exec"] for r in o.records()]
+    assert rx.inverted_syncs() == o.inverted_syncs()
+    st = rx.stats()
+    # 20 calls of 2 blocks: the first one (and the probes, calls 17 ..) went through the screen as bursts, the rest dense
+    assert 2 <= st["dense_blocks"] <= 8 and st["screen_blocks"] == 0, st
+    rx.close()
 
 
 def test_multi_stream_batch(tb, hot_fixture):

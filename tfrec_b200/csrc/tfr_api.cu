@@ -151,7 +151,17 @@ struct tfr_handle {
 	                                   // the dense exact kernel of frontend.cu for every block
 	uint8_t *d_screen_consts = nullptr;
 	int screen_shift = 0, screen_slack = 0;
-	uint32_t *d_screen_stat = nullptr; // [4] sparse blocks, dense blocks, candidates, true bound-triggers
+	uint32_t *d_screen_stat = nullptr; // [4] sparse blocks, dense blocks, candidates, true bound-triggers (since create)
+	// Bursty input (a fixed threshold inside the noise, a continuous strong signal): when most blocks come back from the screen
+	// as bursts, screening only adds work - the in-place cascade runs at a third of the dense kernel's occupancy.  The counters
+	// of every call are copied to the host behind its front-end; a call after one with more than a quarter of burst blocks takes
+	// the dense kernel, every kDenseProbe-th call tries the screen again.
+	uint32_t *h_screen_stat = nullptr;         // pinned [4]: snapshot behind the latest screened call's front-end
+	cudaEvent_t ev_screen_stat = nullptr;
+	uint32_t screen_seen[2] = { 0, 0 };        // sparse / burst blocks of the snapshot before
+	bool screen_stat_pending = false;
+	bool dense_mode = false;
+	int dense_calls = 0;
 	int32_t *d_screen_dbg = nullptr;   // TFR_FLAG_TAPS: screen values of the last call [block][8192][2]
 	size_t screen_dbg_blocks = 0;
 	int win_demod = -1;                // the demodulator with the longest timeout: its windows contain every sample any demodulator reads
@@ -284,6 +294,8 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 	cudaFree(h->d_cfg); cudaFree(h->d_state); cudaFree(h->d_counters);
 	cudaFree(h->d_frames); cudaFree(h->d_records);
 	cudaFree(h->d_screen_consts); cudaFree(h->d_screen_stat); cudaFree(h->d_screen_dbg);
+	if (h->h_screen_stat) cudaFreeHost(h->h_screen_stat);
+	if (h->ev_screen_stat) cudaEventDestroy(h->ev_screen_stat);
 	for (auto &sl : h->slot) {
 		cudaFree(sl.d_work_ctr); cudaFree(sl.d_hist_copy); cudaFree(sl.d_fin);
 		if (sl.early_done) cudaEventDestroy(sl.early_done);
@@ -409,6 +421,9 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		CUH(cudaMemcpy(h->d_screen_consts, blob.data(), kScreenConstBytes, cudaMemcpyHostToDevice));
 		CUH(cudaMalloc(&h->d_screen_stat, 4 * sizeof(uint32_t)));
 		CUH(cudaMemset(h->d_screen_stat, 0, 4 * sizeof(uint32_t)));
+		CUH(cudaMallocHost(&h->h_screen_stat, 4 * sizeof(uint32_t)));
+		memset(h->h_screen_stat, 0, 4 * sizeof(uint32_t));
+		CUH(cudaEventCreateWithFlags(&h->ev_screen_stat, cudaEventDisableTiming));
 	}
 	CUH(cudaStreamCreateWithFlags(&h->stream_fe2, cudaStreamNonBlocking));
 	for (auto &e : h->chunk_ev) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -653,7 +668,23 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	// h->jobs stays untouched until the copy has run: the next tfr_process first waits for this slot's events
 	CU(cudaMemcpyAsync(sl.d_jobs, h->jobs.data(), sizeof(StreamJob) * ns, cudaMemcpyHostToDevice, sf));
 	// screening front-end: raw bytes, nothing that wants every decimated sample, the back-end as one part
-	const bool screen = h->use_screen && !decimated && !(h->cfg.flags & TFR_FLAG_KEEP_DECIM) && h->be_parts == 1 && !getenv("TFR_DEVFM_BLOCKS");
+	bool screen = h->use_screen && !decimated && !(h->cfg.flags & TFR_FLAG_KEEP_DECIM) && h->be_parts == 1 && !getenv("TFR_DEVFM_BLOCKS");
+	if (screen) {
+		constexpr int kDenseProbe = 16;
+		if (h->screen_stat_pending && cudaEventQuery(h->ev_screen_stat) == cudaSuccess) {
+			const uint32_t sp = h->h_screen_stat[0] - h->screen_seen[0], bu = h->h_screen_stat[1] - h->screen_seen[1];
+			h->screen_seen[0] = h->h_screen_stat[0];
+			h->screen_seen[1] = h->h_screen_stat[1];
+			h->screen_stat_pending = false;
+			if (sp + bu) h->dense_mode = bu > (sp + bu) / 4;
+			h->dense_calls = 0;
+		} else {
+			cudaGetLastError();
+		}
+		if (h->dense_mode && !getenv("TFR_NO_DENSE_MODE")) {
+			if (++h->dense_calls % kDenseProbe) screen = false;   // (every kDenseProbe-th call probes the screen again)
+		}
+	}
 	if ((h->use_tc || screen) && !decimated) {
 		// the call's tensor maps (TMA descriptors of every stream's submit), encoded on the host, 64-byte aligned
 		uint8_t *tm = reinterpret_cast<uint8_t *>(((uintptr_t)sl.h_tmaps.data() + 63) & ~(uintptr_t)63);
@@ -875,6 +906,11 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 		}
 		if (last_odd >= 0) CU(cudaStreamWaitEvent(sf, h->chunk_ev[last_odd], 0));
 		CU(cudaEventRecord(sl.fe1, sf));
+		if (screen && !h->screen_stat_pending) {
+			CU(cudaMemcpyAsync(h->h_screen_stat, h->d_screen_stat, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sf));
+			CU(cudaEventRecord(h->ev_screen_stat, sf));
+			h->screen_stat_pending = true;
+		}
 		CU(cudaEventRecord(h->walk_ev, h->stream_walk));
 		CU(cudaEventRecord(h->dbg_ev[0], h->stream_walk));
 		CU(cudaStreamWaitEvent(sf, h->walk_ev, 0));   // rejoin: everything after this on the front stream sees the walk
@@ -1607,11 +1643,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_get_stats(tfr_handle *
 		int rc = tfr_sync(h);
 		if (rc) return rc;
 		CU(cudaMemcpy(v, h->d_screen_stat, sizeof(v), cudaMemcpyDeviceToHost));
-		CU(cudaMemset(h->d_screen_stat, 0, sizeof(v)));
-		h->stats.screen_blocks += v[0];
-		h->stats.dense_blocks += v[1];
-		h->stats.screen_candidates += v[2];
-		h->stats.screen_triggers += v[3];
+		h->stats.screen_blocks = v[0];
+		h->stats.dense_blocks = v[1];
+		h->stats.screen_candidates = v[2];
+		h->stats.screen_triggers = v[3];
 	}
 	*out = h->stats;
 	return TFR_OK;
