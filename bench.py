@@ -432,7 +432,7 @@ def main():
         fe_ms += st["last_frontend_ms"]
         be_ms += st["last_backend_ms"]
     st_end = rx.stats()
-    windows = st_end["windows"] * args.steps          # (tfr_stats.windows counts the last call)
+    windows = st_end["windows"] * args.steps          # (tfr_stats.windows counts the last call; every step decodes the same streams)
     rx.clear()
     barrier()
     m1 = sampler.mark() + 1
