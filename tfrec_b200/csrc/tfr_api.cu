@@ -737,9 +737,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 	// one chunk of blocks through the screen: persistent CTAs, two per SM, fetching blocks from the chunk's counter
 	auto launch_screen = [&](FrontParams q, int chunk, cudaStream_t st) -> cudaError_t {
 		q.work_ctr = sl.d_work_ctr + chunk;
-		// one persistent CTA per SM: measured on B200 the kernel streams as fast with 148 CTAs as with 296 (0.85 ms per 4 GiB
-		// either way - it is bound by HBM and the per-SM tensor-memory / shared-memory paths, not by concurrency per SM), and
-		// the back-end kernels of the call in flight keep half of every SM (TFR_SCREEN_CTAS overrides, profiles/r2_screen_ctas.txt)
+		// one persistent CTA per SM and launch: the chunk launches alternate between two streams and overlap pairwise, so two
+		// CTAs are resident per SM either way (shared memory allows no more); measured on B200 launches of 296 CTAs stream no
+		// faster (0.85 ms per 4 GiB), and with 148 the tail of a launch leaves room for the back-end kernels of the call in
+		// flight (TFR_SCREEN_CTAS overrides, profiles/r2_screen_ctas.txt)
 		static const int ctas_env = getenv("TFR_SCREEN_CTAS") ? atoi(getenv("TFR_SCREEN_CTAS")) : 0;
 		return launch_frontend_screen(q, h->dcfg.filter, ctas_env > 0 ? ctas_env : h->n_sms, st);
 	};
