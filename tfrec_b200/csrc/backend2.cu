@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 {
 	const int stream = blockIdx.x;
 	const int lane = threadIdx.x;
+	__shared__ uint32_t s_trig[128];   // the triggers of a chunk's accepted blocks, in order (at most four per block)
 	if (stream >= p.n_streams) return;
 	const StreamJob job = p.jobs[stream];
 	const DevConfig &cfg = *p.cfg;
@@ -308,6 +309,32 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 			if (acc_end > j0) c = __shfl_sync(0xffffffffu, out, acc_end - 1);
 			// ---- 4. window lists: the accepted blocks' triggers in order
 			unsigned wm = __ballot_sync(0xffffffffu, accepted && has);
+			// The usual case - no accepted block holds more than four triggers - without a warp-wide broadcast per block:
+			// every lane drops its triggers into an ordered list in shared memory (one scan), then the demodulator lanes run
+			// the window bookkeeping over the list on their own.  (Per block the loop below costs five shuffles and a
+			// divergent call; on the stream's serial chain every instruction waits for the one before it.)
+			if (wm && !__any_sync(0xffffffffu, accepted && cnt > 4)) {
+				const int mine = (accepted && has) ? cnt : 0;
+				int incl = mine;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const int o = __shfl_up_sync(0xffffffffu, incl, d);
+					if (lane >= d) incl += o;
+				}
+				const int total = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t base = (uint32_t)(chunk + lane) * kBlockDec;
+				int at = incl - mine;
+				if (mine > 0) s_trig[at] = base + tp0;
+				if (mine > 1) s_trig[at + 1] = base + tp1;
+				if (mine > 2) s_trig[at + 2] = base + tp2;
+				if (mine > 3) s_trig[at + 3] = base + tp3;
+				__syncwarp();
+				if (lane < nd)
+					for (int i = 0; i < total; i++) win_trigger(s_trig[i]);
+				last_trig = s_trig[total - 1];
+				__syncwarp();
+				wm = 0;
+			}
 			while (wm) {
 				const int j = __ffs(wm) - 1;
 				wm &= wm - 1;
