@@ -432,7 +432,7 @@ def main():
         fe_ms += st["last_frontend_ms"]
         be_ms += st["last_backend_ms"]
     st_end = rx.stats()
-    windows = st_end["windows"] * args.steps          # (tfr_stats.windows counts the last call; every step decodes the same streams)
+    windows = st_end["windows"]                       # (counted since the clear() above: the K synchronised steps)
     rx.clear()
     barrier()
     m1 = sampler.mark() + 1
