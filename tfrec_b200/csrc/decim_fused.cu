@@ -3,7 +3,7 @@
 //
 // decim.cu runs the cascade as one launch per stage with int16 I,Q between the stages in HBM; the /8 cascade then
 // moves 2 + 2*2 + 2*1 + 0.5 = 8.5 bytes per raw sample instead of the 2 it reads and 0.5 it writes.  Here a CTA takes a
-// tile of 4096 raw samples plus the halo the stages need in front of it (18 / 42 / 90 / 186 / 378 raw samples for
+// tile of 4096 (/2, /4) or 2048 (deeper cascades) raw samples plus the halo the stages need in front of it (18 / 42 / 90 / 186 / 378 raw samples for
 // passes 1..5), stages the bytes in shared memory and runs every stage out of shared memory into shared memory: stage
 // outputs stay on chip as exact float pairs (the next stage's FMA operand, no int16 round trip, no conversion), only
 // the last stage writes int16 I,Q.  The arithmetic is the front-end's: every tap product is one round-toward-minus-
@@ -46,8 +46,16 @@ __device__ __forceinline__ f2 fadd2_rn(f2 a, f2 b)
 	return d;
 }
 
-constexpr int kDcTile = 4096;        // raw samples per CTA tile
-constexpr int kDcThreads = 128;
+#ifndef TFR_DC_TILE
+#define TFR_DC_TILE 0
+#endif
+#ifndef TFR_DC_THREADS
+#define TFR_DC_THREADS 128
+#endif
+// raw samples per CTA tile: the deeper cascades want more resident CTAs rather than less halo (measured on B200 for
+// 2^30 samples, tile 4096 -> 2048: /8 1.42 -> 1.58, /16 1.21 -> 1.38, /32 0.96 -> 1.20 TB/s; /2 and /4 lose a little)
+__host__ __device__ constexpr int dc_tile(int passes) { return TFR_DC_TILE ? TFR_DC_TILE : (passes >= 3 ? 2048 : 4096); }
+constexpr int kDcThreads = TFR_DC_THREADS;
 constexpr int kDcR = 8;              // outputs per thread and pass over a stage
 constexpr int kDcHist = 384;         // raw samples of history kept between calls (needs 378 for passes = 5)
 constexpr float kDcAcc0 = 12582912.0f;        // 2^23 + 2^22: accumulator start for float inputs (|sum| < 20k)
@@ -72,7 +80,7 @@ struct DcGeom {
 	int len[P + 1];
 	constexpr DcGeom() : len()
 	{
-		len[P] = dc_round8(kDcTile >> P);
+		len[P] = dc_round8(dc_tile(P) >> P);
 		for (int k = P; k >= 1; k--) len[k - 1] = dc_round8(2 * len[k] + (k == P ? 18 : 6));
 	}
 };
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(kDcThreads) dc_fused_kernel(const uint8_t *__r
 	int back = 0;
 #pragma unroll
 	for (int k = P; k >= 1; k--) back = 2 * back + (k == P ? 18 : 6);
-	const long long r0 = tile * (long long)kDcTile - back;
+	const long long r0 = tile * (long long)dc_tile(P) - back;
 
 	// ---- stage the raw bytes: 16 bytes (8 samples) of shared memory per thread and turn; the tile's first byte is
 	// 4-byte aligned in iq (the halo is an even number of samples) but not 16-byte aligned: four 32-bit loads
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(kDcThreads) dc_fused_kernel(const uint8_t *__r
 	}
 	__syncthreads();
 	// ---- the stages
-	const long long g0 = tile * (long long)(kDcTile >> P);
+	const long long g0 = tile * (long long)(dc_tile(P) >> P);
 	if constexpr (P == 1) {
 		dc_stage<20, WIDE, true, true>(smem + S.off[0], nullptr, G.len[1], out, g0, n_out);
 	} else {
@@ -250,7 +258,7 @@ static cudaError_t dc_launch_p(const uint8_t *iq, const uint8_t *hist, long long
 	constexpr DcSmem<P> S{};
 	const long long n_out = n_pairs >> P;
 	if (n_out <= 0) return cudaSuccess;
-	const long long tiles = (n_out + (kDcTile >> P) - 1) / (kDcTile >> P);
+	const long long tiles = (n_out + (dc_tile(P) >> P) - 1) / (dc_tile(P) >> P);
 	if (tiles > 0x7fffffffll) return cudaErrorInvalidValue;
 	cudaError_t e;
 	if (wide) {

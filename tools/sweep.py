@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import tfrec_b200 as tb
+if os.environ.get("TFR_LIB"):   # experiments: a library built with other compile-time knobs
+    tb.LIB_PATH = os.environ["TFR_LIB"]
 
 
 def decim_sweep(peak):
