@@ -21,14 +21,9 @@ def frame_key(f):
 
 
 def one_case(tb, rng, k):
-    n_blocks = int(rng.integers(12, 72))
-    n = n_blocks * 32768
+    S = int(rng.choice([1, 1, 2, 3]))                       # streams in the handle, each with its own data and oracle
     sigma = float(rng.choice([0.6, 1.0, 2.0, 4.0, 8.0]))
-    sensors = [g.TFA_1, g.TFA_2, g.TFA_3, g.TX22, g.TFA_WHB]
-    rng.shuffle(sensors)
-    period = int(rng.integers(150000, 900000))
     amp = int(rng.choice([12, 30, 60, 100]))
-    iq, bursts = g.fixture_continuous(n, sensors[:int(rng.integers(1, 6))], period, seed=int(rng.integers(1, 1 << 30)), sigma=sigma, amp=amp)
     types = int(rng.choice([0x01, 0x07, 0x0E, 0x2F, 0x21, 0x06]))
     filt = int(rng.integers(0, 2))
     thresh = int(rng.choice([0, 0, 0, 500, 300, 150, 60]))
@@ -36,39 +31,60 @@ def one_case(tb, rng, k):
     in_flight = bool(rng.integers(0, 2))
     os.environ["TFR_BE_SPLIT"] = split
     os.environ["TFR_MIN_CHUNK"] = str(int(rng.choice([1, 4, 8192])))
-    desc = "case %d: blocks %d sigma %.1f amp %d types %#x filter %d thresh %d split %s in_flight %d bursts %d min_chunk %s" % (
-        k, n_blocks, sigma, amp, types, filt, thresh, split, in_flight, len(bursts), os.environ["TFR_MIN_CHUNK"])
+    streams = []
+    for s_ in range(S):
+        n_blocks = int(rng.integers(12, 72))
+        sensors = [g.TFA_1, g.TFA_2, g.TFA_3, g.TX22, g.TFA_WHB]
+        rng.shuffle(sensors)
+        period = int(rng.integers(150000, 900000))
+        iq, bursts = g.fixture_continuous(n_blocks * 32768, sensors[:int(rng.integers(1, 6))], period, seed=int(rng.integers(1, 1 << 30)),
+                                          sigma=sigma, amp=amp)
+        streams.append([iq, n_blocks, 0])
+    desc = "case %d: streams %d blocks %s sigma %.1f amp %d types %#x filter %d thresh %d split %s in_flight %d min_chunk %s" % (
+        k, S, [x[1] for x in streams], sigma, amp, types, filt, thresh, split, in_flight, os.environ["TFR_MIN_CHUNK"])
     if os.environ.get("FUZZ_VERBOSE"):
         print("start", desc, flush=True)
-    rx = tb.Receiver(types=types, filter=filt, thresh=thresh)
-    off = 0
-    while off < n_blocks:
-        nb = int(min(n_blocks - off, rng.integers(1, 24)))
-        rx.submit(0, iq[off * 65536:(off + nb) * 65536].copy())
+    rx = tb.Receiver(types=types, filter=filt, thresh=thresh, n_streams=S)
+    last_nb = [0] * S
+    while any(x[2] < x[1] for x in streams):
+        for s_, x in enumerate(streams):                    # ragged: a stream may sit a call out, lengths differ
+            if x[2] < x[1] and rng.integers(0, 4) > 0:
+                nb = int(min(x[1] - x[2], rng.integers(1, 24)))
+                rx.submit(s_, x[0][x[2] * 65536:(x[2] + nb) * 65536].copy())
+                x[2] += nb
+                last_nb[s_] = nb
+            else:
+                last_nb[s_] = 0 if x[2] < x[1] or last_nb[s_] == 0 else 0
         rx.process()
         if not in_flight:
             rx.sync()
-        off += nb
-    o = ol.Oracle(types=types, filter=filt, thresh=thresh)
-    o.process(iq)
     ok = True
-    if [frame_key(f) for f in rx.frames()] != [frame_key(f) for f in o.frames()]:
-        ok = False
-        print("FRAMES differ:", desc)
-    if [r["exec"] for r in rx.records()] != [r["exec"] for r in o.records()]:
-        ok = False
-        print("RECORDS differ:", desc)
-    if rx.inverted_syncs() != o.inverted_syncs():
-        ok = False
-        print("INVERTED SYNC count differs (%d / %d):" % (rx.inverted_syncs(), o.inverted_syncs()), desc)
-    tr = rx.block_trace(0)
-    if not np.array_equal(tr, o.blocks()[-len(tr):]) or rx.thresh(0) != o.thresh():
-        ok = False
-        print("TRACE / threshold differ:", desc)
+    frames, records = rx.frames(), rx.records()
+    nf = nr = 0
+    for s_, x in enumerate(streams):
+        o = ol.Oracle(types=types, filter=filt, thresh=thresh)
+        o.process(x[0])
+        if [frame_key(f) for f in frames if f["stream"] == s_] != [frame_key(f) for f in o.frames()]:
+            ok = False
+            print("FRAMES differ (stream %d):" % s_, desc)
+        if [r["exec"] for r in records if r["stream"] == s_] != [r["exec"] for r in o.records()]:
+            ok = False
+            print("RECORDS differ (stream %d):" % s_, desc)
+        if rx.inverted_syncs(s_) != o.inverted_syncs():
+            ok = False
+            print("INVERTED SYNC count differs (stream %d: %d / %d):" % (s_, rx.inverted_syncs(s_), o.inverted_syncs()), desc)
+        if rx.thresh(s_) != o.thresh():
+            ok = False
+            print("THRESHOLD differs (stream %d):" % s_, desc)
+        tr = rx.block_trace(s_)                              # of the last call (empty if the stream sat it out)
+        if len(tr) and not np.array_equal(tr, o.blocks()[-len(tr):]):
+            ok = False
+            print("TRACE differs (stream %d):" % s_, desc)
+        nf += len(o.frames())
+        nr += len(o.records())
+        o.close()
     st = rx.stats()
-    nf, nr = len(o.frames()), len(o.records())
     rx.close()
-    o.close()
     print("%s  %s  frames %d records %d screen/dense %d/%d" % ("ok  " if ok else "FAIL", desc, nf, nr, st["screen_blocks"], st["dense_blocks"]),
           flush=True)
     return ok
