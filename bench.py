@@ -41,6 +41,14 @@ SENSORS = (0, 1, 2)            # TFA_1, TFA_2, TFA_3
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "tfrec")
 
 
+def bench_config(args):
+    """the `config` object of the JSON line: the same for both arms (the driver compares them)"""
+    nbytes = args.mib << 20
+    return {"workload": workload_name(args), "streams_per_gpu": args.streams, "bytes_per_stream": nbytes,
+            "l2": "inputs (%.1f GiB per GPU) are far larger than the 126 MB L2" % (args.streams * nbytes / 2**30),
+            "types": "0x%02x" % int(args.types, 16), "thresh": args.thresh}
+
+
 def workload_name(args):
     t = int(args.types, 16)
     mix = "T7 default mix" if t == 7 else "T%x (all five decoders)" % t if t == 0x2f else "T%x" % t
@@ -286,7 +294,7 @@ def main_reference(args):
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * tot / args.steps, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/f64", "data": "synthetic",
            "telegrams_per_s": round(lines / tot, 3),
-           "config": {"workload": workload_name(args), "step": "bounded sample: %d processes x %d MiB" % (cores, sample_mib)},
+           "config": bench_config(args), "reference_step": "bounded sample: %d processes x %d MiB" % (cores, sample_mib),
            "cpu_baseline": {"value": round(v, 2), "unit": "MSamples/s", "cores": cores, "kind": "reference",
                             "sample": "unmodified reference `tfrec -T %x -L`, %d processes x %d MiB per step" % (rtypes, cores, sample_mib)},
            "e2e": {"value": round(v, 2), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -542,9 +550,7 @@ def main():
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_pipe / args.steps, 4),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->i16 (exact fp32 FMA.RM), f64 demod",
            "data": "synthetic",
-           "config": {"workload": workload_name(args), "streams_per_gpu": S, "bytes_per_stream": nbytes,
-                      "l2": "inputs (%.1f GiB per GPU) are far larger than the 126 MB L2" % (S * nbytes / 2**30),
-                      "types": "0x%02x" % types_mask, "thresh": args.thresh},
+           "config": bench_config(args),
            "parity_checked_streams": par_total, "parity_checker": par_checker,
            "telegrams_per_s": round(total_decoded / t_pipe, 2), "telegrams_decoded": int(total_decoded),
            "telegrams_sent": int(total_sent), "wall_ms_per_step": round(1e3 * t_wall / args.steps, 4),
