@@ -1,7 +1,7 @@
 """GPU suite: a short randomised differential run against the oracle (tools/fuzz_gpu.py): random streams, decoder masks,
 filters, thresholds (auto, fixed, inside the noise), call patterns (ragged submits, synchronised or in flight), front-end
 chunking and back-end split modes - frames, records, "Inverted SYNC" count, block trace and threshold all equal the
-oracle's.  (980 cases of the same generator passed on the B200 while the round-2 kernels were written.)"""
+oracle's.  (1980 cases of the same generator passed on the B200 while the round-2 kernels were written.)"""
 import numpy as np
 import pytest
 
