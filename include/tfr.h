@@ -206,6 +206,8 @@ long tfr_dc_process_i16(tfr_dc *h, int16_t *data_iq, int len, int filter);
 int tfr_parse_bytes(tfr_handle *h, int type, const uint8_t *bytes, int len, tfr_frame *frame,
 		    tfr_record *recs, int max_recs);
 
+/* (with the screening front-end active this waits for the calls in flight, like tfr_sync: the screen's counters live on
+ * the device) */
 int tfr_get_stats(tfr_handle *h, tfr_stats *out);
 const char *tfr_last_error(void);
 int tfr_abi_version(void);
