@@ -66,6 +66,111 @@ __device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int t
 
 
 // ------------------------------------------------------------------------------------------------
+// walk_table_kernel: one warp per block of the launch, ahead of thresh2_kernel on the same stream.
+//
+// The walk's chain (threshold -> triggered count -> average -> threshold) is serial over a stream's blocks, but what a
+// block contributes is a function of the block and ITS threshold alone, and the threshold moves in steps of two around
+// where the launch found it.  So every block is evaluated here, in parallel, under the kWalkNT thresholds
+// base + 2k (base = threshold at the start of the launch - kWalkNT): first and last trigger, samples its own triggers
+// cover, and the trigger gaps no shorter than the shortest demodulator timeout - the only triggers besides the first
+// that can open a window (tfa1.cpp:147-148, tfa2.cpp:351-356).  Burst blocks (no complete event list) are scanned
+// here too, by all warps at once instead of by the stream's one.  The walk then costs a table look-up per block and
+// never repeats a block because the threshold stepped.
+//   entry: x = first | last << 16      y = covered | min(gaps, 3) << 16 | has << 31      z, w = the first two gaps,
+//   (trigger before) << 16 | (trigger after)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kWalkSet = 0x80000000u;   // s_trig item: only moves last_trig
+__global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
+{
+	const int stream = blockIdx.y;
+	const int lane = threadIdx.x & 31;
+	const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+	const StreamJob job = p.jobs[stream];
+	if (job.n_blocks == 0) return;
+	const StreamState *st = p.st + stream;
+	const int b0 = (int)st->t2_done;
+	const int b = b0 + i;
+	if (b >= min(b0 + p.n_tiles, (int)job.n_blocks)) return;
+	const DevConfig &cfg = *p.cfg;
+	const int base = st->thresh - kWalkNT;
+	if (i == 0 && lane == 0) p.walk_base[stream] = base;
+	int t_min = 0x7fffffff;
+	for (int d = 0; d < cfg.n_demods; d++) t_min = min(t_min, cfg.d[d].timeout);
+	const int t_max = cfg.t_max;
+	const int kk = lane & (kWalkNT - 1);
+	const int theta = base + 2 * kk;
+	const size_t g = (size_t)job.dec_off + b;
+	const uint32_t n = p.tiles[g].n_trig;
+	int f = -1, l = 0, cov = 0, cend = 0, ng = 0;
+	uint32_t g0 = 0, g1 = 0;
+	// triggers pf .. pl (less than t_max apart, in order after everything seen so far)
+	auto upd = [&](int pf, int pl) {
+		if (f < 0) {
+			f = pf;
+		} else if (pf - l >= t_min) {
+			const uint32_t gp = ((uint32_t)l << 16) | (uint32_t)pf;
+			if (ng == 0) g0 = gp;
+			else if (ng == 1) g1 = gp;
+			ng = min(ng + 1, 3);
+		}
+		const int hi = min(pl + t_max, kBlockDec);
+		cov += max(hi - max(pf, cend), 0);
+		cend = hi;
+		l = pl;
+	};
+	if (n <= (uint32_t)kMaxEvt) {
+		const uint32_t *ev = p.events + g * kMaxEvt;
+		for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+			const uint32_t mine = (e0 + (uint32_t)lane < n) ? ev[e0 + lane] : 0u;
+			const int cnt = (int)min(32u, n - e0);
+			for (int q = 0; q < cnt; q++) {
+				const uint32_t e = __shfl_sync(0xffffffffu, mine, q);
+				if ((int)(e & 0xffff) > theta) upd((int)(e >> 16), (int)(e >> 16));
+			}
+		}
+	} else {
+		// a burst block: every sample that can be a trigger lies in a stored segment
+		const TileDesc &td = p.tiles[g];
+		const uint32_t *d = p.dec + g * kBlockDec;
+		const int ns = td.n_seg;
+		for (int sgi = 0; sgi < ns; sgi++) {
+			const int a = td.seg_start[sgi], e_ = a + td.seg_len[sgi];
+			for (int mb = a; mb < e_; mb += 256) {
+				int pw[8];
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int m = mb + 32 * q + lane;
+					pw[q] = (m < e_) ? pwr_of(d[m]) : (int)0x80000000;
+				}
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int m0 = mb + 32 * q;
+					const unsigned lo = __ballot_sync(0xffffffffu, pw[q] > base);
+					if (!lo) continue;
+					unsigned mm = lo;
+					if (lo != __ballot_sync(0xffffffffu, pw[q] > base + 2 * (kWalkNT - 1))) {
+						for (int k = 1; k < kWalkNT; k++) {
+							const unsigned mk = __ballot_sync(0xffffffffu, pw[q] > base + 2 * k);
+							if (kk == k) mm = mk;
+						}
+					}
+					if (mm) upd(m0 + __ffs(mm) - 1, m0 + 31 - __clz(mm));
+				}
+			}
+		}
+	}
+	if (lane < kWalkNT) {
+		uint4 e;
+		const bool has = f >= 0;
+		e.x = has ? ((uint32_t)f | ((uint32_t)l << 16)) : 0u;
+		e.y = (uint32_t)cov | ((uint32_t)ng << 16) | (has ? 0x80000000u : 0u);
+		e.z = g0;
+		e.w = g1;
+		reinterpret_cast<uint4 *>(p.walk_tab)[g * kWalkNT + lane] = e;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // thresh2_kernel: one warp per stream; reproduces fsk_demod::process' per-block bookkeeping
 // (fm_demod.cpp:51-73) from the front-end's event lists and lists every demodulator's windows.
 //
@@ -84,11 +189,13 @@ __device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int t
 //      bookkeeping (lane d = demod d).
 // Blocks with more than kMaxEvt events (a burst) have no complete list: the warp scans their stored samples.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
+__global__ void __launch_bounds__(32, 1) thresh2_kernel(const BackParams p)
 {
 	const int stream = blockIdx.x;
 	const int lane = threadIdx.x;
-	__shared__ uint32_t s_trig[128];   // the triggers of a chunk's accepted blocks, in order (at most four per block)
+	__shared__ uint32_t s_trig[192];   // the triggers of a chunk's accepted blocks, in order (at most four / six items per block)
+	__shared__ uint4 s_tab[32][kWalkNT + 1];   // the chunk's rows of the walk table (padded: conflict-free 16-byte stores)
+	__shared__ int s_t[32], s_avg[32];         // a pass' triggered counts and running averages
 	if (stream >= p.n_streams) return;
 	const StreamJob job = p.jobs[stream];
 	const DevConfig &cfg = *p.cfg;
@@ -137,6 +244,15 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 	unsigned long long act_lane = 0;
 	const int t_end = min(b0 + p.n_tiles, (int)job.n_blocks);
 	int t_stop = t_end;                   // first block NOT walked (a violated bound stops the walk early)
+	const bool tab = p.walk_tab != nullptr;   // walk_table_kernel ran ahead of this launch
+#ifdef TFR_WALK_PROFILE
+	long long wp_t0 = clock64(), wp_chain = 0, wp_items = 0, wp_feed = 0, wp_stage = 0, wp_old = 0, wp_a;
+	int wp_fast = 0, wp_slow = 0, wp_nitems = 0, wp_ncomplex = 0;
+#define WP(x) x
+#else
+#define WP(x)
+#endif
+	const int tab_base = tab ? p.walk_base[stream] : 0;
 
 	// one trigger at position t (inside the call), in order: the window lists
 	auto win_trigger = [&](uint32_t t) {
@@ -179,19 +295,256 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 		}
 	};
 
+	// lane L's row of the walk table
+	auto fetch_row = [&](int chunk, uint4 (&row)[kWalkNT]) {
+		const int b = chunk + lane;
+		if (b >= b0 && b < t_end) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(p.walk_tab) + ((size_t)job.dec_off + b) * kWalkNT;
+#pragma unroll
+			for (int k = 0; k < kWalkNT; k++) row[k] = src[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < kWalkNT; k++) row[k] = make_uint4(0, 0, 0, 0);
+		}
+	};
+	auto stage_row = [&](const uint4 (&row)[kWalkNT]) {
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < kWalkNT; k++) s_tab[lane][k] = row[k];
+		__syncwarp();
+	};
+	// every trigger of block chunk+j above theta_j to the window lists, in order (all lanes call this together)
+	auto feed_block = [&](int chunk, int j, int theta_j) {
+		const uint32_t base = (uint32_t)(chunk + j) * kBlockDec;
+		const size_t gj = (size_t)job.dec_off + chunk + j;
+		const uint32_t nj = p.tiles[gj].n_trig;
+		if (nj <= (uint32_t)kMaxEvt) {
+			const uint32_t *ev = p.events + gj * kMaxEvt;
+			for (uint32_t e0 = 0; e0 < nj; e0 += 32) {
+				const bool have = e0 + (uint32_t)lane < nj;
+				const uint32_t e = have ? ev[e0 + lane] : 0u;
+				unsigned mask = __ballot_sync(0xffffffffu, have && (int)(e & 0xffff) > theta_j);
+				while (mask) {
+					const int k = __ffs(mask) - 1;
+					mask &= mask - 1;
+					win_trigger(base + (__shfl_sync(0xffffffffu, e, k) >> 16));
+				}
+			}
+		} else {
+			const TileDesc &td = p.tiles[gj];
+			const uint32_t *d = p.dec + gj * kBlockDec;
+			const int ns = td.n_seg;
+			for (int sgi = 0; sgi < ns; sgi++) {
+				const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+				for (int mb = a; mb < b; mb += 256) {
+					uint32_t v[8];
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						const int m = mb + 32 * q + lane;
+						v[q] = (m < b) ? d[m] : 0u;
+					}
+#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						const int m0 = mb + 32 * q, m = m0 + lane;
+						const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(v[q]) > theta_j));
+						if (mask) {
+							const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
+							win_trigger(base + m0 + pf);
+							if (pl != pf) last_trig = base + m0 + pl;   // < 32 apart: they only move the tail
+						}
+					}
+				}
+			}
+		}
+	};
+
 	bool stop = false;
 	int chunk = b0 & ~31;
-	uint32_t n, n_nx;
+	uint32_t n = 0, n_nx = 0;
 	uint4 ea, eb, ec, ed, ea_nx, eb_nx, ec_nx, ed_nx;
-	fetch(chunk, n, ea, eb, ec, ed);
+	ea = eb = ec = ed = ea_nx = eb_nx = ec_nx = ed_nx = make_uint4(0, 0, 0, 0);
+	uint4 row_nx[kWalkNT];
+	if (tab) {
+		fetch_row(chunk, row_nx);
+		stage_row(row_nx);
+	} else {
+		fetch(chunk, n, ea, eb, ec, ed);
+	}
 	int pos = b0;
 	while (pos < t_end && !stop) {
-		fetch(chunk + 32, n_nx, ea_nx, eb_nx, ec_nx, ed_nx);   // in flight while this chunk is walked
+		// the next chunk's inputs are in flight while this chunk is walked
+		if (tab) fetch_row(chunk + 32, row_nx);
+		else fetch(chunk + 32, n_nx, ea_nx, eb_nx, ec_nx, ed_nx);
+		bool have_ev = !tab;
 		const int jend = min(32, t_end - chunk);
 		const size_t g = (size_t)job.dec_off + chunk + lane;
 		while (pos < chunk + jend && !stop) {
-			const int theta = thresh;
 			const int j0 = pos - chunk;
+			if (tab && (unsigned)((thresh - tab_base) >> 1) < (unsigned)kWalkNT && !(mode == 1 && thresh < thresh_lo)) {
+				// ---- from the table: every lane looks its block up under the threshold in force (a step of the threshold
+				// ends the pass, the next one costs a look-up again); on the serial chain are two instructions per block
+				WP(wp_a = clock64(); wp_fast++;)
+				const int k = (thresh - tab_base) >> 1;
+				const bool active = lane >= j0 && lane < jend;
+				const uint2 e = active ? *reinterpret_cast<const uint2 *>(&s_tab[lane][k]) : make_uint2(0u, 0u);
+				const bool has = (e.y >> 31) != 0;
+				const int f = (int)(e.x & 0xffff), l = (int)(e.x >> 16);
+				const int out = has ? max(l + t_max - kBlockDec, 0) : 0;
+				int c_in = __shfl_up_sync(0xffffffffu, out, 1);
+				if (lane == j0) c_in = c;
+				const int trig = (int)(e.y & 0xffff) + (has ? min(c_in, f) : c_in);
+				s_t[lane] = trig;
+				__syncwarp();
+				const int used = thresh;
+				int acc_end = jend;
+				for (int j = j0; j < jend;) {
+					// up to the next threshold decision (every 4th block, fm_demod.cpp:58-73)
+					const int nstep = min((mode == 1) ? 4 - (runs & 3) : 4, jend - j);
+					const int t0 = s_t[j], t1 = s_t[min(j + 1, 31)], t2 = s_t[min(j + 2, 31)], t3 = s_t[min(j + 3, 31)];
+					avg = (int)((uint32_t)(31 * avg + t0) >> 5);   // (both are >= 0: the same as the reference's signed /32)
+					s_avg[j] = avg;
+					if (nstep > 1) { avg = (int)((uint32_t)(31 * avg + t1) >> 5); s_avg[j + 1] = avg; }
+					if (nstep > 2) { avg = (int)((uint32_t)(31 * avg + t2) >> 5); s_avg[j + 2] = avg; }
+					if (nstep > 3) { avg = (int)((uint32_t)(31 * avg + t3) >> 5); s_avg[j + 3] = avg; }
+					runs += nstep;
+					j += nstep;
+					if (mode == 1 && (runs & 3) == 0) {
+						if (avg >= kIdxPerBlock / 32) thresh += 2;
+						else if (avg <= kIdxPerBlock / 64 && thresh > 50) thresh -= 2;
+						if (thresh != used) { acc_end = j; break; }
+					}
+				}
+				__syncwarp();
+				const bool accepted = lane >= j0 && lane < acc_end;
+				if (accepted) {
+					BlockTrace bt = { used, trig, s_avg[lane] };
+					p.trace[g] = bt;
+					act_lane += (unsigned long long)trig;
+				}
+				c = __shfl_sync(0xffffffffu, out, acc_end - 1);
+				WP(wp_chain += clock64() - wp_a; wp_a = clock64();)
+				// ---- window lists.  Per block: its first trigger, the gaps that can open a window, its last trigger, as
+				// items in shared memory (T: a trigger, S: only moves last_trig); then lanes = items, demodulator by
+				// demodulator: which items open a window is a ballot, the windows' running sample count a scan
+				const bool acc_has = accepted && has;
+				unsigned wm = __ballot_sync(0xffffffffu, acc_has);
+				const int ngl = acc_has ? (int)((e.y >> 16) & 3u) : 0;
+				if (wm) {
+					// a block with more gaps than the table holds feeds all its triggers one by one, in its place
+					unsigned cm = __ballot_sync(0xffffffffu, ngl == 3);
+					const int mine = (acc_has && ngl < 3) ? 1 + 2 * ngl + (l != f ? 1 : 0) : 0;
+					int incl = mine;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const int o = __shfl_up_sync(0xffffffffu, incl, d);
+						if (lane >= d) incl += o;
+					}
+					const int total = __shfl_sync(0xffffffffu, incl, 31);
+					const uint32_t base = (uint32_t)(chunk + lane) * kBlockDec;
+					const int at0 = incl - mine;
+					int at = at0;
+					if (mine) {
+						s_trig[at++] = base + (uint32_t)f;
+						if (ngl > 0) {
+							const uint32_t gz = s_tab[lane][k].z;
+							s_trig[at++] = kWalkSet | (base + (gz >> 16));
+							s_trig[at++] = base + (gz & 0xffff);
+						}
+						if (ngl > 1) {
+							const uint32_t gw = s_tab[lane][k].w;
+							s_trig[at++] = kWalkSet | (base + (gw >> 16));
+							s_trig[at++] = base + (gw & 0xffff);
+						}
+						if (l != f) s_trig[at++] = kWalkSet | (base + (uint32_t)l);
+					}
+					__syncwarp();
+					int cur = 0;
+					for (;;) {
+						const int jc = cm ? __ffs(cm) - 1 : 0;
+						const int seg_end = cm ? __shfl_sync(0xffffffffu, at0, jc) : total;
+						for (; cur < seg_end; cur += 32) {
+							const int cntb = min(32, seg_end - cur);
+							const bool valid = lane < cntb;
+							const uint32_t v = valid ? s_trig[cur + lane] : 0u;
+							const bool is_t = valid && !(v & kWalkSet);
+							const uint32_t t = v & ~kWalkSet;
+							const uint32_t pv = __shfl_up_sync(0xffffffffu, t, 1);
+							const long long prev = (lane == 0) ? last_trig : (long long)pv;
+							const unsigned tm = __ballot_sync(0xffffffffu, is_t);
+							for (int d = 0; d < nd; d++) {
+								const int T_dd = __shfl_sync(0xffffffffu, T_d, d);
+								const uint32_t open_d = __shfl_sync(0xffffffffu, open, d);
+								unsigned m = __ballot_sync(0xffffffffu, is_t && ((long long)t - prev >= (long long)T_dd));
+								if (!open_d) m |= tm & (0u - tm);
+								if (!m) continue;
+								const uint32_t nwin_d = __shfl_sync(0xffffffffu, n_win, d);
+								const uint32_t cum_d = __shfl_sync(0xffffffffu, cum, d);
+								const uint32_t ostart_d = __shfl_sync(0xffffffffu, open_start, d);
+								const unsigned pm = m & ((1u << lane) - 1u);
+								const bool opens = (m >> lane) & 1u;
+								const uint32_t t_before = __shfl_sync(0xffffffffu, t, pm ? 31 - __clz(pm) : 0);
+								const bool had_open = pm ? true : (open_d != 0);
+								const uint32_t os_prev = pm ? t_before : ostart_d;
+								const uint32_t end = (uint32_t)(prev + (long long)T_dd - 1);   // of the window this item's opening closes
+								uint32_t len = (opens && had_open) ? end - os_prev + 1u : 0u;
+#pragma unroll
+								for (int q = 1; q < 32; q <<= 1) {
+									const uint32_t o = __shfl_up_sync(0xffffffffu, len, q);
+									if (lane >= q) len += o;
+								}
+								// a window opened here is closed by the next opening of the batch, if there is one (every lane writes
+								// its own entry whole; only the batch's first opening touches an entry that was there before)
+								const unsigned nm = m & ~((2u << lane) - 1u);
+								const uint32_t end_next = __shfl_sync(0xffffffffu, end, nm ? __ffs(nm) - 1 : 0);
+								WinEntry *wd = p.wins + job.win_off + (size_t)d * job.win_cap;
+								if (opens) {
+									const uint32_t idx = nwin_d + (uint32_t)__popc(pm);
+									if (!pm && had_open && idx - 1u < job.win_cap) wd[idx - 1u].end = end;
+									if (idx < job.win_cap) {
+										WinEntry we = { t, nm ? end_next : 0xffffffffu, cum_d + len, 0u };
+										wd[idx] = we;
+									} else {
+										p.counters->overflow = 1;
+									}
+								}
+								const int last_o = 31 - __clz(m);
+								const uint32_t cum_new = cum_d + __shfl_sync(0xffffffffu, len, last_o);
+								const uint32_t os_new = __shfl_sync(0xffffffffu, t, last_o);
+								if (lane == d) {
+									const uint32_t n_new = nwin_d + (uint32_t)__popc(m);
+									cum = cum_new;
+									open = 1;
+									if (n_new <= job.win_cap) {
+										n_win = n_new;
+										open_start = os_new;
+									} else {
+										// (the list is full: the call reports TFR_E_OVERFLOW, what follows is truncated)
+										n_win = job.win_cap;
+									}
+								}
+							}
+							last_trig = (long long)__shfl_sync(0xffffffffu, t, cntb - 1);
+						}
+						cur = seg_end;
+						if (!cm) break;
+						cm &= cm - 1;
+						WP(long long wp_b = clock64(); wp_ncomplex++;)
+						feed_block(chunk, jc, used);
+						WP(wp_feed += clock64() - wp_b;)
+					}
+					__syncwarp();
+					WP(wp_nitems += total;)
+				}
+				WP(wp_items += clock64() - wp_a;)
+				pos = chunk + acc_end;
+				continue;
+			}
+			if (!have_ev) {
+				fetch(chunk, n, ea, eb, ec, ed);
+				have_ev = true;
+			}
+			WP(wp_slow++; wp_a = clock64();)
+			const int theta = thresh;
 			const bool active = lane >= j0 && lane < jend;
 			// ---- 1. own block against theta
 			int f = -1, l = -1, cov = 0, cnt = 0, cend = 0;
@@ -342,52 +695,16 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 				const uint32_t q0 = __shfl_sync(0xffffffffu, tp0, j), q1 = __shfl_sync(0xffffffffu, tp1, j);
 				const uint32_t q2 = __shfl_sync(0xffffffffu, tp2, j), q3 = __shfl_sync(0xffffffffu, tp3, j);
 				const uint32_t base = (uint32_t)(chunk + j) * kBlockDec;
-				const size_t gj = (size_t)job.dec_off + chunk + j;
 				if (cj <= 4) {
 					win_trigger(base + q0);
 					if (cj > 1) win_trigger(base + q1);
 					if (cj > 2) win_trigger(base + q2);
 					if (cj > 3) win_trigger(base + q3);
-				} else if (cj < 1000) {
-					const uint32_t nj = __shfl_sync(0xffffffffu, n, j);
-					const uint32_t *ev = p.events + gj * kMaxEvt;
-					for (uint32_t e0 = 0; e0 < nj; e0 += 32) {
-						const bool have = e0 + (uint32_t)lane < nj;
-						const uint32_t e = have ? ev[e0 + lane] : 0u;
-						unsigned mask = __ballot_sync(0xffffffffu, have && (int)(e & 0xffff) > theta);
-						while (mask) {
-							const int k = __ffs(mask) - 1;
-							mask &= mask - 1;
-							win_trigger(base + (__shfl_sync(0xffffffffu, e, k) >> 16));
-						}
-					}
 				} else {
-					const TileDesc &td = p.tiles[gj];
-					const uint32_t *d = p.dec + gj * kBlockDec;
-					const int ns = td.n_seg;
-					for (int sgi = 0; sgi < ns; sgi++) {
-						const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
-						for (int mb = a; mb < b; mb += 256) {
-							uint32_t v[8];
-#pragma unroll
-							for (int q = 0; q < 8; q++) {
-								const int m = mb + 32 * q + lane;
-								v[q] = (m < b) ? d[m] : 0u;
-							}
-#pragma unroll
-							for (int q = 0; q < 8; q++) {
-								const int m0 = mb + 32 * q, m = m0 + lane;
-								const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(v[q]) > theta));
-								if (mask) {
-									const int pf = __ffs(mask) - 1, pl = 31 - __clz(mask);
-									win_trigger(base + m0 + pf);
-									if (pl != pf) last_trig = base + m0 + pl;   // < 32 apart: they only move the tail
-								}
-							}
-						}
-					}
+					feed_block(chunk, j, theta);
 				}
 			}
+			WP(wp_old += clock64() - wp_a;)
 			pos = chunk + acc_end;
 		}
 		if (stop) {
@@ -395,13 +712,24 @@ __global__ void __launch_bounds__(32) thresh2_kernel(const BackParams p)
 			break;
 		}
 		chunk += 32;
-		n = n_nx;
-		ea = ea_nx;
-		eb = eb_nx;
-		ec = ec_nx;
-		ed = ed_nx;
+		if (tab) {
+			WP(wp_a = clock64();)
+			stage_row(row_nx);
+			WP(wp_stage += clock64() - wp_a;)
+		} else {
+			n = n_nx;
+			ea = ea_nx;
+			eb = eb_nx;
+			ec = ec_nx;
+			ed = ed_nx;
+		}
 	}
 
+#ifdef TFR_WALK_PROFILE
+	if (stream == 0 && lane == 0)
+		printf("walk: blocks %d total %lld chain %lld items %lld (feed %lld) stage %lld old %lld | passes fast %d slow %d items %d complex %d\n",
+		       t_end - b0, clock64() - wp_t0, wp_chain, wp_items, wp_feed, wp_stage, wp_old, wp_fast, wp_slow, wp_nitems, wp_ncomplex);
+#endif
 	const bool finished = (t_stop == (int)job.n_blocks);
 	if (finished && lane < nd) {
 		uint32_t cont = 0;
@@ -2367,6 +2695,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 {
+	if (p.walk_tab && p.n_tiles > 0) walk_table_kernel<<<dim3((p.n_tiles + 3) / 4, p.n_streams), 128, 0, s>>>(p);
 	thresh2_kernel<<<p.n_streams, 32, 0, s>>>(p);
 	return cudaGetLastError();
 }

@@ -296,7 +296,11 @@ struct BackParams {
 	WinCount *partcnt;       // [kMaxParts][n_streams]
 	int part_idx;            // thresh2_kernel: which row of partcnt this launch fills, -1 none
 	int part_lo, part_hi;    // window kernels: rows of partcnt bounding the windows of this launch (lo -1: from window 0, hi -1: to the end)
+	// threshold-walk table (walk_table_kernel, null: the walk evaluates the blocks' event lists itself)
+	uint32_t *walk_tab;      // [gtile][kWalkNT][4]: what the walk needs of a block under threshold walk_base + 2k
+	int32_t *walk_base;      // [stream]: threshold of column 0, written by the table kernel of the same launch
 };
+constexpr int kWalkNT = 16;  // thresholds tabulated per block: the one at the start of the launch -16 .. +14 in steps of two
 constexpr int kMaxParts = 8;
 // partcnt row kLateRow: the leading windows of every (stream, demodulator) that depend on the previous call's final state -
 // window 0 (true carried state, the sample before position 0) and the windows whose filter warm-up reaches back to it

@@ -1,6 +1,7 @@
 import sys, os
 sys.path.insert(0, "/root/repo")
 import torch, tfrec_b200 as tb
+if os.environ.get("TFR_LIB"): tb.LIB_PATH = os.environ["TFR_LIB"]
 n = 1 << 30
 g = torch.Generator(device="cuda"); g.manual_seed(5)
 buf = (torch.randn(2 * n, device="cuda", generator=g) * 4.0 + 128.0).round_().clamp_(0, 255).to(torch.uint8)
