@@ -373,6 +373,38 @@ def test_front_end_chunks_and_back_end_parts(tb, hot_fixture, monkeypatch, parts
     rx.close()
 
 
+@pytest.mark.parametrize("walk", ["cta64", "cta256", "warp", "lists"])
+def test_threshold_walk_variants(tb, hot_fixture, monkeypatch, walk):
+    """The threshold walk from the per-block table (walk_table_kernel) by a CTA per stream of two or eight warps
+    (walk_cta_kernel), by a warp per stream (thresh2_kernel), and from the event lists: the same block trace, thresholds,
+    windows (hence frames and records) as the oracle, over several launches per call (TFR_MIN_CHUNK), two calls, signals
+    that push the threshold out of the table's range, and a start-up transient (noise far below the start threshold)."""
+    env = {"cta64": {"TFR_WALK_CT": "64"}, "cta256": {"TFR_WALK_CT": "256"}, "warp": {"TFR_WALK": "warp"},
+           "lists": {"TFR_WALK_TAB": "0"}}[walk]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("TFR_MIN_CHUNK", "24")
+    names = ["mixed5", "cont_noisy", "strong_t7"]
+    iqs = [hot_fixture(n) for n in names] + [g.make_stream(6 * 1024 * 1024, [], seed=33, sigma=4.0)]
+    rx = tb.Receiver(types=0x0F, thresh=0, n_streams=len(iqs))
+    nb = min(x.size for x in iqs) // 65536
+    half = (nb // 2) * 65536
+    for lo, hi in ((0, half), (half, nb * 65536)):
+        for s, iq in enumerate(iqs):
+            rx.submit(s, iq[lo:hi].copy())
+        rx.process()
+    frames, records = rx.frames(), rx.records()
+    for s, iq in enumerate(iqs):
+        o = ol.Oracle(types=0x0F)
+        o.process(iq[:half])
+        o.process(iq[half:nb * 65536])
+        assert np.array_equal(rx.block_trace(s), o.blocks()[half // 65536:]), (walk, s)
+        assert [frame_key(f) for f in frames if f["stream"] == s] == [frame_key(f) for f in o.frames()], (walk, s)
+        assert [r["exec"] for r in records if r["stream"] == s] == [r["exec"] for r in o.records()], (walk, s)
+        assert rx.thresh(s) == o.thresh()
+    rx.close()
+
+
 @pytest.mark.parametrize("mode", ["0", "2"])
 def test_split_back_end_across_calls(tb, hot_fixture, monkeypatch, mode):
     """TFR_BE_SPLIT=2: every call's decwin, fm_dev and the windows that do not need the previous call's final state run on

@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "demod_dev.cuh"
 
@@ -80,6 +81,8 @@ __device__ __forceinline__ bool chain_head(const WinEntry *wl, uint32_t w, int t
 //   (trigger before) << 16 | (trigger after)
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kWalkSet = 0x80000000u;   // s_trig item: only moves last_trig
+// thresholds above the table's last column at which walk_table_kernel also evaluates a block (lanes 17..31)
+__device__ const int kWalkLadder[15] = { 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024 };
 __global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
 {
 	const int stream = blockIdx.y;
@@ -97,12 +100,23 @@ __global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
 	int t_min = 0x7fffffff;
 	for (int d = 0; d < cfg.n_demods; d++) t_min = min(t_min, cfg.d[d].timeout);
 	const int t_max = cfg.t_max;
-	const int kk = lane & (kWalkNT - 1);
-	const int theta = base + 2 * kk;
+	// Lane 16 evaluates the block under the lowest threshold its lists are complete for, lanes 17..31 under a ladder of
+	// thresholds above the table.  The triggers above a threshold shrink as it rises, so an entry that is the same at
+	// both ends of a range of thresholds holds for the whole range (first/last trigger and coverage are monotone in the
+	// set; a gap of the middle set spans no trigger of the larger one and is one of the smaller one's): bit 30 of column
+	// 0 says so for the range below the table, bits 26..29 of column 15 hold the number of ladder steps its entry stays
+	// the same for, and the walk follows the threshold out of the table that far - which it does after every telegram.
+	const int mode = st->thresh_mode;
+	const int theta_lo = (mode == 1) ? (p.margin ? st->thresh - p.margin : st->spec_lo) : st->thresh;
+	const int theta_top = base + 2 * (kWalkNT - 1);
+	const int theta_hi = theta_top + kWalkLadder[14];
+	const int kk = lane;
+	const int theta = (lane < kWalkNT) ? base + 2 * lane : (lane == kWalkNT ? theta_lo : theta_top + kWalkLadder[lane - kWalkNT - 1]);
+	const int theta_min = min(base, theta_lo);
 	const size_t g = (size_t)job.dec_off + b;
 	const uint32_t n = p.tiles[g].n_trig;
 	int f = -1, l = 0, cov = 0, cend = 0, ng = 0;
-	uint32_t g0 = 0, g1 = 0;
+	uint32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
 	// triggers pf .. pl (less than t_max apart, in order after everything seen so far)
 	auto upd = [&](int pf, int pl) {
 		if (f < 0) {
@@ -111,7 +125,9 @@ __global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
 			const uint32_t gp = ((uint32_t)l << 16) | (uint32_t)pf;
 			if (ng == 0) g0 = gp;
 			else if (ng == 1) g1 = gp;
-			ng = min(ng + 1, 3);
+			else if (ng == 2) g2 = gp;
+			else if (ng == 3) g3 = gp;
+			ng = min(ng + 1, 5);
 		}
 		const int hi = min(pl + t_max, kBlockDec);
 		cov += max(hi - max(pf, cend), 0);
@@ -145,12 +161,12 @@ __global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
 #pragma unroll
 				for (int q = 0; q < 8; q++) {
 					const int m0 = mb + 32 * q;
-					const unsigned lo = __ballot_sync(0xffffffffu, pw[q] > base);
+					const unsigned lo = __ballot_sync(0xffffffffu, pw[q] > theta_min);
 					if (!lo) continue;
 					unsigned mm = lo;
-					if (lo != __ballot_sync(0xffffffffu, pw[q] > base + 2 * (kWalkNT - 1))) {
-						for (int k = 1; k < kWalkNT; k++) {
-							const unsigned mk = __ballot_sync(0xffffffffu, pw[q] > base + 2 * k);
+					if (lo != __ballot_sync(0xffffffffu, pw[q] > theta_hi) || p.walk_dbg == 4) {
+						for (int k = 0; k < 32; k++) {
+							const unsigned mk = __ballot_sync(0xffffffffu, pw[q] > __shfl_sync(0xffffffffu, theta, k));
 							if (kk == k) mm = mk;
 						}
 					}
@@ -159,14 +175,29 @@ __global__ void __launch_bounds__(128) walk_table_kernel(const BackParams p)
 			}
 		}
 	}
+	const bool has = f >= 0;
+	const uint32_t fl = has ? ((uint32_t)f | ((uint32_t)l << 16)) : 0u;
+	uint32_t cv = (uint32_t)cov | ((uint32_t)ng << 16) | (has ? 0x80000000u : 0u);
+	if (p.walk_gap) {
+		// lane 16 against column 0, lanes 17.. against column 15
+		const int ref = (lane <= kWalkNT) ? 0 : kWalkNT - 1;
+		// (every shuffle by every lane: no short-circuit between them)
+		const uint32_t r_fl = __shfl_sync(0xffffffffu, fl, ref), r_cv = __shfl_sync(0xffffffffu, cv, ref);
+		const uint32_t r_g0 = __shfl_sync(0xffffffffu, g0, ref), r_g1 = __shfl_sync(0xffffffffu, g1, ref);
+		const uint32_t r_g2 = __shfl_sync(0xffffffffu, g2, ref), r_g3 = __shfl_sync(0xffffffffu, g3, ref);
+		const bool same = (r_fl == fl) & (r_cv == cv) & (r_g0 == g0) & (r_g1 == g1) & (r_g2 == g2) & (r_g3 == g3);
+		const unsigned eq = __ballot_sync(0xffffffffu, same);
+		if (lane == 0 && ((eq >> kWalkNT) & 1u) && p.walk_dbg < 2) cv |= 0x40000000u;
+		if (lane == kWalkNT - 1 && (p.walk_dbg < 1 || p.walk_dbg == 4 || p.walk_dbg == 32 || (p.walk_dbg == 8 && n <= (uint32_t)kMaxEvt) || (p.walk_dbg == 16 && n > (uint32_t)kMaxEvt))) cv |= (uint32_t)(__ffs(~(eq >> (kWalkNT + 1))) - 1) << 26;   // (15 lanes: at most 15)
+	}
 	if (lane < kWalkNT) {
-		uint4 e;
-		const bool has = f >= 0;
-		e.x = has ? ((uint32_t)f | ((uint32_t)l << 16)) : 0u;
-		e.y = (uint32_t)cov | ((uint32_t)ng << 16) | (has ? 0x80000000u : 0u);
-		e.z = g0;
-		e.w = g1;
-		reinterpret_cast<uint4 *>(p.walk_tab)[g * kWalkNT + lane] = e;
+		if (p.walk_gap) {   // for walk_cta_kernel: the chain's half apart (it is staged in shared memory), four gaps, 5 = more
+			reinterpret_cast<uint2 *>(p.walk_tab)[g * kWalkNT + lane] = make_uint2(fl, cv);
+			reinterpret_cast<uint4 *>(p.walk_gap)[g * kWalkNT + lane] = make_uint4(g0, g1, g2, g3);
+		} else {            // for thresh2_kernel: two gaps, 3 = more
+			reinterpret_cast<uint4 *>(p.walk_tab)[g * kWalkNT + lane] =
+				make_uint4(fl, (uint32_t)cov | ((uint32_t)min(ng, 3) << 16) | (has ? 0x80000000u : 0u), g0, g1);
+		}
 	}
 }
 
@@ -790,6 +821,617 @@ __global__ void __launch_bounds__(32, 1) thresh2_kernel(const BackParams p)
 		st->t2_done = (uint32_t)t_stop;   // == n_blocks when finished; submit_epilogue_kernel clears it for the next call
 		if (p.progress) p.progress[stream] = (uint32_t)t_stop;
 		if (act_lane) atomicAdd(&p.counters->active_samples, act_lane);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// walk_cta_kernel: the walk from the table (walk_table_kernel) with one CTA of eight warps per stream.
+//
+// thresh2_kernel is one warp, and a lone warp pays a pipeline latency for every instruction: even from the table it
+// spends ~250 cycles per block.  Here a super-chunk of 256 blocks is taken at once, thread = block:
+//   A  all threads look their block up under the threshold in force and derive its triggered count (the coverage
+//      carried in from the block before is one shared-memory read away)
+//   B  warp 0 runs the chain  avg = (31 avg + triggered) / 32, threshold step every 4th block  (fm_demod.cpp:58-73)
+//      over the counts until the threshold moves; the blocks up to there are accepted, the rest is looked up again
+//   C  every accepted block turns its table entry into items - T: a trigger that may open a window, S: only moves
+//      last_trig - packed in order by a block-wide scan (a block with more gaps than the table holds walks its own
+//      event list)
+//   D  warp d keeps demodulator d's window list: lanes = items, the openings are a ballot, the windows' running
+//      sample counts a scan.
+// Where the walk cannot go on from the table (the front-end's bound fails, or the threshold left the table's range)
+// it stops like thresh2_kernel does; the next launch, or the host's epochs, carry on from there.
+// ------------------------------------------------------------------------------------------------
+// CT = threads = blocks of a super-chunk.  64 (two warps, <= 176 registers) fits beside two front-end CTAs on an SM, which
+// leave 11.7 k registers and 40 KB of shared memory - a walk that has to wait for a whole SM stalls the front-end launches
+// queued behind it; 256 is for calls of few streams, where the SMs are not the constraint and a demodulator gets a warp.
+struct WalkDem { uint32_t n_win, cum, open, open_start; };
+
+template <int CT>
+__global__ void __launch_bounds__(CT, 1) walk_cta_kernel(const BackParams p)
+{
+	constexpr int kWalkCta = CT, kWalkItems = CT * 8;
+	const int stream = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ uint2 s_tab[kWalkCta][kWalkNT + 1];   // (padded: conflict-free 8-byte accesses along a column)
+	__shared__ int s_t[kWalkCta], s_out[kWalkCta], s_avg[kWalkCta];
+	__shared__ uint32_t s_items[kWalkItems];
+	__shared__ int s_scan[kWalkCta / 32];
+	__shared__ int s_ctl[8];
+	__shared__ WalkDem s_dem[kMaxDemods];
+	if (stream >= p.n_streams) return;
+	const StreamJob job = p.jobs[stream];
+	const DevConfig &cfg = *p.cfg;
+	const int nd = cfg.n_demods;
+	WinCount *part = (p.part_idx >= 0) ? p.partcnt + (size_t)p.part_idx * p.n_streams + stream : nullptr;
+	if (job.n_blocks == 0) {
+		if (part && tid < nd) part->n[tid] = 0;
+		return;
+	}
+	StreamState *st = p.st + stream;
+	const int b0 = (int)st->t2_done;
+	if (b0 >= (int)job.n_blocks) {   // this stream finished in an earlier launch of the call: every window is final
+		if (part && tid < nd) part->n[tid] = p.wincnt[stream].n[tid];
+		return;
+	}
+	const int t_max = cfg.t_max;
+	const uint32_t call_len = job.n_blocks * (uint32_t)kBlockDec;
+	int t_min = 0x7fffffff;
+	for (int d = 0; d < nd; d++) t_min = min(t_min, cfg.d[d].timeout);
+
+	int thresh = st->thresh, avg = st->triggered_avg, runs = st->runs;
+	int c = st->any_timeout;
+	const int mode = st->thresh_mode;
+	const int thresh_lo = (mode == 1) ? (p.margin ? thresh - p.margin : st->spec_lo) : thresh;
+	long long last_trig;
+	// the carried window state, by thread d as in thresh2_kernel; warp d works on it below
+	const int T_d = (tid < nd) ? cfg.d[tid].timeout : 0x7fffffff;
+	uint32_t n_win = 0, cum = 0, open = 0, open_start = 0;
+	WinEntry *wl = (tid < nd) ? p.wins + job.win_off + (size_t)tid * job.win_cap : nullptr;
+	if (b0 == 0) {
+		last_trig = -(long long)st->trig_age;
+		if (tid < nd && st->win_cont[tid]) {   // a window was open when the previous call ended
+			WinEntry e = { 0u, 0xffffffffu, 0u, kWinCont };
+			wl[0] = e;
+			n_win = 1;
+			open = 1;
+		}
+	} else {
+		last_trig = st->call_last_trig;
+		if (tid < nd) {
+			n_win = st->win_n[tid];
+			cum = st->win_cum[tid];
+			open = st->win_open[tid];
+			if (open && n_win) open_start = wl[n_win - 1].start;
+		}
+	}
+	if (tid < nd) {
+		WalkDem wdm = { n_win, cum, open, open_start };
+		s_dem[tid] = wdm;
+	}
+#ifdef TFR_WALK_PROFILE
+	if (tid == 0) s_ctl[6] = s_ctl[7] = 0;
+#endif
+	__syncthreads();
+	unsigned long long act = 0;
+	const int t_end = min(b0 + p.n_tiles, (int)job.n_blocks);
+	int t_stop = t_end;
+	const int tab_base = p.walk_base[stream];
+	const uint2 *chain_tab = reinterpret_cast<const uint2 *>(p.walk_tab);
+	const uint4 *gap_tab = reinterpret_cast<const uint4 *>(p.walk_gap);
+#ifdef TFR_WALK_PROFILE
+	long long wp_t0 = clock64(), wp_ab = 0, wp_c = 0, wp_d = 0, wp_a;
+	int wp_pass = 0, wp_nitems = 0, wp_ncomplex = 0;
+#endif
+
+	auto fetch_row = [&](int sc, uint4 (&row)[kWalkNT / 2]) {
+		const int b = sc + tid;
+		if (b >= b0 && b < t_end) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(chain_tab + ((size_t)job.dec_off + b) * kWalkNT);
+#pragma unroll
+			for (int k = 0; k < kWalkNT / 2; k++) row[k] = src[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < kWalkNT / 2; k++) row[k] = make_uint4(0, 0, 0, 0);
+		}
+	};
+	auto stage_row = [&](const uint4 (&row)[kWalkNT / 2]) {
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < kWalkNT / 2; k++) {
+			s_tab[tid][2 * k] = make_uint2(row[k].x, row[k].y);
+			s_tab[tid][2 * k + 1] = make_uint2(row[k].z, row[k].w);
+		}
+		__syncthreads();
+	};
+	// a block's table entry under a threshold the table does not hold (the threshold drifted more than eight steps
+	// inside one launch: start-up transients), from the block's own event list - what walk_table_kernel does, by one thread
+	auto eval_block = [&](size_t gb, int theta_b, uint2 &e, uint4 &gp) {
+		int f = -1, l = 0, cov = 0, cend = 0, ng = 0;
+		gp = make_uint4(0, 0, 0, 0);
+		auto upd = [&](int t) {
+			if (f < 0) {
+				f = t;
+			} else if (t - l >= t_min) {
+				const uint32_t q = ((uint32_t)l << 16) | (uint32_t)t;
+				if (ng == 0) gp.x = q;
+				else if (ng == 1) gp.y = q;
+				else if (ng == 2) gp.z = q;
+				else if (ng == 3) gp.w = q;
+				ng = min(ng + 1, 5);
+			}
+			const int hi = min(t + t_max, kBlockDec);
+			cov += max(hi - max(t, cend), 0);
+			cend = hi;
+			l = t;
+		};
+		const uint32_t nj = p.tiles[gb].n_trig;
+		if (nj <= (uint32_t)kMaxEvt) {
+			const uint32_t *ev = p.events + gb * kMaxEvt;
+			for (uint32_t q = 0; q < nj; q++) {
+				const uint32_t v = ev[q];
+				if ((int)(v & 0xffff) > theta_b) upd((int)(v >> 16));
+			}
+		} else {
+			const TileDesc &td = p.tiles[gb];
+			const uint32_t *d = p.dec + gb * kBlockDec;
+			for (int sgi = 0; sgi < (int)td.n_seg; sgi++) {
+				const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+				for (int m = a; m < b; m++)
+					if (pwr_of(d[m]) > theta_b) upd(m);
+			}
+		}
+		const bool has = f >= 0;
+		e.x = has ? ((uint32_t)f | ((uint32_t)l << 16)) : 0u;
+		e.y = (uint32_t)cov | ((uint32_t)ng << 16) | (has ? 0x80000000u : 0u);
+	};
+	// the same for a burst block (no complete list: its stored samples are scanned), by all lanes of a warp together
+	auto eval_burst_warp = [&](size_t gb, int theta_b, uint2 &e, uint4 &gp) {
+		int f = -1, l = 0, cov = 0, cend = 0, ng = 0;
+		gp = make_uint4(0, 0, 0, 0);
+		const TileDesc &td = p.tiles[gb];
+		const uint32_t *d = p.dec + gb * kBlockDec;
+		const int ns = td.n_seg;
+		for (int sgi = 0; sgi < ns; sgi++) {
+			const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+			for (int mb = a; mb < b; mb += 256) {
+				uint32_t v[8];
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int m = mb + 32 * q + lane;
+					v[q] = (m < b) ? d[m] : 0u;
+				}
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int m0 = mb + 32 * q, m = m0 + lane;
+					const unsigned mask = __ballot_sync(0xffffffffu, (m < b) && (pwr_of(v[q]) > theta_b));
+					if (mask) {
+						const int pf = m0 + __ffs(mask) - 1, pl = m0 + 31 - __clz(mask);   // (< 32 apart: no gap in between)
+						if (f < 0) {
+							f = pf;
+						} else if (pf - l >= t_min) {
+							const uint32_t qg = ((uint32_t)l << 16) | (uint32_t)pf;
+							if (ng == 0) gp.x = qg;
+							else if (ng == 1) gp.y = qg;
+							else if (ng == 2) gp.z = qg;
+							else if (ng == 3) gp.w = qg;
+							ng = min(ng + 1, 5);
+						}
+						const int hi = min(pl + t_max, kBlockDec);
+						cov += max(hi - max(pf, cend), 0);
+						cend = hi;
+						l = pl;
+					}
+				}
+			}
+		}
+		const bool has = f >= 0;
+		e.x = has ? ((uint32_t)f | ((uint32_t)l << 16)) : 0u;
+		e.y = (uint32_t)cov | ((uint32_t)ng << 16) | (has ? 0x80000000u : 0u);
+	};
+	// the items of one block from its own triggers (a block with more gaps than its table entry holds): count, or write
+	auto gen_items = [&](size_t gb, int theta_b, uint32_t base, uint32_t *dst) -> int {
+		int cnt = 0, first = -1, prev = -1;
+		auto trig = [&](int t) {
+			if (first < 0) {
+				first = t;
+				if (dst) dst[cnt] = base + (uint32_t)t;
+				cnt++;
+			} else if (t - prev >= t_min) {
+				if (dst) {
+					dst[cnt] = kWalkSet | (base + (uint32_t)prev);
+					dst[cnt + 1] = base + (uint32_t)t;
+				}
+				cnt += 2;
+			}
+			prev = t;
+		};
+		const uint32_t nj = p.tiles[gb].n_trig;
+		if (nj <= (uint32_t)kMaxEvt) {
+			const uint32_t *ev = p.events + gb * kMaxEvt;
+			for (uint32_t q = 0; q < nj; q++) {
+				const uint32_t e = ev[q];
+				if ((int)(e & 0xffff) > theta_b) trig((int)(e >> 16));
+			}
+		} else {
+			const TileDesc &td = p.tiles[gb];
+			const uint32_t *d = p.dec + gb * kBlockDec;
+			for (int sgi = 0; sgi < (int)td.n_seg; sgi++) {
+				const int a = td.seg_start[sgi], b = a + td.seg_len[sgi];
+				for (int m = a; m < b; m++)
+					if (pwr_of(d[m]) > theta_b) trig(m);
+			}
+		}
+		if (prev != first) {
+			if (dst) dst[cnt] = kWalkSet | (base + (uint32_t)prev);
+			cnt++;
+		}
+		return cnt;
+	};
+
+	bool stop = false;
+	int sc = b0;
+	uint4 row[kWalkNT / 2];
+	fetch_row(sc, row);
+	stage_row(row);
+	int pos = b0;
+	while (pos < t_end && !stop) {
+		fetch_row(sc + kWalkCta, row);   // in flight while this super-chunk is walked
+		const int jend = min(kWalkCta, t_end - sc);
+		const size_t g = (size_t)job.dec_off + sc + tid;
+		uint32_t my_fl = 0, my_cv = 0;
+		int my_k = 0, my_used = 0;
+		bool mine_acc = false, my_own = false;   // my_own: the entry came from eval_block, its gaps are in my_gaps
+		uint4 my_gaps = make_uint4(0, 0, 0, 0);
+#ifdef TFR_WALK_PROFILE
+		wp_a = clock64();
+#endif
+		// ---- A, B
+		while (pos < sc + jend) {
+			const int k = (thresh - tab_base) >> 1;
+			if (mode == 1 && thresh < thresh_lo) {   // the front-end's bound does not cover this block: hand back
+				stop = true;
+				break;
+			}
+			const bool in_tab = (unsigned)k < (unsigned)kWalkNT;
+			const int j0 = pos - sc;
+			const bool active = tid >= j0 && tid < jend;
+			uint2 e = make_uint2(0u, 0u);
+			uint4 e_gaps = make_uint4(0, 0, 0, 0);
+			const int kq = min(max(k, 0), kWalkNT - 1);
+			bool own = false;
+			if (active) {
+				e = s_tab[tid][kq];
+				// off the table: the nearest column holds if its entry is proven constant out to here (walk_table_kernel)
+				if (k < 0) {
+					own = !((e.y >> 30) & 1u);
+				} else if (!in_tab) {
+					const int run = (int)((e.y >> 26) & 15u);
+					own = !(run > 0 && thresh <= tab_base + 2 * (kWalkNT - 1) + kWalkLadder[max(run - 1, 0)]);
+				}
+			}
+			if (!in_tab && p.walk_dbg == 32 && active && !own && p.tiles[g].n_trig <= (uint32_t)kMaxEvt) {
+				uint2 e2;
+				uint4 g2;
+				eval_block(g, thresh, e2, g2);
+				if (e2.x != e.x || ((e2.y ^ e.y) & 0x8007ffffu))
+					printf("MISMATCH stream %d block %d thresh %d base %d k %d n %u tab %08x %08x eval %08x %08x\n", stream, sc + tid, thresh,
+					       tab_base, k, p.tiles[g].n_trig, e.x, e.y, e2.x, e2.y);
+			}
+			if (!in_tab) {
+				// ... else the block is evaluated here: a list by its thread, a burst block by the warp
+				const bool burst = own && p.tiles[g].n_trig > (uint32_t)kMaxEvt;
+				if (own && !burst) eval_block(g, thresh, e, e_gaps);
+				unsigned bm = __ballot_sync(0xffffffffu, burst);
+				while (bm) {
+					const int jb = __ffs(bm) - 1;
+					bm &= bm - 1;
+					uint2 eb;
+					uint4 gb4;
+					eval_burst_warp((size_t)job.dec_off + sc + 32 * warp + jb, thresh, eb, gb4);
+					if (lane == jb) {
+						e = eb;
+						e_gaps = gb4;
+					}
+				}
+#ifdef TFR_WALK_PROFILE
+				if (own) atomicAdd(&s_ctl[6], 1);
+				if (burst) atomicAdd(&s_ctl[7], 1);
+#endif
+			}
+			const bool has = (e.y >> 31) != 0;
+			const int f = (int)(e.x & 0xffff), l = (int)(e.x >> 16);
+			const int out = has ? max(l + t_max - kBlockDec, 0) : 0;
+			s_out[tid] = out;
+			__syncthreads();
+			const int c_in = (tid == j0) ? c : s_out[max(tid - 1, 0)];
+			const int trig = (int)(e.y & 0xffff) + (has ? min(c_in, f) : c_in);
+			s_t[tid] = trig;
+			__syncthreads();
+			const int used = thresh;
+			if (warp == 0) {
+				// the averages as if the threshold stayed (two instructions per block on the chain, nothing else) ...
+				// (eight counts are loaded, eight steps taken, eight averages stored: a load behind the store of the step
+				// before would sit on the chain)
+				// ... in stretches of 32 blocks; the first decision (every 4th block, fm_demod.cpp:58-73) that moves the
+				// threshold ends the pass
+				int a = avg;
+				int first = kWalkCta;
+				for (int seg = j0; seg < jend && first == kWalkCta; seg += 32) {
+					const int send = min(seg + 32, jend);
+					int tn[8];
+#pragma unroll
+					for (int q = 0; q < 8; q++) tn[q] = s_t[min(seg + q, kWalkCta - 1)];
+					for (int j = seg; j < send; j += 8) {
+						int tc[8], r[8];
+#pragma unroll
+						for (int q = 0; q < 8; q++) tc[q] = tn[q];
+#pragma unroll
+						for (int q = 0; q < 8; q++) tn[q] = s_t[min(j + 8 + q, kWalkCta - 1)];   // the next eight, off the chain
+#pragma unroll
+						for (int q = 0; q < 8; q++) {
+							if (j + q < send) a = (int)((uint32_t)(31 * a + tc[q]) >> 5);   // (both >= 0: the reference's signed /32)
+							r[q] = a;
+						}
+#pragma unroll
+						for (int q = 0; q < 8; q++)
+							if (j + q < send) s_avg[j + q] = r[q];
+					}
+					__syncwarp();
+					if (mode == 1) {
+						const int j = seg + lane;
+						bool moves = false;
+						if (j < send && ((runs + (j - j0 + 1)) & 3) == 0) {
+							const int aj = s_avg[j];
+							moves = aj >= kIdxPerBlock / 32 || (aj <= kIdxPerBlock / 64 && thresh > 50);
+						}
+						const unsigned mv = __ballot_sync(0xffffffffu, moves);
+						if (mv) first = seg + __ffs(mv) - 1;
+					}
+				}
+				int acc_end = jend;
+				if (first < kWalkCta) {
+					acc_end = first + 1;
+					thresh += (s_avg[first] >= kIdxPerBlock / 32) ? 2 : -2;
+				}
+				if (lane == 0) {
+					s_ctl[0] = thresh;
+					s_ctl[1] = s_avg[acc_end - 1];
+					s_ctl[2] = runs + (acc_end - j0);
+					s_ctl[3] = acc_end;
+				}
+			}
+			__syncthreads();
+			thresh = s_ctl[0];
+			avg = s_ctl[1];
+			runs = s_ctl[2];
+			const int acc_end = s_ctl[3];
+			if (tid >= j0 && tid < acc_end) {
+				BlockTrace bt = { used, trig, s_avg[tid] };
+				p.trace[g] = bt;
+				act += (unsigned long long)trig;
+				mine_acc = true;
+				my_fl = e.x;
+				my_cv = e.y;
+				my_k = kq;
+				my_used = used;
+				my_own = own;
+				my_gaps = e_gaps;
+				const int ng_e = (int)((e.y >> 16) & 7u);
+				if (has && !own && ng_e > 0 && ng_e <= 4) my_gaps = gap_tab[g * kWalkNT + kq];   // (in flight until the items are made)
+			}
+			c = s_out[acc_end - 1];
+			pos = sc + acc_end;
+			__syncthreads();   // (the next pass writes s_out, s_t and s_ctl again)
+#ifdef TFR_WALK_PROFILE
+			wp_pass++;
+#endif
+		}
+#ifdef TFR_WALK_PROFILE
+		wp_ab += clock64() - wp_a; wp_a = clock64();
+#endif
+		// ---- C: the accepted blocks' items, in order
+		const bool acc_has = mine_acc && (my_cv >> 31);
+		const int ngl = acc_has ? (int)((my_cv >> 16) & 7u) : 0;
+		const uint32_t f_l = my_fl & 0xffff, l_l = my_fl >> 16;
+		const uint32_t base = (uint32_t)(sc + tid) * kBlockDec;
+		int cnt = 0;
+		if (acc_has) cnt = (ngl <= 4) ? 1 + 2 * ngl + (l_l != f_l ? 1 : 0) : gen_items(g, my_used, base, nullptr);
+		int incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int o = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) incl += o;
+		}
+		if (lane == 31) s_scan[warp] = incl;
+		__syncthreads();
+		int total = 0;
+#pragma unroll
+		for (int w = 0; w < kWalkCta / 32; w++) {
+			const int sw = s_scan[w];
+			if (w < warp) incl += sw;
+			total += sw;
+		}
+		const uint4 gaps = my_gaps;
+		int done = 0;
+		while (done < total) {   // (more than once only if the items of 256 blocks do not fit s_items)
+			if (tid == 0) s_ctl[4] = done;
+			__syncthreads();
+			const bool in = cnt > 0 && incl - cnt >= done && incl <= done + kWalkItems;
+			if (in) {
+				atomicMax(&s_ctl[4], incl);
+				uint32_t *dst = s_items + (incl - cnt - done);
+				if (ngl <= 4) {
+					int at = 0;
+					dst[at++] = base + f_l;
+					if (ngl > 0) { dst[at++] = kWalkSet | (base + (gaps.x >> 16)); dst[at++] = base + (gaps.x & 0xffff); }
+					if (ngl > 1) { dst[at++] = kWalkSet | (base + (gaps.y >> 16)); dst[at++] = base + (gaps.y & 0xffff); }
+					if (ngl > 2) { dst[at++] = kWalkSet | (base + (gaps.z >> 16)); dst[at++] = base + (gaps.z & 0xffff); }
+					if (ngl > 3) { dst[at++] = kWalkSet | (base + (gaps.w >> 16)); dst[at++] = base + (gaps.w & 0xffff); }
+					if (l_l != f_l) dst[at++] = kWalkSet | (base + l_l);
+				} else {
+					gen_items(g, my_used, base, dst);
+#ifdef TFR_WALK_PROFILE
+					wp_ncomplex++;
+#endif
+				}
+			}
+			__syncthreads();
+			const int n = s_ctl[4] - done;
+			if (n == 0) break;   // (cannot happen: a block holds at most 48 items)
+#ifdef TFR_WALK_PROFILE
+			wp_c += clock64() - wp_a; wp_a = clock64();
+			wp_nitems += n;
+#endif
+			// ---- D: the demodulators over the warps
+			for (int dd = warp; dd < nd; dd += kWalkCta / 32) {
+				const int T_w = cfg.d[dd].timeout;
+				WinEntry *w_wl = p.wins + job.win_off + (size_t)dd * job.win_cap;
+				const WalkDem wdm = s_dem[dd];
+				uint32_t w_n = wdm.n_win, w_cum = wdm.cum, w_open = wdm.open, w_os = wdm.open_start;
+				long long lt = last_trig;
+				for (int cur = 0; cur < n; cur += 32) {
+					const int cntb = min(32, n - cur);
+					const bool valid = lane < cntb;
+					const uint32_t v = valid ? s_items[cur + lane] : 0u;
+					const bool is_t = valid && !(v & kWalkSet);
+					const uint32_t t = v & ~kWalkSet;
+					const uint32_t pv = __shfl_up_sync(0xffffffffu, t, 1);
+					const long long prev = (lane == 0) ? lt : (long long)pv;
+					const unsigned tm = __ballot_sync(0xffffffffu, is_t);
+					unsigned m = __ballot_sync(0xffffffffu, is_t && ((long long)t - prev >= (long long)T_w));
+					if (!w_open) m |= tm & (0u - tm);
+					if (m) {
+						const unsigned pm = m & ((1u << lane) - 1u);
+						const bool opens = (m >> lane) & 1u;
+						const uint32_t t_before = __shfl_sync(0xffffffffu, t, pm ? 31 - __clz(pm) : 0);
+						const bool had_open = pm ? true : (w_open != 0);
+						const uint32_t os_prev = pm ? t_before : w_os;
+						const uint32_t end = (uint32_t)(prev + (long long)T_w - 1);   // of the window this item's opening closes
+						uint32_t len = (opens && had_open) ? end - os_prev + 1u : 0u;
+#pragma unroll
+						for (int q = 1; q < 32; q <<= 1) {
+							const uint32_t o = __shfl_up_sync(0xffffffffu, len, q);
+							if (lane >= q) len += o;
+						}
+						// a window opened here is closed by the next opening of the batch, if there is one (every lane writes
+						// its own entry whole; only the batch's first opening touches an entry that was there before)
+						const unsigned nm = m & ~((2u << lane) - 1u);
+						const uint32_t end_next = __shfl_sync(0xffffffffu, end, nm ? __ffs(nm) - 1 : 0);
+						if (opens) {
+							const uint32_t idx = w_n + (uint32_t)__popc(pm);
+							if (!pm && had_open && idx - 1u < job.win_cap) w_wl[idx - 1u].end = end;
+							if (idx < job.win_cap) {
+								WinEntry we = { t, nm ? end_next : 0xffffffffu, w_cum + len, 0u };
+								w_wl[idx] = we;
+							} else {
+								p.counters->overflow = 1;
+							}
+						}
+						const int last_o = 31 - __clz(m);
+						w_cum += __shfl_sync(0xffffffffu, len, last_o);
+						const uint32_t os_new = __shfl_sync(0xffffffffu, t, last_o);
+						const uint32_t n_new = w_n + (uint32_t)__popc(m);
+						w_open = 1;
+						if (n_new <= job.win_cap) {
+							w_n = n_new;
+							w_os = os_new;
+						} else {
+							w_n = job.win_cap;   // (the list is full: the call reports TFR_E_OVERFLOW, what follows is truncated)
+						}
+					}
+					lt = (long long)__shfl_sync(0xffffffffu, t, cntb - 1);
+				}
+				if (lane == 0) {
+					WalkDem o = { w_n, w_cum, w_open, w_os };
+					s_dem[dd] = o;
+				}
+			}
+			if (n) last_trig = (long long)(s_items[n - 1] & ~kWalkSet);
+			done += n;
+			__syncthreads();   // (the next round writes s_items and s_ctl again)
+#ifdef TFR_WALK_PROFILE
+			wp_d += clock64() - wp_a; wp_a = clock64();
+#endif
+		}
+#ifdef TFR_WALK_PROFILE
+		wp_c += clock64() - wp_a;
+#endif
+		if (stop) {
+			t_stop = pos;
+			break;
+		}
+		sc += kWalkCta;
+		stage_row(row);
+	}
+#ifdef TFR_WALK_PROFILE
+	if (tid == 0 && (stream == 0 || clock64() - wp_t0 > 150000))
+		printf("walk_cta[%d]: blocks %d total %lld A+B %lld C %lld D %lld | passes %d items %d complex(t0) %d evals %d (burst blocks %d)\n", stream,
+		       t_end - b0, clock64() - wp_t0, wp_ab, wp_c, wp_d, wp_pass, wp_nitems, wp_ncomplex, s_ctl[6], s_ctl[7]);
+#endif
+
+	// ---- the state goes back to thread d; from here on as in thresh2_kernel
+	__syncthreads();
+	if (tid < nd) {
+		const WalkDem wdm = s_dem[tid];
+		n_win = wdm.n_win;
+		cum = wdm.cum;
+		open = wdm.open;
+		open_start = wdm.open_start;
+	}
+	const bool finished = (t_stop == (int)job.n_blocks);
+	if (finished && tid < nd) {
+		uint32_t cont = 0;
+		if (open) {
+			const long long end = last_trig + T_d - 1;   // >= 0 because an open window means last_trig > -T_d
+			wl[n_win - 1].end = (uint32_t)end;
+			cum += (uint32_t)end - open_start + 1;
+			cont = (end >= (long long)call_len) ? 1u : 0u;   // still running when the data ends: the next call resumes it
+		}
+		st->win_cont[tid] = cont;
+		p.wincnt[stream].n[tid] = n_win;
+		p.wincnt[stream].cum[tid] = cum;
+		uint32_t W = 0;   // the leading windows that need the previous call's final state (see thresh2_kernel)
+		if (n_win) {
+			W = 1;
+			if (cfg.d[tid].kind != K_TFA1) {
+				const uint32_t want = ((uint32_t)TFR_WARM_X4 * (uint32_t)T_d) / 4u;
+				const uint32_t c1 = (n_win > 1) ? wl[1].cum : 0u;
+				while (W < n_win && !(wl[W].cum - c1 >= want && chain_head(wl, W, T_d))) W++;
+			}
+		}
+		p.partcnt[(size_t)kLateRow * p.n_streams + stream].n[tid] = W;
+	}
+	if (tid < nd) {
+		st->win_n[tid] = n_win;
+		st->win_cum[tid] = cum;
+		st->win_open[tid] = open;
+		if (part) {
+			uint32_t W = n_win;
+			if (!finished) {
+				const uint32_t bound = (uint32_t)t_stop * (uint32_t)kBlockDec;
+				while (W > 0 && wl[W - 1].end >= bound) W--;
+				if (cfg.d[tid].kind != K_TFA1) {
+					if (W == n_win && W > 0 && bound - wl[W - 1].end <= (uint32_t)T_d + 1u) W--;
+					while (W > 0 && W < n_win && !chain_head(wl, W, T_d)) W--;
+				}
+			}
+			part->n[tid] = W;
+		}
+	}
+	for (int o = 16; o; o >>= 1) act += __shfl_xor_sync(0xffffffffu, act, o);
+	if (lane == 0 && act) atomicAdd(&p.counters->active_samples, act);
+	if (tid == 0) {
+		st->thresh = thresh;
+		st->triggered_avg = avg;
+		st->runs = runs;
+		st->any_timeout = c;
+		st->call_last_trig = (int32_t)max(last_trig, (long long)INT32_MIN / 2);
+		if (finished) {
+			const long long age = (long long)call_len - last_trig;
+			st->trig_age = (int32_t)min(age, (long long)INT32_MAX / 2);
+		}
+		st->t2_done = (uint32_t)t_stop;
+		if (p.progress) p.progress[stream] = (uint32_t)t_stop;
 	}
 }
 
@@ -2696,7 +3338,13 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 {
 	if (p.walk_tab && p.n_tiles > 0) walk_table_kernel<<<dim3((p.n_tiles + 3) / 4, p.n_streams), 128, 0, s>>>(p);
-	thresh2_kernel<<<p.n_streams, 32, 0, s>>>(p);
+	if (p.walk_tab && p.walk_gap) {
+		static const int ct_env = getenv("TFR_WALK_CT") ? atoi(getenv("TFR_WALK_CT")) : 0;   // tests: either variant on any input
+		const bool wide = ct_env ? ct_env >= 256 : p.n_streams <= 4;
+		if (wide) walk_cta_kernel<256><<<p.n_streams, 256, 0, s>>>(p);
+		else walk_cta_kernel<64><<<p.n_streams, 64, 0, s>>>(p);
+	}
+	else thresh2_kernel<<<p.n_streams, 32, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_devfm(const BackParams &p, cudaStream_t s)

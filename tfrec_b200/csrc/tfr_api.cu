@@ -113,7 +113,8 @@ struct tfr_handle {
 		uint32_t *d_dec = nullptr;
 		BlockTrace *d_trace = nullptr;
 		uint32_t *d_events = nullptr;
-		uint32_t *d_walk_tab = nullptr;          // [cap_blocks][kWalkNT][4]: walk_table_kernel -> thresh2_kernel
+		uint32_t *d_walk_tab = nullptr;          // [cap_blocks][kWalkNT][4]: walk_table_kernel -> thresh2_kernel / walk_cta_kernel
+		uint32_t *d_walk_gap = nullptr;          // [cap_blocks][kWalkNT][4]: ... -> walk_cta_kernel
 		int32_t *d_walk_base = nullptr;          // [n_streams]
 		int32_t *d_devfm = nullptr;
 		int32_t *d_ld = nullptr;                 // filter chains: (int)y per fm demodulator, direct mapped like d_devfm
@@ -148,6 +149,7 @@ struct tfr_handle {
 	cudaStream_t part_stream[kMaxParts] = { nullptr }, part_long[kMaxParts] = { nullptr };
 	cudaEvent_t part_fm[kMaxParts] = { nullptr }, part_done[kMaxParts] = { nullptr }, part_ldone[kMaxParts] = { nullptr };
 	int t_min = 0x7fffffff;            // shortest demodulator timeout
+	bool walk_cta = true;              // ... by walk_cta_kernel, a CTA per stream (TFR_WALK=warp: by thresh2_kernel, a warp per stream)
 	bool walk_table = true;            // threshold walk from the per-block table of walk_table_kernel (TFR_WALK_TAB=0: from the event lists)
 	size_t min_chunk = 8192;           // blocks per front-end chunk launch at least (TFR_MIN_CHUNK: tests exercise chunks and parts on small inputs)
 	bool use_screen = false;           // screening front-end (frontend_screen.cu): the tensor core proves which samples cannot trigger,
@@ -304,7 +306,7 @@ extern "C" __attribute__((visibility("default"))) void tfr_destroy(tfr_handle *h
 		cudaFree(sl.d_work_ctr); cudaFree(sl.d_hist_copy); cudaFree(sl.d_fin); cudaFree(sl.d_walk_base);
 		if (sl.early_done) cudaEventDestroy(sl.early_done);
 		if (sl.raw_done) cudaEventDestroy(sl.raw_done);
-		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_walk_tab);
+		cudaFree(sl.d_jobs); cudaFree(sl.d_tmaps); cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_walk_tab); cudaFree(sl.d_walk_gap);
 		cudaFree(sl.d_devfm); cudaFree(sl.d_wins); cudaFree(sl.d_recs); cudaFree(sl.d_wincnt); cudaFree(sl.d_partcnt);
 		cudaFree(sl.d_ld); cudaFree(sl.d_biq);
 		for (cudaEvent_t e : { sl.front_done, sl.back_done, sl.fe0, sl.fe1 })
@@ -407,6 +409,7 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 			CUH(cudaStreamCreateWithPriority(&h->part_long[k], cudaStreamNonBlocking, prio_hi));
 		}
 		if (const char *wt = getenv("TFR_WALK_TAB")) h->walk_table = atoi(wt) != 0;
+		if (const char *wk = getenv("TFR_WALK")) h->walk_cta = strcmp(wk, "warp") != 0;
 		for (int k = 0; k < h->dcfg.n_demods; k++) h->t_min = std::min(h->t_min, h->dcfg.d[k].timeout);
 		if (const char *mc = getenv("TFR_MIN_CHUNK")) h->min_chunk = (size_t)std::max(1, atoi(mc));
 		if (const char *be = getenv("TFR_BE")) h->biq_chains = strcmp(be, "chains") == 0;
@@ -510,14 +513,15 @@ static int ensure_blocks(tfr_handle *h, tfr_handle::Slot &sl, size_t blocks, siz
 	if (blocks > sl.cap_blocks) {
 		int rc = sync_all(h);
 		if (rc) return rc;
-		cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_walk_tab); cudaFree(sl.d_devfm); cudaFree(sl.d_ld);
-		sl.d_tiles = nullptr; sl.d_dec = nullptr; sl.d_trace = nullptr; sl.d_events = nullptr; sl.d_walk_tab = nullptr; sl.d_devfm = nullptr; sl.d_ld = nullptr;
+		cudaFree(sl.d_tiles); cudaFree(sl.d_dec); cudaFree(sl.d_trace); cudaFree(sl.d_events); cudaFree(sl.d_walk_tab); cudaFree(sl.d_walk_gap); cudaFree(sl.d_devfm); cudaFree(sl.d_ld);
+		sl.d_tiles = nullptr; sl.d_dec = nullptr; sl.d_trace = nullptr; sl.d_events = nullptr; sl.d_walk_tab = nullptr; sl.d_walk_gap = nullptr; sl.d_devfm = nullptr; sl.d_ld = nullptr;
 		sl.cap_blocks = 0;
 		cudaError_t e = cudaMalloc(&sl.d_tiles, blocks * sizeof(TileDesc));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_dec, blocks * (size_t)kBlockDec * sizeof(uint32_t));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_trace, blocks * sizeof(BlockTrace));
 		if (e == cudaSuccess) e = cudaMalloc(&sl.d_events, blocks * (size_t)kMaxEvt * sizeof(uint32_t));
 		if (e == cudaSuccess && h->walk_table) e = cudaMalloc(&sl.d_walk_tab, blocks * (size_t)kWalkNT * 4 * sizeof(uint32_t));
+		if (e == cudaSuccess && h->walk_table && h->walk_cta) e = cudaMalloc(&sl.d_walk_gap, blocks * (size_t)kWalkNT * 4 * sizeof(uint32_t));
 		if (e == cudaSuccess && h->has_fm) e = cudaMalloc(&sl.d_devfm, blocks * (size_t)kBlockDec * sizeof(int32_t));
 		if (e == cudaSuccess && h->has_fm && h->biq_chains) e = cudaMalloc(&sl.d_ld, (size_t)h->n_fm * blocks * (size_t)kBlockDec * sizeof(int32_t));
 		if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? TFR_E_NOMEM : TFR_E_CUDA, std::string("work buffers: ") + cudaGetErrorString(e)); }
@@ -899,9 +903,15 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			// (table items carry positions in 31 bits; a trigger group of the burst scan must be shorter than any timeout)
 			const bool use_tab = sl.d_walk_tab && max_blocks < (1u << 18) && h->t_min > 32;
 			bp.walk_tab = use_tab ? sl.d_walk_tab : nullptr;
+			bp.walk_gap = use_tab ? sl.d_walk_gap : nullptr;
 			bp.walk_base = sl.d_walk_base;
+			{
+				static const int dbg = getenv("TFR_WALK_DBG") ? atoi(getenv("TFR_WALK_DBG")) : 0;
+				bp.walk_dbg = dbg;
+			}
 			CU(launch_thresh2(bp, h->stream_walk));
 			bp.walk_tab = nullptr;
+			bp.walk_gap = nullptr;
 			bp.part_idx = -1;
 			h->stats.kernel_launches += use_tab ? 3 : 2;
 			if (part_end) {
