@@ -379,8 +379,8 @@ def test_threshold_walk_variants(tb, hot_fixture, monkeypatch, walk):
     (walk_cta_kernel), by a warp per stream (thresh2_kernel), and from the event lists: the same block trace, thresholds,
     windows (hence frames and records) as the oracle, over several launches per call (TFR_MIN_CHUNK), two calls, signals
     that push the threshold out of the table's range, and a start-up transient (noise far below the start threshold)."""
-    env = {"cta64": {"TFR_WALK_CT": "64"}, "cta256": {"TFR_WALK_CT": "256"}, "warp": {"TFR_WALK": "warp"},
-           "lists": {"TFR_WALK_TAB": "0"}}[walk]
+    env = {"cta64": {"TFR_WALK_TAB": "1", "TFR_WALK_CT": "64"}, "cta256": {"TFR_WALK_TAB": "1", "TFR_WALK_CT": "256"},
+           "warp": {"TFR_WALK_TAB": "1", "TFR_WALK": "warp"}, "lists": {"TFR_WALK_TAB": "0"}}[walk]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     monkeypatch.setenv("TFR_MIN_CHUNK", "24")

@@ -408,6 +408,10 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 			CUH(cudaStreamCreateWithFlags(&h->part_stream[k], cudaStreamNonBlocking));
 			CUH(cudaStreamCreateWithPriority(&h->part_long[k], cudaStreamNonBlocking, prio_hi));
 		}
+		// The table walk pays where a stream's serial chain is the long pole: few, long streams.  With many streams the
+		// list walk's warps hide behind the front-end anyway and the table kernel takes SM time from it (32 streams x 128 MiB
+		// on B200: the same step either way, front-end 0.85 -> 0.90 ms): from 17 streams on the lists are walked.
+		h->walk_table = cfg->n_streams <= 16;
 		if (const char *wt = getenv("TFR_WALK_TAB")) h->walk_table = atoi(wt) != 0;
 		if (const char *wk = getenv("TFR_WALK")) h->walk_cta = strcmp(wk, "warp") != 0;
 		for (int k = 0; k < h->dcfg.n_demods; k++) h->t_min = std::min(h->t_min, h->dcfg.d[k].timeout);
