@@ -3266,6 +3266,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(const BackParams
 #ifdef TFR_VER_PROFILE
 	atomicMax(&g_verprof[5], (unsigned long long)vp_mine);
 	atomicMax(&g_verprof[6], (unsigned long long)vp_wins);
+	if (tid == 0 && gid < 5)
+		printf("verify[%d]: windows %u rounds %u total %lld flags %lld starts %lld repair %lld | thread 0: cheap %u full %u sr %u\n", gid, n_win, rounds,
+		       clock64() - vp_t0, vp_flags, vp_starts, vp_repair, n_cheap, n_full, n_sr);
 	if (tid == 0) {
 		atomicMax(&g_verprof[0], (unsigned long long)vp_flags); atomicMax(&g_verprof[1], (unsigned long long)vp_starts);
 		atomicMax(&g_verprof[2], (unsigned long long)vp_repair); atomicMax(&g_verprof[3], (unsigned long long)rounds);
@@ -3339,8 +3342,7 @@ cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 {
 	if (p.walk_tab && p.n_tiles > 0) walk_table_kernel<<<dim3((p.n_tiles + 3) / 4, p.n_streams), 128, 0, s>>>(p);
 	if (p.walk_tab && p.walk_gap) {
-		static const int ct_env = getenv("TFR_WALK_CT") ? atoi(getenv("TFR_WALK_CT")) : 0;   // tests: either variant on any input
-		const bool wide = ct_env ? ct_env >= 256 : p.n_streams <= 4;
+		const bool wide = p.walk_ct ? p.walk_ct >= 256 : p.n_streams <= 4;
 		if (wide) walk_cta_kernel<256><<<p.n_streams, 256, 0, s>>>(p);
 		else walk_cta_kernel<64><<<p.n_streams, 64, 0, s>>>(p);
 	}

@@ -149,6 +149,7 @@ struct tfr_handle {
 	cudaStream_t part_stream[kMaxParts] = { nullptr }, part_long[kMaxParts] = { nullptr };
 	cudaEvent_t part_fm[kMaxParts] = { nullptr }, part_done[kMaxParts] = { nullptr }, part_ldone[kMaxParts] = { nullptr };
 	int t_min = 0x7fffffff;            // shortest demodulator timeout
+	int walk_ct = 0, walk_dbg = 0;     // TFR_WALK_CT (CTA size of walk_cta_kernel, 0 = by the number of streams), TFR_WALK_DBG (experiments)
 	bool walk_cta = true;              // ... by walk_cta_kernel, a CTA per stream (TFR_WALK=warp: by thresh2_kernel, a warp per stream)
 	bool walk_table = true;            // threshold walk from the per-block table of walk_table_kernel (TFR_WALK_TAB=0: from the event lists)
 	size_t min_chunk = 8192;           // blocks per front-end chunk launch at least (TFR_MIN_CHUNK: tests exercise chunks and parts on small inputs)
@@ -414,6 +415,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_create(const tfr_confi
 		h->walk_table = cfg->n_streams <= 16;
 		if (const char *wt = getenv("TFR_WALK_TAB")) h->walk_table = atoi(wt) != 0;
 		if (const char *wk = getenv("TFR_WALK")) h->walk_cta = strcmp(wk, "warp") != 0;
+		if (const char *wc = getenv("TFR_WALK_CT")) h->walk_ct = atoi(wc);
+		if (const char *wd = getenv("TFR_WALK_DBG")) h->walk_dbg = atoi(wd);
 		for (int k = 0; k < h->dcfg.n_demods; k++) h->t_min = std::min(h->t_min, h->dcfg.d[k].timeout);
 		if (const char *mc = getenv("TFR_MIN_CHUNK")) h->min_chunk = (size_t)std::max(1, atoi(mc));
 		if (const char *be = getenv("TFR_BE")) h->biq_chains = strcmp(be, "chains") == 0;
@@ -909,10 +912,8 @@ extern "C" __attribute__((visibility("default"))) int tfr_process(tfr_handle *h)
 			bp.walk_tab = use_tab ? sl.d_walk_tab : nullptr;
 			bp.walk_gap = use_tab ? sl.d_walk_gap : nullptr;
 			bp.walk_base = sl.d_walk_base;
-			{
-				static const int dbg = getenv("TFR_WALK_DBG") ? atoi(getenv("TFR_WALK_DBG")) : 0;
-				bp.walk_dbg = dbg;
-			}
+			bp.walk_dbg = h->walk_dbg;
+			bp.walk_ct = h->walk_ct;
 			CU(launch_thresh2(bp, h->stream_walk));
 			bp.walk_tab = nullptr;
 			bp.walk_gap = nullptr;

@@ -299,6 +299,7 @@ struct BackParams {
 	// threshold-walk table (walk_table_kernel, null: the walk evaluates the blocks' event lists itself)
 	uint32_t *walk_tab;      // [gtile][kWalkNT][4]: what the walk needs of a block under threshold walk_base + 2k
 	int32_t *walk_base;      // [stream]: threshold of column 0, written by the table kernel of the same launch
+	int walk_ct;             // walk_cta_kernel: threads per CTA, 0 = by the number of streams (TFR_WALK_CT)
 	int walk_dbg;            // experiments (TFR_WALK_DBG): 1 = no ladder above the table, 2 = no range below it either
 	uint32_t *walk_gap;      // non-null: the walk is walk_cta_kernel; walk_tab holds [gtile][kWalkNT][2] (the chain's part of an
 	                         // entry), walk_gap [gtile][kWalkNT][4] (up to four window-opening gaps)

@@ -31,6 +31,11 @@ def one_case(tb, rng, k):
     in_flight = bool(rng.integers(0, 2))
     os.environ["TFR_BE_SPLIT"] = split
     os.environ["TFR_MIN_CHUNK"] = str(int(rng.choice([1, 4, 8192])))
+    walk = str(rng.choice(["lists", "cta64", "cta256", "warp"]))   # the threshold walk's variants
+    for key in ("TFR_WALK_TAB", "TFR_WALK", "TFR_WALK_CT"):
+        os.environ.pop(key, None)
+    os.environ.update({"lists": {"TFR_WALK_TAB": "0"}, "cta64": {"TFR_WALK_TAB": "1", "TFR_WALK_CT": "64"},
+                       "cta256": {"TFR_WALK_TAB": "1", "TFR_WALK_CT": "256"}, "warp": {"TFR_WALK_TAB": "1", "TFR_WALK": "warp"}}[walk])
     streams = []
     for s_ in range(S):
         n_blocks = int(rng.integers(12, 72))
@@ -40,8 +45,8 @@ def one_case(tb, rng, k):
         iq, bursts = g.fixture_continuous(n_blocks * 32768, sensors[:int(rng.integers(1, 6))], period, seed=int(rng.integers(1, 1 << 30)),
                                           sigma=sigma, amp=amp)
         streams.append([iq, n_blocks, 0])
-    desc = "case %d: streams %d blocks %s sigma %.1f amp %d types %#x filter %d thresh %d split %s in_flight %d min_chunk %s" % (
-        k, S, [x[1] for x in streams], sigma, amp, types, filt, thresh, split, in_flight, os.environ["TFR_MIN_CHUNK"])
+    desc = "case %d: streams %d blocks %s sigma %.1f amp %d types %#x filter %d thresh %d split %s in_flight %d min_chunk %s walk %s" % (
+        k, S, [x[1] for x in streams], sigma, amp, types, filt, thresh, split, in_flight, os.environ["TFR_MIN_CHUNK"], walk)
     if os.environ.get("FUZZ_VERBOSE"):
         print("start", desc, flush=True)
     rx = tb.Receiver(types=types, filter=filt, thresh=thresh, n_streams=S)
