@@ -841,9 +841,9 @@ __global__ void __launch_bounds__(32, 1) thresh2_kernel(const BackParams p)
 // Where the walk cannot go on from the table (the front-end's bound fails, or the threshold left the table's range)
 // it stops like thresh2_kernel does; the next launch, or the host's epochs, carry on from there.
 // ------------------------------------------------------------------------------------------------
-// CT = threads = blocks of a super-chunk.  64 (two warps, <= 176 registers) fits beside two front-end CTAs on an SM, which
-// leave 11.7 k registers and 40 KB of shared memory - a walk that has to wait for a whole SM stalls the front-end launches
-// queued behind it; 256 is for calls of few streams, where the SMs are not the constraint and a demodulator gets a warp.
+// CT = threads = blocks of a super-chunk.  256 (a warp per demodulator in D) is what runs; 64 (two warps, <= 176 registers)
+// would fit beside the two front-end CTAs an SM holds, which leave 11.7 k registers and 40 KB of shared memory, but measured
+// slower at 8, 16 and 32 streams (TFR_WALK_CT=64 selects it; profiles/r2_walk_table.txt).
 struct WalkDem { uint32_t n_win, cum, open, open_start; };
 
 template <int CT>
@@ -3342,7 +3342,7 @@ cudaError_t launch_thresh2(const BackParams &p, cudaStream_t s)
 {
 	if (p.walk_tab && p.n_tiles > 0) walk_table_kernel<<<dim3((p.n_tiles + 3) / 4, p.n_streams), 128, 0, s>>>(p);
 	if (p.walk_tab && p.walk_gap) {
-		const bool wide = p.walk_ct ? p.walk_ct >= 256 : p.n_streams <= 4;
+		const bool wide = p.walk_ct ? p.walk_ct >= 256 : true;   // (64 measured slower at 8, 16 and 32 streams: profiles/r2_walk_table.txt)
 		if (wide) walk_cta_kernel<256><<<p.n_streams, 256, 0, s>>>(p);
 		else walk_cta_kernel<64><<<p.n_streams, 64, 0, s>>>(p);
 	}
