@@ -514,6 +514,32 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- extra: ONE stick (BASELINE.json configs[4], single long stream): the first streams of the workload back to back ----
+    if extra is not None:
+        try:
+            n_cat = max(1, min(S, (1 << 31) // nbytes))
+            one = torch.cat([bufs[s] for s in range(n_cat)])
+            rx1 = tb.Receiver(types=types_mask, thresh=args.thresh, n_streams=1, device=local, max_blocks_per_submit=int(one.numel()) // 65536)
+            ms1, k1, rec1 = 0.0, 3, 0
+            for i in range(2 + k1):
+                rx1.submit(0, one.data_ptr(), nbytes=int(one.numel()))
+                rx1.process()
+                rx1.sync()
+                if i >= 2:
+                    ms1 += rx1.stats()["last_total_ms"]
+                    rec1 = len(rx1.records())
+                rx1.clear()
+            rx1.close()
+            extra["one_stream"] = {"value": round(int(one.numel()) // 2 * k1 / (ms1 / 1e3) / 1e6, 2), "unit": "MSamples/s",
+                                   "ms_per_step": round(ms1 / k1, 4), "raw_samples": int(one.numel()) // 2, "records_per_step": rec1,
+                                   "steps": k1, "warmup": 2,
+                                   "note": "the first %d streams of the workload back to back as ONE stream on one handle (resident in HBM, "
+                                           "synchronised per step): the per-stream serial chains - threshold walk, verifier - decide; not parity-gated itself "
+                                           "(the gate above checks the decoders on the streams, tests/test_gpu_parity.py long single streams)" % n_cat}
+            del one
+        except Exception as e:   # an extra must not cost the headline line
+            extra["one_stream"] = {"error": str(e)[:200]}
+
     # ---- roofline of the front-end kernel -------------------------------------------------------
     peaks = {}
     try:
